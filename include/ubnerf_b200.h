@@ -1,0 +1,235 @@
+/*
+ * ubnerf_b200.h -- C ABI of libubnerf_b200.so: the B200-native (sm_100a) replacement for the native
+ * layer of sjtuytc/UnboundedNeRFPytorch's FourierGrid / DVGO rendering hot path.
+ *
+ * Boundary contract
+ *   - Plain C: raw DEVICE pointers + sizes + scalars; no torch / ATen types anywhere.
+ *   - Every entry point enqueues its kernels on `stream` (a cudaStream_t passed as void*; NULL = the
+ *     legacy default stream) of the CURRENT device and returns immediately (asynchronous), exactly
+ *     like the reference's launches, except that the reference always used the legacy default stream
+ *     of the current device (no CUDAGuard, no getCurrentCUDAStream -- SURVEY.md 2a).
+ *   - Return value: 0 on success, otherwise the cudaError_t of the failed launch / API call
+ *     (the reference never checks; ubn_last_error_string() gives the text).
+ *   - All float tensors are fp32, ids are int64, masks are 1-byte bools (torch.bool), all densely
+ *     packed ("contiguous") unless a stride argument says otherwise.  Inputs are borrowed for the
+ *     duration of the enqueued work; outputs are caller-allocated.
+ *   - Unlike the reference (outputs pre-filled with zeros_like/ones_like), every output element is
+ *     written by the kernels themselves, so callers may pass uninitialised (torch.empty) buffers.
+ *
+ * Each declaration cites the reference interface it replaces (paths relative to the reference repo).
+ * The Python binding a maintainer would add is in INTEGRATION.md; this repo's own binding is
+ * unboundednerfpytorch_b200/_cabi.py (ctypes).
+ */
+#ifndef UBNERF_B200_H_
+#define UBNERF_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+#define UBN_ABI_VERSION 1
+
+/* ---- library introspection ------------------------------------------------------------------ */
+int ubn_abi_version(void);
+/* Text of the last non-zero return value on this thread's device ("no error" if none). */
+const char* ubn_last_error_string(void);
+/* Number of kernel launches issued by this library since load / last reset (bench.py's gpu_launches). */
+int64_t ubn_launch_count(void);
+void ubn_reset_launch_count(void);
+
+/* ---- render_utils_cuda (FourierGrid/cuda/render_utils.cpp:170-184) --------------------------- */
+
+/* render_utils_cuda.infer_t_minmax            render_utils.cpp:50-57  / render_utils_kernel.cu:12-35,82-104 */
+int ubn_infer_t_minmax(const float* rays_o, const float* rays_d, const float* xyz_min, const float* xyz_max,
+                       float near, float far, int64_t n_rays, float* t_min, float* t_max, void* stream);
+
+/* render_utils_cuda.infer_n_samples           render_utils.cpp:59-64  / render_utils_kernel.cu:38-55,106-121 */
+int ubn_infer_n_samples(const float* rays_d, const float* t_min, const float* t_max, float stepdist,
+                        int64_t n_rays, int64_t* n_samples, void* stream);
+
+/* render_utils_cuda.infer_ray_start_dir       render_utils.cpp:66-71  / render_utils_kernel.cu:58-79,123-139 */
+int ubn_infer_ray_start_dir(const float* rays_o, const float* rays_d, const float* t_min, int64_t n_rays,
+                            float* rays_start, float* rays_dir, void* stream);
+
+/* render_utils_cuda.sample_pts_on_rays        render_utils.cpp:73-83  / render_utils_kernel.cu:144-242.
+ * The reference needs the ragged total on the host (N_steps.sum().item(), :212); the replacement
+ * splits the call so the caller owns that single D2H read:
+ *   ubn_sample_pts_count : fills t_min[n], t_max[n], n_steps[n] and offsets[n+1] (exclusive scan of
+ *                          n_steps; offsets[n] == total_len).  scan_scratch: >= n/1024+2 int64.
+ *   ubn_sample_pts_emit  : fills rays_pts[total,3], mask_outbbox[total], ray_id[total], step_id[total]. */
+int ubn_sample_pts_count(const float* rays_o, const float* rays_d, const float* xyz_min, const float* xyz_max,
+                         float near, float far, float stepdist, int64_t n_rays,
+                         float* t_min, float* t_max, int64_t* n_steps, int64_t* offsets,
+                         int64_t* scan_scratch, void* stream);
+int ubn_sample_pts_emit(const float* rays_o, const float* rays_d, const float* xyz_min, const float* xyz_max,
+                        const float* t_min, const int64_t* offsets, float stepdist, int64_t n_rays,
+                        int64_t total_len, float* rays_pts, uint8_t* mask_outbbox, int64_t* ray_id,
+                        int64_t* step_id, void* stream);
+
+/* render_utils_cuda.sample_ndc_pts_on_rays    render_utils.cpp:85-94  / render_utils_kernel.cu:245-293 */
+int ubn_sample_ndc_pts_on_rays(const float* rays_o, const float* rays_d, const float* xyz_min,
+                               const float* xyz_max, int64_t n_samples, int64_t n_rays,
+                               float* rays_pts, uint8_t* mask_outbbox, void* stream);
+
+/* render_utils_cuda.sample_bg_pts_on_rays     render_utils.cpp:96-103 / render_utils_kernel.cu:301-360 (no live caller) */
+int ubn_sample_bg_pts_on_rays(const float* rays_o, const float* rays_d, const float* t_max, float bg_preserve,
+                              int64_t n_samples, int64_t n_rays, float* rays_pts, void* stream);
+
+/* render_utils_cuda.maskcache_lookup          render_utils.cpp:105-117 / render_utils_kernel.cu:367-424 */
+int ubn_maskcache_lookup(const uint8_t* world, const float* xyz, const float* xyz2ijk_scale,
+                         const float* xyz2ijk_shift, int64_t sz_i, int64_t sz_j, int64_t sz_k,
+                         int64_t n_pts, uint8_t* out, void* stream);
+
+/* render_utils_cuda.raw2alpha / raw2alpha_nonuni          render_utils.cpp:119-131 / render_utils_kernel.cu:431-504
+ * interval_arr == NULL -> uniform `interval`; else per-point interval_arr[n_pts] (nonuni). */
+int ubn_raw2alpha(const float* density, float shift, float interval, const float* interval_arr,
+                  int64_t n_pts, float* exp_d, float* alpha, void* stream);
+
+/* render_utils_cuda.raw2alpha_backward / _nonuni_backward  render_utils.cpp:133-147 / render_utils_kernel.cu:507-574 */
+int ubn_raw2alpha_backward(const float* exp_d, const float* grad_back, float interval,
+                           const float* interval_arr, int64_t n_pts, float* grad, void* stream);
+
+/* render_utils_cuda.alpha2weight              render_utils.cpp:149-154 / render_utils_kernel.cu:577-651.
+ * ray_id must be sorted.  Writes weight[n_pts], T[n_pts], alphainv_last[n_rays], i_start/i_end[n_rays]. */
+int ubn_alpha2weight(const float* alpha, const int64_t* ray_id, int64_t n_pts, int64_t n_rays,
+                     float* weight, float* T, float* alphainv_last, int64_t* i_start, int64_t* i_end,
+                     void* stream);
+
+/* render_utils_cuda.alpha2weight_backward     render_utils.cpp:156-167 / render_utils_kernel.cu:654-707 */
+int ubn_alpha2weight_backward(const float* alpha, const float* weight, const float* T,
+                              const float* alphainv_last, const int64_t* i_start, const int64_t* i_end,
+                              int64_t n_pts, int64_t n_rays, const float* grad_weights,
+                              const float* grad_last, float* grad, void* stream);
+
+/* ---- total_variation_cuda (FourierGrid/cuda/total_variation.cpp:22-24) ----------------------- */
+/* total_variation_cuda.total_variation_add_grad   total_variation.cpp:13-20 / total_variation_kernel.cu:14-67.
+ * param/grad: logical [lead, sz_i, sz_j, sz_k, inner] row-major in MEMORY.  Reference layout
+ * [P,C,X,Y,Z] contiguous -> lead=P*C, inner=1;  channels-last storage [P,X,Y,Z,C] -> lead=P, inner=C.
+ * Keeps the reference's axis-weight quirk (i-axis uses wz; wx unused, :31-32) and the /6 (:45-47). */
+int ubn_total_variation_add_grad(const float* param, float* grad, float wx, float wy, float wz,
+                                 int64_t lead, int64_t sz_i, int64_t sz_j, int64_t sz_k, int64_t inner,
+                                 int dense_mode, void* stream);
+
+/* ---- adam_upd_cuda (FourierGrid/cuda/adam_upd.cpp:79-86) -------------------------------------- */
+/* adam_upd_cuda.adam_upd (mode 0) / masked_adam_upd (mode 1) / adam_upd_with_perlr (mode 2, needs perlr)
+ * adam_upd.cpp:31-77 / adam_upd_kernel.cu:9-132.  Elementwise over n floats (any common layout). */
+int ubn_adam_upd(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, const float* perlr,
+                 int64_t n, int step, float beta1, float beta2, float lr, float eps, int mode, void* stream);
+
+/* Fused training-step tail: total-variation add + (masked) Adam + grad zeroing in
+ * ONE sweep over the grid; same per-element arithmetic as ubn_total_variation_add_grad followed by
+ * ubn_adam_upd.  tv_mode: 0 = no TV, 1 = dense TV, 2 = sparse TV (only where grad != 0). */
+int ubn_tv_adam_fused(float* param, float* grad, float* exp_avg, float* exp_avg_sq,
+                      float wx, float wy, float wz, int64_t lead, int64_t sz_i, int64_t sz_j, int64_t sz_k,
+                      int64_t inner, int tv_mode, int step, float beta1, float beta2, float lr, float eps,
+                      int adam_mode, int zero_grad, void* stream);
+
+/* ---- ub360_utils_cuda (FourierGrid/cuda/ub360_utils.cpp:20-22) -------------------------------- */
+/* ub360_utils_cuda.cumdist_thres              ub360_utils.cpp:13-18 / ub360_utils_kernel.cu:13-47 */
+int ubn_cumdist_thres(const float* dist, float thres, int64_t n_rays, int64_t n_pts, uint8_t* mask,
+                      void* stream);
+
+/* ---- trilinear voxel-grid reads: DenseGrid.forward (grid.py:50-61) and FourierGrid.forward
+ *      (FourierGrid_grid.py:60-78) == torch F.grid_sample(bilinear, align_corners=True, zero padding)
+ *      + its adjoint (grid_sampler_3d_backward wrt the grid) -------------------------------------
+ * grid: P slabs x C channels x [X,Y,Z]; element (p,c,x,y,z) lives at
+ *       grid[p*stride_p + c*stride_c + ((x*Y + y)*Z + z)*stride_v].
+ *       reference layout [P,C,X,Y,Z] contiguous: stride_p=C*X*Y*Z, stride_c=X*Y*Z, stride_v=1
+ *       channels-last storage [P,X,Y,Z,C]      : stride_p=X*Y*Z*C, stride_c=1,     stride_v=C
+ * num_freqs: 0 -> DenseGrid / FourierGrid(use_nerf_pos=False) (P must be 1);
+ *            F>0 -> FourierGrid with P = 1+2F slabs sampled at gamma_n(ind_norm), averaged over slabs.
+ * out / grad_out: [n_pts, C] row-major.  xyz_min/xyz_max: HOST float[3]. */
+typedef struct UbnGridDesc {
+  int32_t P, C, X, Y, Z;
+  int32_t num_freqs;
+  int64_t stride_p, stride_c, stride_v;
+  float xyz_min[3];
+  float xyz_max[3];
+} UbnGridDesc;
+
+int ubn_grid_sample_fwd(const float* grid, const UbnGridDesc* desc, const float* xyz, int64_t n_pts,
+                        float* out, void* stream);
+int ubn_grid_sample_bwd(const float* grad_out, const UbnGridDesc* desc, const float* xyz, int64_t n_pts,
+                        float* grad_grid, void* stream);
+
+/* ---- fused ray march: sample_ray + density query + Raw2Alpha + Alphas2Weights + thresholds + k0 query
+ *      for FourierGridModel.forward (FourierGrid_model.py:509-621) and DirectContractedVoxGO.forward
+ *      (dcvgo.py:228-331) ------------------------------------------------------------------------ */
+typedef struct UbnMarchCfg {
+  /* scene normalisation (rays_o - center) / radius: FourierGrid_model.py:522, dcvgo.py:239 */
+  float scene_center[3];
+  float scene_radius[3];
+  /* contraction p/|p| * (contract_B - contract_A/|p|) when |p| > 1: B = 1+bg_len, A = bg_len, both
+   * narrowed to float by the host exactly as torch narrows the Python scalars
+   * (dcvgo.py:260, FourierGrid_model.py:541-547) */
+  float contract_B;
+  float contract_A;
+  int32_t contracted_norm;      /* 0 = inf-norm, 1 = l2-norm */
+  int32_t n_samples;            /* S = len(t) (host builds the t table exactly as the reference does) */
+  float act_shift;              /* Raw2Alpha shift */
+  float interval;               /* stepsize * voxel_size_ratio */
+  float fast_color_thres;       /* <= 0: no thresholding (dense output, M = N*S) */
+  int32_t use_cumdist;          /* dcvgo.py:286-294: keep inner points + cumdist_thres survivors */
+  float cumdist_thres;
+  int32_t use_maskcache;        /* dcvgo.py:297-302 */
+  int32_t mask_sz[3];
+  float mask_scale[3];
+  float mask_shift[3];
+} UbnMarchCfg;
+
+/* per-sample flag bits written by pass A */
+#define UBN_FLAG_QUERIED   1   /* density was queried (survived cumdist / mask-cache) */
+#define UBN_FLAG_LISTED    2   /* member of the Alphas2Weights list (alpha > thres) */
+#define UBN_FLAG_SCANNED   4   /* consumed by the transmittance scan before its early stop (i < i_end) */
+#define UBN_FLAG_KEEP      8   /* survives every mask: feature query + compacted output */
+#define UBN_FLAG_INNER    16   /* |p| <= 1 before contraction (inner_mask) */
+
+/* Pass A: per nominal sample (r,s): contracted point, masks, density, alpha, exact sequential
+ * transmittance scan (identical arithmetic to alpha2weight, early stop at T < 1e-3 included), weights,
+ * both thresholds.  Dense per-sample outputs [n_rays*S]: density, alpha, weight, T, flags.
+ * Per ray: alphainv_last[n_rays], n_keep[n_rays] (number of UBN_FLAG_KEEP samples). */
+int ubn_march_density_fwd(const float* rays_o, const float* rays_d, const float* t_table,
+                          const float* density_grid, const UbnGridDesc* density_desc,
+                          const uint8_t* mask_world, const UbnMarchCfg* cfg, int64_t n_rays,
+                          float* density, float* alpha, float* weight, float* T, uint8_t* flags,
+                          float* alphainv_last, int32_t* n_keep, void* stream);
+
+/* Exclusive scan of n_keep -> offsets[n_rays+1] (offsets[n_rays] = M). scratch >= n_rays/1024+2 int64. */
+int ubn_exclusive_scan_i32(const int32_t* in, int64_t n, int64_t* offsets, int64_t* scratch, void* stream);
+
+/* Pass B: for every survivor (flags bit1), in (ray, step) order at offsets[ray]+rank: recompute the
+ * contracted point, query the feature grid (k0), and emit the compacted per-survivor records. */
+int ubn_march_feature_fwd(const float* rays_o, const float* rays_d, const float* t_table,
+                          const float* k0_grid, const UbnGridDesc* k0_desc, const UbnMarchCfg* cfg,
+                          int64_t n_rays, const uint8_t* flags, const int64_t* offsets,
+                          const float* density, const float* alpha, const float* weight,
+                          float* k0_feat, float* out_density, float* out_alpha, float* out_weight,
+                          int64_t* ray_id, int64_t* step_id, float* out_t, uint8_t* out_inner, void* stream);
+
+/* Backward of pass B: scatter grad_feat[M,C] into grad_k0 (adjoint of the trilinear read). */
+int ubn_march_feature_bwd(const float* rays_o, const float* rays_d, const float* t_table,
+                          const UbnGridDesc* k0_desc, const UbnMarchCfg* cfg, int64_t n_rays,
+                          const uint8_t* flags, const int64_t* offsets, const float* grad_feat,
+                          float* grad_k0, void* stream);
+
+/* Backward of pass A: grads wrt compacted weights / alpha / density and alphainv_last -> exact reverse
+ * scan (alpha2weight_backward arithmetic) -> raw2alpha_backward -> scatter into grad_density. */
+int ubn_march_density_bwd(const float* rays_o, const float* rays_d, const float* t_table,
+                          const UbnGridDesc* density_desc, const UbnMarchCfg* cfg, int64_t n_rays,
+                          const float* density, const float* alpha, const float* weight, const float* T,
+                          const uint8_t* flags, const float* alphainv_last, const int64_t* offsets,
+                          const float* g_weight, const float* g_alpha, const float* g_density,
+                          const float* g_last, float* grad_density_grid, void* stream);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif  /* UBNERF_B200_H_ */

@@ -355,3 +355,143 @@ def rgbnet_forward(feat, w):
     h = torch.relu(F.linear(feat, w['W1'], w['b1']))
     h = torch.relu(F.linear(h, w['W2'], w['b2']))
     return F.linear(h, w['W3'], w['b3'])
+
+
+# --------------------------------------------------------------------------------------
+# autograd wrappers over the C oracle (dvgo.py:430-488 semantics) and full model forwards
+# --------------------------------------------------------------------------------------
+class _Raw2Alpha(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, density, shift, interval):
+        exp_d, alpha = raw2alpha(density, shift, interval)
+        ctx.save_for_backward(exp_d)
+        ctx.interval = float(interval)
+        return alpha
+
+    @staticmethod
+    def backward(ctx, g):
+        return raw2alpha_backward(ctx.saved_tensors[0], g.contiguous(), ctx.interval), None, None
+
+
+class _Alphas2Weights(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, alpha, ray_id, n_rays):
+        w, T, last, i_s, i_e = alpha2weight(alpha, ray_id, n_rays)
+        ctx.save_for_backward(alpha, w, T, last, i_s, i_e)
+        ctx.n_rays = n_rays
+        return w, last
+
+    @staticmethod
+    def backward(ctx, gw, gl):
+        alpha, w, T, last, i_s, i_e = ctx.saved_tensors
+        return alpha2weight_backward(alpha, w, T, last, i_s, i_e, ctx.n_rays, gw.contiguous(), gl.contiguous()), None, None
+
+
+def model_forward(flavor, p, rays_o, rays_d, viewdirs, stepsize, bg=1, rand_bkgd=False, is_train=False,
+                  render_depth=True):
+    """CPU restatement of FourierGridModel.forward (flavor='fouriergrid', FourierGrid_model.py:554-672) and
+    DirectContractedVoxGO.forward (flavor='dcvgo', dcvgo.py:264-384).
+
+    p: dict(density_grid [Pd,1,X,Y,Z], k0_grid [Pk,C,X,Y,Z], rgbnet=dict(W1,b1,W2,b2,W3,b3)|None, act_shift,
+            scene_center[3], scene_radius[3], bg_len, contracted_norm, fast_color_thres, voxel_size_ratio,
+            world_len, freq_density, freq_k0, viewfreq, mask (bool [X,Y,Z], dcvgo), mask_scale, mask_shift)
+    Tensors with requires_grad=True in p receive gradients through the returned dict."""
+    N = rays_o.shape[0]
+    bg_len = p['bg_len']
+    gmin = torch.tensor([-1., -1., -1.]) - bg_len
+    gmax = torch.tensor([1., 1., 1.]) + bg_len
+    t_boundary = 1.5 if flavor == 'fouriergrid' else 2.0
+    t = contracted_t_schedule(p['world_len'], stepsize, bg_len, t_boundary)
+    ray_pts, inner_mask = contracted_sample_ray(rays_o, rays_d, p['scene_center'], p['scene_radius'], t, bg_len,
+                                                p['contracted_norm'])
+    S = len(t)
+    interval = stepsize * float(p['voxel_size_ratio'])
+    ray_id = torch.arange(N).view(-1, 1).expand(N, S).flatten()
+    step_id = torch.arange(S).view(1, -1).expand(N, S).flatten()
+    tt = t[None].repeat(N, 1)
+    thres = p['fast_color_thres']
+
+    def dgrid(x):
+        return fourier_grid_forward(p['density_grid'], x, gmin, gmax, p['freq_density'])
+
+    def kgrid(x):
+        return fourier_grid_forward(p['k0_grid'], x, gmin, gmax, p['freq_k0'])
+
+    if flavor == 'dcvgo':
+        mask = inner_mask.clone()
+        dist_thres = (2 + 2 * bg_len) / p['world_len'] * stepsize * 0.95
+        dist = (ray_pts[:, 1:] - ray_pts[:, :-1]).norm(dim=-1)
+        mask[:, 1:] |= cumdist_thres(dist, dist_thres)
+        ray_pts, inner_mask, tt = ray_pts[mask], inner_mask[mask], tt[mask]
+        ray_id, step_id = ray_id[mask.flatten()], step_id[mask.flatten()]
+        mask = maskcache_lookup(p['mask'], ray_pts.contiguous(), p['mask_scale'], p['mask_shift'])
+        ray_pts, inner_mask, tt, ray_id, step_id = ray_pts[mask], inner_mask[mask], tt[mask], ray_id[mask], step_id[mask]
+    else:
+        ray_pts, inner_mask, tt = ray_pts.reshape(-1, 3), inner_mask.reshape(-1), tt.reshape(-1)
+    density = dgrid(ray_pts)
+    alpha = _Raw2Alpha.apply(density.contiguous(), float(p['act_shift']), interval)
+    if thres > 0:
+        mask = alpha > thres
+        ray_pts, inner_mask, tt, ray_id, step_id = ray_pts[mask], inner_mask[mask], tt[mask], ray_id[mask], step_id[mask]
+        density, alpha = density[mask], alpha[mask]
+    weights, alphainv_last = _Alphas2Weights.apply(alpha.contiguous(), ray_id.contiguous(), N)
+    if thres > 0:
+        mask = weights > thres
+        ray_pts, inner_mask, tt, ray_id, step_id = ray_pts[mask], inner_mask[mask], tt[mask], ray_id[mask], step_id[mask]
+        density, alpha, weights = density[mask], alpha[mask], weights[mask]
+    k0 = kgrid(ray_pts)
+    if p.get('rgbnet') is None:
+        rgb = torch.sigmoid(k0)
+    else:
+        emb = view_embedding(viewdirs, p['viewfreq']).flatten(0, -2)[ray_id]
+        rgb = torch.sigmoid(rgbnet_forward(torch.cat([k0, emb], -1), p['rgbnet']))
+    rgb_marched = torch.zeros(N, 3).index_add_(0, ray_id, weights.unsqueeze(-1) * rgb)
+    if flavor == 'dcvgo':
+        if rand_bkgd and is_train:
+            rgb_marched = rgb_marched + alphainv_last.unsqueeze(-1) * torch.rand_like(rgb_marched)
+        else:
+            rgb_marched = rgb_marched + alphainv_last.unsqueeze(-1) * bg
+    elif rand_bkgd:
+        rgb_marched = rgb_marched + alphainv_last.unsqueeze(-1) * torch.rand_like(rgb_marched)
+    s = 1 - 1 / (1 + tt)
+    ret = dict(alphainv_last=alphainv_last, weights=weights, rgb_marched=rgb_marched, raw_density=density, raw_alpha=alpha,
+               raw_rgb=rgb, ray_id=ray_id, step_id=step_id, n_max=S, t=tt, s=s)
+    if flavor == 'dcvgo':
+        ret['wsum_mid'] = torch.zeros(N).index_add_(0, ray_id[inner_mask], weights[inner_mask])
+    if render_depth:
+        with torch.no_grad():
+            ret['depth'] = torch.zeros(N).index_add_(0, ray_id, weights * s)
+    return ret
+
+
+def params_from_state(flavor, kwargs, state, requires_grad=False):
+    """Build the ``p`` dict of model_forward from a reference-style (kwargs, state_dict) pair."""
+    g = lambda k: state[k].detach().clone().float().requires_grad_(requires_grad)
+    bg_len = kwargs.get('bg_len', 0.2)
+    gmin = torch.tensor([-1., -1., -1.]) - bg_len
+    gmax = torch.tensor([1., 1., 1.]) + bg_len
+    p = dict(density_grid=g('density.grid'), k0_grid=g('k0.grid'), act_shift=float(state['act_shift']),
+             scene_center=state['scene_center'].float(), scene_radius=state['scene_radius'].float(), bg_len=bg_len,
+             contracted_norm=kwargs.get('contracted_norm', 'inf'), fast_color_thres=kwargs.get('fast_color_thres', 0))
+    if 'rgbnet.0.weight' in state:
+        p['rgbnet'] = dict(W1=g('rgbnet.0.weight'), b1=g('rgbnet.0.bias'), W2=g('rgbnet.2.0.weight'),
+                           b2=g('rgbnet.2.0.bias'), W3=g('rgbnet.3.weight'), b3=g('rgbnet.3.bias'))
+        p['viewfreq'] = state['viewfreq'].float()
+    else:
+        p['rgbnet'] = None
+    if flavor == 'fouriergrid':
+        nv, nvb = kwargs['num_voxels_density'], kwargs['num_voxels_base_density']
+        F_ = kwargs.get('fourier_freq_num', 5)
+        p['freq_density'] = F_
+        p['freq_k0'] = F_ if p['rgbnet'] is not None else 0
+    else:
+        nv, nvb = kwargs['num_voxels'], kwargs['num_voxels_base']
+        p['freq_density'] = p['freq_k0'] = 0
+        p['mask'] = state['mask_cache.mask'].bool()
+        p['mask_scale'] = state['mask_cache.xyz2ijk_scale'].float()
+        p['mask_shift'] = state['mask_cache.xyz2ijk_shift'].float()
+    voxel_size = ((gmax - gmin).prod() / nv).pow(1 / 3)
+    voxel_size_base = ((gmax - gmin).prod() / nvb).pow(1 / 3)
+    p['world_len'] = ((gmax - gmin) / voxel_size).long()[0].item()
+    p['voxel_size_ratio'] = voxel_size / voxel_size_base
+    return p

@@ -1,0 +1,59 @@
+"""Shared helpers for the parity tests."""
+import importlib.util
+import os
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+RTOL = 1e-5          # north-star tolerance for fp32 RGB / depth / weights (BASELINE.json)
+
+
+def load_golden(name):
+    return torch.load(os.path.join(ROOT, 'tests', 'golden', name), map_location='cpu', weights_only=False)
+
+
+def assert_close(a, b, rtol=RTOL, atol=1e-6, what=''):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    assert a.shape == b.shape, f'{what}: shape {tuple(a.shape)} vs {tuple(b.shape)}'
+    if a.numel() == 0:
+        return
+    err = (a - b).abs()
+    tol = atol + rtol * b.abs()
+    bad = err > tol
+    assert not bad.any(), (f'{what}: {int(bad.sum())}/{a.numel()} elements off; max abs err {err.max().item():.3e}, '
+                           f'max rel err {(err / b.abs().clamp_min(1e-12)).max().item():.3e}')
+
+
+def assert_equal(a, b, what=''):
+    a, b = a.detach().cpu(), b.detach().cpu()
+    assert a.shape == b.shape, f'{what}: shape {tuple(a.shape)} vs {tuple(b.shape)}'
+    assert torch.equal(a, b), f'{what}: {int((a != b).sum())}/{a.numel()} elements differ (bit-exact target)'
+
+
+_ref_cache = {}
+
+
+def ref_cuda(name):
+    """The reference's OWN CUDA extension module built into oracle/_ref (GPU oracle), or None when absent."""
+    if name in _ref_cache:
+        return _ref_cache[name]
+    path = os.path.join(ROOT, 'oracle', '_ref', f'{name}.so')
+    mod = None
+    if os.path.exists(path):
+        try:
+            spec = importlib.util.spec_from_file_location(name, path)
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+        except Exception as e:            # pragma: no cover
+            print(f'[tests] could not load reference extension {name}: {e}')
+            mod = None
+    _ref_cache[name] = mod
+    return mod
+
+
+def seeded_rays(n, seed, device='cpu', spread=0.5):
+    g = torch.Generator().manual_seed(seed)
+    ro = (torch.rand(n, 3, generator=g) - 0.5) * 2 * spread
+    rd = torch.randn(n, 3, generator=g)
+    vd = rd / rd.norm(dim=-1, keepdim=True)
+    return ro.to(device), rd.to(device), vd.to(device)

@@ -1,0 +1,93 @@
+"""Autograd Functions with the reference's names and call signatures (FourierGrid/dvgo.py:430-488).
+
+``Raw2Alpha.apply(density, shift, interval)``, ``Raw2Alpha_nonuni.apply(density, shift, interval)``,
+``Alphas2Weights.apply(alpha, ray_id, N) -> (weights, alphainv_last)``.  ``shift`` / ``interval`` may be
+Python numbers or 1-element tensors (the reference passes ``self.act_shift``, a 1-element CUDA tensor;
+its pybind float caster turns that into an implicit ``.item()`` on EVERY call, SURVEY.md 8b -- here the
+host value is cached per tensor version so steady-state calls do not synchronise).
+"""
+import torch
+
+from . import ops
+
+_scalar_cache = {}
+
+
+def host_scalar(v):
+    """float(v) with a (data_ptr, version) cache for device tensors."""
+    if isinstance(v, torch.Tensor):
+        if v.is_cuda:
+            key = (v.data_ptr(), v._version, v.device.index)
+            hit = _scalar_cache.get(key)
+            if hit is None:
+                if len(_scalar_cache) > 64:
+                    _scalar_cache.clear()
+                hit = float(v)
+                _scalar_cache[key] = hit
+            return hit
+        return float(v)
+    return float(v)
+
+
+class Raw2Alpha(torch.autograd.Function):
+    """alpha = 1 - (1 + exp(density + shift)) ** (-interval)   (dvgo.py:430-454)."""
+
+    @staticmethod
+    def forward(ctx, density, shift, interval):
+        interval = host_scalar(interval)
+        exp, alpha = ops.raw2alpha(density, host_scalar(shift), interval)
+        if density.requires_grad:
+            ctx.save_for_backward(exp)
+            ctx.interval = interval
+        return alpha
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_back):
+        exp = ctx.saved_tensors[0]
+        return ops.raw2alpha_backward(exp, grad_back.contiguous(), ctx.interval), None, None
+
+
+class Raw2Alpha_nonuni(torch.autograd.Function):
+    """Per-point interval variant (dvgo.py:456-470)."""
+
+    @staticmethod
+    def forward(ctx, density, shift, interval):
+        exp, alpha = ops.raw2alpha_nonuni(density, host_scalar(shift), interval)
+        if density.requires_grad:
+            ctx.save_for_backward(exp, interval)
+        return alpha
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_back):
+        exp, interval = ctx.saved_tensors
+        return ops.raw2alpha_nonuni_backward(exp, grad_back.contiguous(), interval), None, None
+
+
+class Alphas2Weights(torch.autograd.Function):
+    """weights_i = alpha_i * prod_{j<i}(1 - alpha_j) per ray with the reference's early stop (dvgo.py:472-488)."""
+
+    @staticmethod
+    def forward(ctx, alpha, ray_id, N):
+        weights, T, alphainv_last, i_start, i_end = ops.alpha2weight(alpha, ray_id, N)
+        if alpha.requires_grad:
+            ctx.save_for_backward(alpha, weights, T, alphainv_last, i_start, i_end)
+            ctx.n_rays = N
+        return weights, alphainv_last
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_weights, grad_last):
+        alpha, weights, T, alphainv_last, i_start, i_end = ctx.saved_tensors
+        grad = ops.alpha2weight_backward(alpha, weights, T, alphainv_last, i_start, i_end, ctx.n_rays,
+                                         grad_weights.contiguous(), grad_last.contiguous())
+        return grad, None, None
+
+
+def segment_coo(src, index, out, reduce='sum'):
+    """torch_scatter.segment_coo(reduce='sum') for sorted ``index`` (call sites dvgo.py:401,418;
+    dcvgo.py:345,354,377; FourierGrid_model.py:640,666): accumulate rows of ``src`` into ``out``."""
+    if reduce != 'sum':
+        raise NotImplementedError(reduce)
+    return out.index_add_(0, index, src)

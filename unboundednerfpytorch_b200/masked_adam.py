@@ -1,0 +1,94 @@
+"""MaskedAdam with the reference's constructor / step surface (FourierGrid/masked_adam.py:21-75).
+
+* per-voxel learning rate (``set_pervoxel_lr``), masked update (skip elements whose grad is exactly 0).
+* ``step()`` dispatches per parameter to the adam_upd / masked_adam_upd / adam_upd_with_perlr kernels
+  (adam_upd_kernel.cu:9-58) exactly like masked_adam.py:62-75.
+"""
+import torch
+
+from . import ops
+
+
+class MaskedAdam(torch.optim.Optimizer):
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.99), eps=1e-8):
+        if not 0.0 <= lr:
+            raise ValueError('Invalid learning rate: {}'.format(lr))
+        if not 0.0 <= eps:
+            raise ValueError('Invalid epsilon value: {}'.format(eps))
+        if not 0.0 <= betas[0] < 1.0:
+            raise ValueError('Invalid beta parameter at index 0: {}'.format(betas[0]))
+        if not 0.0 <= betas[1] < 1.0:
+            raise ValueError('Invalid beta parameter at index 1: {}'.format(betas[1]))
+        self.per_lr = None
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
+
+    def set_pervoxel_lr(self, count):
+        assert self.param_groups[0]['params'][0].shape == count.shape
+        self.per_lr = count.float() / count.max()
+
+    @torch.no_grad()
+    def step(self):
+        for group in self.param_groups:
+            lr = group['lr']
+            beta1, beta2 = group['betas']
+            eps = group['eps']
+            skip_zero_grad = group['skip_zero_grad']      # KeyError when absent, like masked_adam.py:49
+            for param in group['params']:
+                if param.grad is None:
+                    continue
+                state = self.state[param]
+                if len(state) == 0:
+                    state['step'] = 0
+                    state['exp_avg'] = torch.zeros_like(param, memory_format=torch.preserve_format)
+                    state['exp_avg_sq'] = torch.zeros_like(param, memory_format=torch.preserve_format)
+                state['step'] += 1
+                grad = param.grad
+                if grad.stride() != param.stride():
+                    grad = torch.empty_like(param, memory_format=torch.preserve_format).copy_(grad)
+                if self.per_lr is not None and param.shape == self.per_lr.shape:
+                    per_lr = self.per_lr
+                    if per_lr.stride() != param.stride():
+                        per_lr = torch.empty_like(param, memory_format=torch.preserve_format).copy_(per_lr)
+                        self.per_lr = per_lr
+                    ops.adam_upd_with_perlr(param, grad, state['exp_avg'], state['exp_avg_sq'], per_lr,
+                                            state['step'], beta1, beta2, lr, eps)
+                elif skip_zero_grad:
+                    ops.masked_adam_upd(param, grad, state['exp_avg'], state['exp_avg_sq'],
+                                        state['step'], beta1, beta2, lr, eps)
+                else:
+                    ops.adam_upd(param, grad, state['exp_avg'], state['exp_avg_sq'],
+                                 state['step'], beta1, beta2, lr, eps)
+
+
+def create_optimizer_or_freeze_model(model, cfg_train, global_step):
+    """Optimizer factory with the reference's config keys (FourierGrid/utils.py:26-56): every ``lrate_<name>``
+    key names a sub-module / parameter of ``model``; lr decays by 0.1 every ``lrate_decay``*1000 steps;
+    ``skip_zero_grad_fields`` selects the masked update."""
+    get = (lambda k, d=None: cfg_train.get(k, d)) if hasattr(cfg_train, 'get') else (lambda k, d=None: getattr(cfg_train, k, d))
+    keys = cfg_train.keys() if hasattr(cfg_train, 'keys') else vars(cfg_train).keys()
+    decay_steps = get('lrate_decay') * 1000
+    decay_factor = 0.1 ** (global_step / decay_steps)
+    skip = get('skip_zero_grad_fields', []) or []
+    groups = []
+    for k in keys:
+        if not k.startswith('lrate_') or k == 'lrate_decay':
+            continue
+        name = k[len('lrate_'):]
+        if not hasattr(model, name):
+            continue
+        param = getattr(model, name)
+        if param is None:
+            continue
+        lr = get(k) * decay_factor
+        if lr > 0:
+            if isinstance(param, torch.nn.Module):
+                param = param.parameters()
+            groups.append({'params': param, 'lr': lr, 'skip_zero_grad': (name in skip)})
+        else:
+            if isinstance(param, torch.nn.Module):
+                for p in param.parameters():
+                    p.requires_grad = False
+            else:
+                param.requires_grad = False
+    return MaskedAdam(groups)

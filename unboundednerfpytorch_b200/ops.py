@@ -1,0 +1,299 @@
+"""Host-side mirror of the reference's four extension modules, on top of the C ABI.
+
+Same function names, argument order/meaning, return values and error behaviour as
+``render_utils_cuda`` (FourierGrid/cuda/render_utils.cpp:170-184), ``total_variation_cuda``
+(total_variation.cpp:22-24), ``adam_upd_cuda`` (adam_upd.cpp:79-86) and ``ub360_utils_cuda``
+(ub360_utils.cpp:20-22): tensor arguments must be CUDA + contiguous (``RuntimeError`` otherwise, the
+reference's CHECK_CUDA / CHECK_CONTIGUOUS, render_utils.cpp:46-48); outputs are freshly allocated.
+Differences, all supersets: outputs live on the *input's* device (the reference hard-codes the current
+device), kernels run on torch's current stream, launch errors are checked, fp32 only.
+"""
+import ctypes
+
+import torch
+
+from . import _cabi
+from ._cabi import c_f, c_i64, c_int, check, ptr, stream_of
+
+
+def _chk(x, name, dtype=torch.float32):
+    if not isinstance(x, torch.Tensor) or not x.is_cuda:
+        raise RuntimeError(f'{name} must be a CUDA tensor')
+    if not x.is_contiguous():
+        raise RuntimeError(f'{name} must be contiguous')
+    if dtype is not None and x.dtype != dtype:
+        raise RuntimeError(f'{name} must be {dtype} (got {x.dtype})')
+    return x
+
+
+def _scalar(v):
+    """Python number, 0-d / 1-element tensor -> float (the reference relies on pybind's float caster,
+    i.e. Tensor.__float__, for `shift` / `interval`: dvgo.py:439, FourierGrid_model.py:493)."""
+    return float(v)
+
+
+class _Guard:
+    """CUDAGuard equivalent: make the tensor's device current for the duration of the call."""
+
+    def __init__(self, t):
+        self.dev = torch.cuda.device(t.device)
+
+    def __enter__(self):
+        self.dev.__enter__()
+        return _cabi.load()
+
+    def __exit__(self, *a):
+        return self.dev.__exit__(*a)
+
+
+# --------------------------------------------------------------------------------------------------
+# render_utils_cuda
+# --------------------------------------------------------------------------------------------------
+def infer_t_minmax(rays_o, rays_d, xyz_min, xyz_max, near, far):
+    _chk(rays_o, 'rays_o'); _chk(rays_d, 'rays_d'); _chk(xyz_min, 'xyz_min'); _chk(xyz_max, 'xyz_max')
+    n = rays_o.shape[0]
+    t_min = torch.empty(n, dtype=torch.float32, device=rays_o.device)
+    t_max = torch.empty_like(t_min)
+    with _Guard(rays_o) as lib:
+        check(lib.ubn_infer_t_minmax(ptr(rays_o), ptr(rays_d), ptr(xyz_min), ptr(xyz_max), c_f(near), c_f(far),
+                                     c_i64(n), ptr(t_min), ptr(t_max), stream_of(rays_o)))
+    return [t_min, t_max]
+
+
+def infer_n_samples(rays_d, t_min, t_max, stepdist):
+    _chk(rays_d, 'rays_d'); _chk(t_min, 't_min'); _chk(t_max, 't_max')
+    n = t_min.shape[0]
+    out = torch.empty(n, dtype=torch.int64, device=rays_d.device)
+    with _Guard(rays_d) as lib:
+        check(lib.ubn_infer_n_samples(ptr(rays_d), ptr(t_min), ptr(t_max), c_f(stepdist), c_i64(n), ptr(out),
+                                      stream_of(rays_d)))
+    return out
+
+
+def infer_ray_start_dir(rays_o, rays_d, t_min):
+    _chk(rays_o, 'rays_o'); _chk(rays_d, 'rays_d'); _chk(t_min, 't_min')
+    n = rays_o.shape[0]
+    start, dirs = torch.empty_like(rays_o), torch.empty_like(rays_o)
+    with _Guard(rays_o) as lib:
+        check(lib.ubn_infer_ray_start_dir(ptr(rays_o), ptr(rays_d), ptr(t_min), c_i64(n), ptr(start), ptr(dirs),
+                                          stream_of(rays_o)))
+    return [start, dirs]
+
+
+def sample_pts_on_rays(rays_o, rays_d, xyz_min, xyz_max, near, far, stepdist):
+    _chk(rays_o, 'rays_o'); _chk(rays_d, 'rays_d'); _chk(xyz_min, 'xyz_min'); _chk(xyz_max, 'xyz_max')
+    dev = rays_o.device
+    n = rays_o.shape[0]
+    t_min = torch.empty(n, dtype=torch.float32, device=dev)
+    t_max = torch.empty_like(t_min)
+    n_steps = torch.empty(n, dtype=torch.int64, device=dev)
+    offsets = torch.empty(n + 1, dtype=torch.int64, device=dev)
+    scratch = torch.empty(n // 1024 + 4, dtype=torch.int64, device=dev)
+    with _Guard(rays_o) as lib:
+        st = stream_of(rays_o)
+        check(lib.ubn_sample_pts_count(ptr(rays_o), ptr(rays_d), ptr(xyz_min), ptr(xyz_max), c_f(near), c_f(far),
+                                       c_f(stepdist), c_i64(n), ptr(t_min), ptr(t_max), ptr(n_steps), ptr(offsets),
+                                       ptr(scratch), st))
+        total = int(offsets[n].item())   # the one host sync the return contract requires (ragged size)
+        pts = torch.empty(total, 3, dtype=torch.float32, device=dev)
+        mask = torch.empty(total, dtype=torch.bool, device=dev)
+        ray_id = torch.empty(total, dtype=torch.int64, device=dev)
+        step_id = torch.empty(total, dtype=torch.int64, device=dev)
+        check(lib.ubn_sample_pts_emit(ptr(rays_o), ptr(rays_d), ptr(xyz_min), ptr(xyz_max), ptr(t_min), ptr(offsets),
+                                      c_f(stepdist), c_i64(n), c_i64(total), ptr(pts), ptr(mask), ptr(ray_id),
+                                      ptr(step_id), st))
+    return [pts, mask, ray_id, step_id, n_steps, t_min, t_max]
+
+
+def sample_ndc_pts_on_rays(rays_o, rays_d, xyz_min, xyz_max, N_samples):
+    _chk(rays_o, 'rays_o'); _chk(rays_d, 'rays_d'); _chk(xyz_min, 'xyz_min'); _chk(xyz_max, 'xyz_max')
+    n = rays_o.shape[0]
+    pts = torch.empty(n, N_samples, 3, dtype=torch.float32, device=rays_o.device)
+    mask = torch.empty(n, N_samples, dtype=torch.bool, device=rays_o.device)
+    with _Guard(rays_o) as lib:
+        check(lib.ubn_sample_ndc_pts_on_rays(ptr(rays_o), ptr(rays_d), ptr(xyz_min), ptr(xyz_max), c_i64(N_samples),
+                                             c_i64(n), ptr(pts), ptr(mask), stream_of(rays_o)))
+    return [pts, mask]
+
+
+def sample_bg_pts_on_rays(rays_o, rays_d, t_max, bg_preserve, N_samples):
+    _chk(rays_o, 'rays_o'); _chk(rays_d, 'rays_d'); _chk(t_max, 't_max')
+    n = rays_o.shape[0]
+    pts = torch.empty(n, N_samples, 3, dtype=torch.float32, device=rays_o.device)
+    with _Guard(rays_o) as lib:
+        check(lib.ubn_sample_bg_pts_on_rays(ptr(rays_o), ptr(rays_d), ptr(t_max), c_f(bg_preserve), c_i64(N_samples),
+                                            c_i64(n), ptr(pts), stream_of(rays_o)))
+    return pts
+
+
+def maskcache_lookup(world, xyz, xyz2ijk_scale, xyz2ijk_shift):
+    _chk(world, 'world', torch.bool); _chk(xyz, 'xyz')
+    _chk(xyz2ijk_scale, 'xyz2ijk_scale'); _chk(xyz2ijk_shift, 'xyz2ijk_shift')
+    n = xyz.shape[0]
+    out = torch.empty(n, dtype=torch.bool, device=xyz.device)
+    if n == 0:
+        return out
+    with _Guard(xyz) as lib:
+        check(lib.ubn_maskcache_lookup(ptr(world), ptr(xyz), ptr(xyz2ijk_scale), ptr(xyz2ijk_shift),
+                                       c_i64(world.shape[0]), c_i64(world.shape[1]), c_i64(world.shape[2]), c_i64(n),
+                                       ptr(out), stream_of(xyz)))
+    return out
+
+
+def raw2alpha(density, shift, interval):
+    _chk(density, 'density')
+    exp_d, alpha = torch.empty_like(density), torch.empty_like(density)
+    with _Guard(density) as lib:
+        check(lib.ubn_raw2alpha(ptr(density), c_f(_scalar(shift)), c_f(_scalar(interval)), ptr(None),
+                                c_i64(density.numel()), ptr(exp_d), ptr(alpha), stream_of(density)))
+    return [exp_d, alpha]
+
+
+def raw2alpha_nonuni(density, shift, interval):
+    _chk(density, 'density'); _chk(interval, 'interval')
+    exp_d, alpha = torch.empty_like(density), torch.empty_like(density)
+    with _Guard(density) as lib:
+        check(lib.ubn_raw2alpha(ptr(density), c_f(_scalar(shift)), c_f(0.0), ptr(interval), c_i64(density.numel()),
+                                ptr(exp_d), ptr(alpha), stream_of(density)))
+    return [exp_d, alpha]
+
+
+def raw2alpha_backward(exp_d, grad_back, interval):
+    _chk(exp_d, 'exp'); _chk(grad_back, 'grad_back')
+    grad = torch.empty_like(exp_d)
+    with _Guard(exp_d) as lib:
+        check(lib.ubn_raw2alpha_backward(ptr(exp_d), ptr(grad_back), c_f(_scalar(interval)), ptr(None),
+                                         c_i64(exp_d.numel()), ptr(grad), stream_of(exp_d)))
+    return grad
+
+
+def raw2alpha_nonuni_backward(exp_d, grad_back, interval):
+    _chk(exp_d, 'exp'); _chk(grad_back, 'grad_back'); _chk(interval, 'interval')
+    grad = torch.empty_like(exp_d)
+    with _Guard(exp_d) as lib:
+        check(lib.ubn_raw2alpha_backward(ptr(exp_d), ptr(grad_back), c_f(0.0), ptr(interval), c_i64(exp_d.numel()),
+                                         ptr(grad), stream_of(exp_d)))
+    return grad
+
+
+def alpha2weight(alpha, ray_id, n_rays):
+    _chk(alpha, 'alpha'); _chk(ray_id, 'ray_id', torch.int64)
+    dev = alpha.device
+    n = alpha.numel()
+    weight, T = torch.empty_like(alpha), torch.empty_like(alpha)
+    last = torch.empty(n_rays, dtype=torch.float32, device=dev)
+    i_start = torch.empty(n_rays, dtype=torch.int64, device=dev)
+    i_end = torch.empty(n_rays, dtype=torch.int64, device=dev)
+    with _Guard(alpha) as lib:
+        check(lib.ubn_alpha2weight(ptr(alpha), ptr(ray_id), c_i64(n), c_i64(n_rays), ptr(weight), ptr(T), ptr(last),
+                                   ptr(i_start), ptr(i_end), stream_of(alpha)))
+    return [weight, T, last, i_start, i_end]
+
+
+def alpha2weight_backward(alpha, weight, T, alphainv_last, i_start, i_end, n_rays, grad_weights, grad_last):
+    _chk(alpha, 'alpha'); _chk(weight, 'weight'); _chk(T, 'T'); _chk(alphainv_last, 'alphainv_last')
+    _chk(i_start, 'i_start', torch.int64); _chk(i_end, 'i_end', torch.int64)
+    _chk(grad_weights, 'grad_weights'); _chk(grad_last, 'grad_last')
+    grad = torch.empty_like(alpha)
+    with _Guard(alpha) as lib:
+        check(lib.ubn_alpha2weight_backward(ptr(alpha), ptr(weight), ptr(T), ptr(alphainv_last), ptr(i_start),
+                                            ptr(i_end), c_i64(alpha.numel()), c_i64(n_rays), ptr(grad_weights),
+                                            ptr(grad_last), ptr(grad), stream_of(alpha)))
+    return grad
+
+
+# --------------------------------------------------------------------------------------------------
+# total_variation_cuda / adam_upd_cuda / ub360_utils_cuda
+# --------------------------------------------------------------------------------------------------
+def _sweep_layout(param):
+    """(lead, inner) of a 5-D [P,C,X,Y,Z] grid stored either contiguous or channels-last."""
+    if param.dim() != 5:
+        raise RuntimeError('param must be 5-D [P,C,X,Y,Z]')
+    P, C = param.shape[0], param.shape[1]
+    if param.is_contiguous():
+        return P * C, 1
+    if param.permute(0, 2, 3, 4, 1).is_contiguous():
+        return P, C
+    raise RuntimeError('param must be contiguous (or channels-last contiguous)')
+
+
+def total_variation_add_grad(param, grad, wx, wy, wz, dense_mode):
+    if not (isinstance(param, torch.Tensor) and param.is_cuda):
+        raise RuntimeError('param must be a CUDA tensor')
+    if not (isinstance(grad, torch.Tensor) and grad.is_cuda):
+        raise RuntimeError('grad must be a CUDA tensor')
+    lead, inner = _sweep_layout(param)
+    if grad.shape != param.shape or grad.stride() != param.stride():
+        raise RuntimeError('grad must be contiguous')   # same layout as param
+    with _Guard(param) as lib:
+        check(lib.ubn_total_variation_add_grad(ptr(param), ptr(grad), c_f(float(wx)), c_f(float(wy)), c_f(float(wz)),
+                                               c_i64(lead), c_i64(param.shape[2]), c_i64(param.shape[3]),
+                                               c_i64(param.shape[4]), c_i64(inner), c_int(int(bool(dense_mode))),
+                                               stream_of(param)))
+
+
+def _is_dense(t):
+    """True when t covers its storage span exactly once (contiguous in SOME dimension order)."""
+    if t.is_contiguous() or t.numel() == 0:
+        return True
+    order = sorted(range(t.dim()), key=lambda d: (-t.stride(d), d))
+    return t.permute(order).is_contiguous()
+
+
+def _dense_like(a, b, name):
+    if not (isinstance(b, torch.Tensor) and b.is_cuda):
+        raise RuntimeError(f'{name} must be a CUDA tensor')
+    if b.shape != a.shape or b.stride() != a.stride() or b.dtype != torch.float32:
+        raise RuntimeError(f'{name} must be contiguous')
+
+
+def _adam(param, grad, exp_avg, exp_avg_sq, perlr, step, beta1, beta2, lr, eps, mode):
+    if not (isinstance(param, torch.Tensor) and param.is_cuda):
+        raise RuntimeError('param must be a CUDA tensor')
+    # elementwise: any dense (non-overlapping) layout works as long as all operands share it
+    if not _is_dense(param):
+        raise RuntimeError('param must be contiguous')
+    _dense_like(param, grad, 'grad'); _dense_like(param, exp_avg, 'exp_avg'); _dense_like(param, exp_avg_sq, 'exp_avg_sq')
+    if perlr is not None:
+        _dense_like(param, perlr, 'perlr')
+    with _Guard(param) as lib:
+        check(lib.ubn_adam_upd(ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), ptr(perlr), c_i64(param.numel()),
+                               c_int(int(step)), c_f(beta1), c_f(beta2), c_f(lr), c_f(eps), c_int(mode),
+                               stream_of(param)))
+
+
+def adam_upd(param, grad, exp_avg, exp_avg_sq, step, beta1, beta2, lr, eps):
+    _adam(param, grad, exp_avg, exp_avg_sq, None, step, beta1, beta2, lr, eps, 0)
+
+
+def masked_adam_upd(param, grad, exp_avg, exp_avg_sq, step, beta1, beta2, lr, eps):
+    _adam(param, grad, exp_avg, exp_avg_sq, None, step, beta1, beta2, lr, eps, 1)
+
+
+def adam_upd_with_perlr(param, grad, exp_avg, exp_avg_sq, perlr, step, beta1, beta2, lr, eps):
+    _adam(param, grad, exp_avg, exp_avg_sq, perlr, step, beta1, beta2, lr, eps, 2)
+
+
+def tv_adam_fused(param, grad, exp_avg, exp_avg_sq, wx, wy, wz, tv_mode, step, beta1, beta2, lr, eps,
+                  skip_zero_grad=True, zero_grad=True):
+    """Training-step tail in two sweeps instead of three (+ no grad memset): TV (tv_mode 0 none / 1 dense /
+    2 sparse) then (masked) Adam that also clears the gradients it consumed."""
+    lead, inner = _sweep_layout(param)
+    _dense_like(param, grad, 'grad'); _dense_like(param, exp_avg, 'exp_avg'); _dense_like(param, exp_avg_sq, 'exp_avg_sq')
+    with _Guard(param) as lib:
+        check(lib.ubn_tv_adam_fused(ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), c_f(float(wx)), c_f(float(wy)),
+                                    c_f(float(wz)), c_i64(lead), c_i64(param.shape[2]), c_i64(param.shape[3]),
+                                    c_i64(param.shape[4]), c_i64(inner), c_int(int(tv_mode)), c_int(int(step)),
+                                    c_f(beta1), c_f(beta2), c_f(lr), c_f(eps), c_int(1 if skip_zero_grad else 0),
+                                    c_int(1 if zero_grad else 0), stream_of(param)))
+
+
+def cumdist_thres(dist, thres):
+    _chk(dist, 'dist')
+    mask = torch.empty(dist.shape, dtype=torch.bool, device=dist.device)
+    if dist.numel() == 0:
+        return mask
+    with _Guard(dist) as lib:
+        check(lib.ubn_cumdist_thres(ptr(dist), c_f(float(thres)), c_i64(dist.shape[0]), c_i64(dist.shape[1]), ptr(mask),
+                                    stream_of(dist)))
+    return mask
