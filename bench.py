@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the FourierGrid / DVGO rendering hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload truck|bicycle]
+
+Metric (BASELINE.json): ray-samples/sec, 8192 rays x 512 samples, one training iteration per step
+(forward + loss + backward + total-variation + MaskedAdam, i.e. run_train.py:251-288 of the reference).
+Workload `truck` = BASELINE config[1]: FourierGridModel, 153^3 grids (S = 512 at stepsize 0.5), F = 4 => 9 slabs,
+12-channel k0 + 39->128->128->3 rgbnet, dense mode (fast_color_thres = 0, density ~ N(0,1), alpha_init 1e-4: every
+nominal sample is live -- the roofline configuration of SURVEY.md 8d), synthetic seeded rays / grids (seed 777).
+`bicycle` = config[2]: DirectContractedVoxGO 320^3 DenseGrid, stepsize 1.045 (S = 512).
+
+One JSON line on stdout (rank 0).  `value` = device-timed throughput with the ray batch resident in HBM; `e2e` = same
+step through the public model API with the batch in pinned HOST memory (H2D of rays + target, D2H of the loss, every
+step, inside the timed region).  `roofline` = the dominant hand-written kernel, timed live with CUDA events inside the
+timed region.  `cpu_baseline` / `--impl reference` = the reference's algorithm on the host cores (CPU oracle port of
+the same step: torch F.grid_sample CPU path + C restatement of the CUDA-only ops) on a bounded ray sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+N_RAYS, N_SAMPLES = 8192, 512
+SEED = 777
+
+
+def workload_kwargs(name):
+    if name == 'truck':
+        world = 153
+        return 'fouriergrid', dict(xyz_min=[-1.] * 3, xyz_max=[1.] * 3, num_voxels_density=world ** 3,
+                                   num_voxels_base_density=world ** 3, num_voxels_rgb=world ** 3,
+                                   num_voxels_base_rgb=world ** 3, num_voxels_viewdir=-1, alpha_init=1e-4,
+                                   fast_color_thres=0, rgbnet_dim=12, fourier_freq_num=4), 0.5
+    if name == 'bicycle':
+        world = 320
+        return 'dcvgo', dict(xyz_min=[-1.] * 3, xyz_max=[1.] * 3, num_voxels=world ** 3, num_voxels_base=world ** 3,
+                             alpha_init=1e-4, fast_color_thres=0, rgbnet_dim=12, contracted_norm='l2'), 1.045
+    raise ValueError(name)
+
+
+def synth_batch(n, seed):
+    g = torch.Generator().manual_seed(seed)
+    ro = torch.rand(n, 3, generator=g) - 0.5
+    rd = torch.randn(n, 3, generator=g)
+    vd = rd / rd.norm(dim=-1, keepdim=True)
+    target = torch.rand(n, 3, generator=g)
+    return ro, rd, vd, target
+
+
+def step_loss(ret, target, n_rays):
+    """The always-on loss terms of run_train.py:254-279: MSE + 1e-3 * entropy_last + 1e-2 * rgbper."""
+    loss = torch.nn.functional.mse_loss(ret['rgb_marched'], target)
+    pout = ret['alphainv_last'].clamp(1e-6, 1 - 1e-6)
+    loss = loss + 1e-3 * (-(pout * torch.log(pout) + (1 - pout) * torch.log(1 - pout)).mean())
+    rgbper = (ret['raw_rgb'] - target[ret['ray_id']]).pow(2).sum(-1)
+    return loss + 1e-2 * (rgbper * ret['weights'].detach()).sum() / n_rays
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--id={self.index}', f'--query-gpu={q}', '--format=csv,noheader,nounits',
+                                          '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace('.', '').isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace('.', '').isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 7:
+                for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[3:7]):
+                    if v.lower().startswith('active'):
+                        reasons.add(name)
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def algorithmic_bytes(flavor, kwargs):
+    """SURVEY.md 8d gather model, rho = 1: fwd 32*P_d + 32*C*P_k bytes per ray-sample; bwd = 2x (RMW scatter)."""
+    P = (1 + 2 * kwargs.get('fourier_freq_num', 0)) if flavor == 'fouriergrid' else 1
+    C = 12
+    return {'march_density_fwd': 32 * P, 'march_feature_fwd': 32 * C * P,
+            'march_density_bwd': 2 * 32 * P, 'march_feature_bwd': 2 * 32 * C * P}
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+    except Exception:
+        return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def load_traffic(kernel):
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as f:
+            return json.load(f).get(kernel)
+    except Exception:
+        return None
+
+
+# ----------------------------------------------------------------------------------------------------------
+def cpu_reference_step(flavor, kwargs, stepsize, n_rays, threads, steps, warmup):
+    """The reference's algorithm on host cores: oracle port of forward + loss + backward (torch F.grid_sample CPU path +
+    C restatement of the CUDA-only ops) on a bounded ray sample of the same workload (same grids).  The TV / Adam sweeps
+    are NOT included: the reference has no CPU implementation of them (CUDA-only extension), so the CPU figure covers
+    LESS work per step than the GPU arm -- it flatters the baseline, never the GPU.  Returns ray-samples/s."""
+    from oracle import cpu_ref
+    from unboundednerfpytorch_b200 import models
+    torch.set_num_threads(threads)
+    torch.manual_seed(SEED)
+    cls = models.FourierGridModel if flavor == 'fouriergrid' else models.DirectContractedVoxGO
+    m = cls(**kwargs)                                  # CPU tensors; used only as a shape / init recipe
+    g = torch.Generator().manual_seed(SEED)
+    with torch.no_grad():
+        m.density.grid.copy_(torch.randn(m.density.grid.shape, generator=g))
+        m.k0.grid.copy_(torch.randn(m.k0.grid.shape, generator=g))
+    state = {k: v.detach().clone().contiguous() for k, v in m.state_dict().items()}
+    p = cpu_ref.params_from_state(flavor, kwargs, state, requires_grad=True)
+    ro, rd, vd, target = synth_batch(n_rays, SEED)
+    leaves = [p['density_grid'], p['k0_grid']] + list(p['rgbnet'].values())
+    times = []
+    for it in range(1, warmup + steps + 1):
+        t0 = time.perf_counter()
+        for x in leaves:
+            x.grad = None
+        ret = cpu_ref.model_forward(flavor, p, ro, rd, vd, stepsize, bg=1, rand_bkgd=False, render_depth=False)
+        step_loss(ret, target, n_rays).backward()
+        dt = time.perf_counter() - t0
+        if it > warmup:
+            times.append(dt)
+    S = ret['n_max']
+    return n_rays * S / (sum(times) / len(times)), sum(times) / len(times)
+
+
+# ----------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='truck', choices=['truck', 'bicycle'])
+    ap.add_argument('--cpu-rays', type=int, default=256, help='ray sample of the CPU baseline (bounded)')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
+
+    from unboundednerfpytorch_b200 import dist as ubdist
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    flavor, kwargs, stepsize = workload_kwargs(args.workload)
+    cores = os.cpu_count() or 1
+    config = {'workload': f'{args.workload}: {flavor} {"153^3 F=4 (9 slabs)" if args.workload == "truck" else "320^3 DenseGrid"} '
+                          f'+ 12-ch k0 + rgbnet, {N_RAYS} rays x {N_SAMPLES} samples per GPU, dense mode (thres=0)',
+              'step': 'fwd + loss(mse+entropy_last+rgbper) + bwd + dense TV + MaskedAdam',
+              'rays_per_gpu': N_RAYS, 'samples_per_ray': N_SAMPLES, 'parallelism': f'ray-sharded dp{max(world, 1)}, grids replicated',
+              'l2_policy': 'inputs larger than L2: 1.7 GB (truck) / 1.7 GB (bicycle) of grid + equally large grad/Adam state'
+                           ' touched every step'}
+
+    # ------------------------------------------------------------------ reference arm: CPU, rank 0 only
+    if args.impl == 'reference':
+        if rank != 0:
+            return
+        v, sec = cpu_reference_step(flavor, kwargs, stepsize, args.cpu_rays, cores, max(args.steps, 1), args.warmup)
+        line = {'impl': 'reference', 'metric': 'ray-samples/sec (fwd+bwd train step) 8192x512', 'value': v, 'unit': 'ray-samples/s',
+                'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': sec * 1e3 * (N_RAYS / args.cpu_rays),
+                'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+                'config': config,
+                'cpu_baseline': {'value': v, 'unit': 'ray-samples/s', 'cores': cores, 'kind': 'port',
+                                 'sample': f'{args.cpu_rays} of {N_RAYS} rays x {N_SAMPLES} samples, same grids, fwd+loss+bwd (no TV/Adam sweeps on CPU)'},
+                'e2e': {'value': v, 'unit': 'ray-samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------ our arm
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py --impl ours needs a GPU (no CPU fallback exists)')
+    rank, world, local = ubdist.init_from_env()
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    from unboundednerfpytorch_b200 import _cabi, models
+    from unboundednerfpytorch_b200.masked_adam import create_optimizer_or_freeze_model
+    _cabi.load()
+    torch.manual_seed(SEED)
+    cls = models.FourierGridModel if flavor == 'fouriergrid' else models.DirectContractedVoxGO
+    model = cls(**kwargs).to(dev)
+    g = torch.Generator(device=dev).manual_seed(SEED)
+    with torch.no_grad():
+        model.density.grid.copy_(torch.randn(model.density.grid.shape, generator=g, device=dev))
+        model.k0.grid.copy_(torch.randn(model.k0.grid.shape, generator=g, device=dev))
+    cfg_train = dict(lrate_density=1e-1, lrate_k0=1e-1, lrate_rgbnet=1e-3, lrate_decay=20, skip_zero_grad_fields=['density', 'k0'])
+    opt = create_optimizer_or_freeze_model(model, cfg_train, global_step=0)
+    rk = dict(near=0., far=1e9, bg=1, rand_bkgd=False, stepsize=stepsize)
+    params = [p for p in model.parameters() if p.requires_grad]
+
+    # every rank gets its own 8192-ray batch (weak scaling); host copies are pinned for the e2e leg
+    host = [t.pin_memory() for t in synth_batch(N_RAYS, SEED + rank)]
+    dev_batch = [t.to(dev) for t in host]
+
+    def train_step(ro, rd, vd, target, it):
+        ret = model(ro, rd, vd, global_step=it, is_train=True, **rk)
+        opt.zero_grad(set_to_none=True)
+        loss = step_loss(ret, target, N_RAYS)
+        loss.backward()
+        if world > 1:
+            ubdist.allreduce_grads(params)
+        model.density_total_variation_add_grad(1e-6 / N_RAYS, True)
+        model.k0_total_variation_add_grad(1e-7 / N_RAYS, True)
+        opt.step()
+        return loss
+
+    def sync_all():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def timed_region(fn, steps):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        sync_all()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+        return ms.item()
+
+    it = [0]
+
+    def dev_step(_):
+        it[0] += 1
+        train_step(*dev_batch, it[0])
+
+    def e2e_step(_):
+        it[0] += 1
+        ro, rd, vd, target = [t.to(dev, non_blocking=True) for t in host]
+        loss = train_step(ro, rd, vd, target, it[0])
+        return loss.item()                                   # D2H read of the step's result
+
+    for i in range(args.warmup):
+        dev_step(i)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    _cabi.TIMER = _cabi.KernelTimer()
+    _cabi.reset_launch_count()
+    ms_total = timed_region(dev_step, args.steps)
+    launches = _cabi.launch_count()
+    ktimes = _cabi.TIMER.summary()
+    _cabi.TIMER = None
+    clk = clocks.stop() if rank == 0 else None
+    for i in range(2):
+        e2e_step(i)
+    ms_e2e = timed_region(e2e_step, args.steps)
+
+    # forward-only (render) throughput, for context
+    def fwd_only(_):
+        with torch.no_grad():
+            model(*dev_batch[:3], global_step=None, is_train=False, **rk)
+    fwd_only(0)
+    ms_fwd = timed_region(fwd_only, args.steps)
+
+    if rank != 0:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return
+
+    samples_per_step = N_RAYS * N_SAMPLES * world
+    ms_per_step = ms_total / args.steps
+    value = samples_per_step / (ms_per_step * 1e-3)
+    peak, peak_src = load_peaks()
+    abytes = algorithmic_bytes(flavor, kwargs)
+    dom = max(ktimes, key=lambda k: ktimes[k][0]) if ktimes else None
+    roof = None
+    if dom:
+        kms = ktimes[dom][0]
+        ach = abytes[dom] * N_RAYS * N_SAMPLES / (kms * 1e-3) / 1e9
+        roof = {'kernel': dom, 'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
+                'traffic': load_traffic(dom), 'kernel_ms': kms, 'algorithmic_bytes_per_sample': abytes[dom],
+                'peak_source': peak_src,
+                'all_kernels_ms': {k: round(v[0], 4) for k, v in ktimes.items()},
+                'all_kernels_frac': {k: abytes[k] * N_RAYS * N_SAMPLES / (v[0] * 1e-3) / 1e9 / peak for k, v in ktimes.items()}}
+    h2d = sum(t.numel() * t.element_size() for t in host)
+    line = {'metric': 'ray-samples/sec (fwd+bwd train step) 8192x512', 'value': value, 'unit': 'ray-samples/s', 'n_gpus': world,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': config, 'clocks': clk,
+            'e2e': {'value': samples_per_step / (ms_e2e / args.steps * 1e-3), 'unit': 'ray-samples/s',
+                    'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4, 'ms_per_step': ms_e2e / args.steps},
+            'gpu_launches': launches, 'roofline': roof,
+            'fwd_only': {'value': samples_per_step / (ms_fwd / args.steps * 1e-3), 'unit': 'ray-samples/s',
+                         'ms_per_step': ms_fwd / args.steps}}
+    if not args.no_cpu_baseline:
+        try:
+            v, sec = cpu_reference_step(flavor, kwargs, stepsize, args.cpu_rays, cores, 1, 1)
+            line['cpu_baseline'] = {'value': v, 'unit': 'ray-samples/s', 'cores': cores, 'kind': 'port',
+                                    'sample': f'{args.cpu_rays} of {N_RAYS} rays x {N_SAMPLES} samples, same grids, fwd+loss+bwd (no TV/Adam sweeps on CPU), '
+                                              f'{sec:.1f} s/step'}
+        except Exception as e:                                           # never lose the GPU numbers to a CPU-side problem
+            line['cpu_baseline'] = {'value': None, 'unit': 'ray-samples/s', 'cores': cores, 'kind': 'port', 'sample': f'failed: {e}'}
+    print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

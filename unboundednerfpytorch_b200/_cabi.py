@@ -122,3 +122,49 @@ def launch_count():
 
 def reset_launch_count():
     load().ubn_reset_launch_count()
+
+
+# ---- optional per-kernel CUDA-event timing (bench.py's roofline line) -------------------------------------
+class KernelTimer:
+    """Records CUDA events on the launching stream around selected C-ABI calls; near-zero overhead, no sync until
+    ``summary()``."""
+
+    def __init__(self):
+        self.records = {}
+
+    class _Range:
+        def __init__(self, timer, name):
+            self.timer, self.name = timer, name
+
+        def __enter__(self):
+            self.s = torch.cuda.Event(enable_timing=True)
+            self.e = torch.cuda.Event(enable_timing=True)
+            self.s.record()
+            return self
+
+        def __exit__(self, *a):
+            self.e.record()
+            self.timer.records.setdefault(self.name, []).append((self.s, self.e))
+            return False
+
+    def range(self, name):
+        return KernelTimer._Range(self, name)
+
+    def summary(self):
+        torch.cuda.synchronize()
+        return {k: (sum(s.elapsed_time(e) for s, e in v) / len(v), len(v)) for k, v in self.records.items()}
+
+
+class _Null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+TIMER = None
+
+
+def timed(name):
+    return TIMER.range(name) if TIMER is not None else _Null()

@@ -1,0 +1,84 @@
+"""Multi-GPU plumbing: one process per GPU, rays sharded, grids replicated.
+
+The reference has no distributed code on this path (0 collectives in the tree).  Rays are
+independent given the grids, so rendering needs no exchange until the frame is gathered, and training needs
+exactly one: the sum of the grid / rgbnet gradients before TV + Adam, after which every rank applies the
+identical update to its replica.  Works with the ``nccl`` backend on GPUs and ``gloo`` on CPU (tests).
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend=None):
+    """Initialise torch.distributed from torchrun's env (RANK / WORLD_SIZE / MASTER_*). Returns (rank, world, local_rank)."""
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if world > 1 and not dist.is_initialized():
+        backend = backend or ('nccl' if torch.cuda.is_available() else 'gloo')
+        if backend == 'nccl':
+            torch.cuda.set_device(local)
+            dist.init_process_group(backend=backend, device_id=torch.device('cuda', local))
+        else:
+            dist.init_process_group(backend=backend)
+    return rank, world, local
+
+
+def shard_range(n_items, rank, world):
+    """Contiguous shard [lo, hi) of n_items for `rank` (contiguous keeps image-space coherence of a frame's rays);
+    the first n_items % world ranks get one extra item."""
+    base, rem = divmod(n_items, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_rays(rank, world, *tensors):
+    lo, hi = shard_range(tensors[0].shape[0], rank, world)
+    return tuple(t[lo:hi] for t in tensors)
+
+
+def allreduce_grads(params, world=None):
+    """Sum gradients across ranks in place (one collective per tensor, large grids first).  With identical replicas and
+    ray-sharded batches this reproduces the single-process gradient of the concatenated batch up to fp32 reassociation."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return
+    handles = []
+    for p in sorted((p for p in params if p.grad is not None), key=lambda p: -p.numel()):
+        g = p.grad
+        if not g.is_contiguous() and g.dim() == 5:
+            # channels-last grids: reduce the dense storage in memory order (no copy)
+            g = g.permute(0, 2, 3, 4, 1)
+        handles.append(dist.all_reduce(g, op=dist.ReduceOp.SUM, async_op=True))
+    for h in handles:
+        h.wait()
+
+
+def gather_frame(local_out, n_total, rank, world, dst=0):
+    """Render path: every rank rendered its contiguous shard of a frame ([n_local, K] rgb/depth/...) -> all ranks get
+    the assembled [n_total, K] tensor (one all_gather of at most ceil(n_total/world) rows per rank)."""
+    if world == 1:
+        return local_out
+    per = (n_total + world - 1) // world
+    pad = torch.zeros(per, *local_out.shape[1:], dtype=local_out.dtype, device=local_out.device)
+    pad[:local_out.shape[0]] = local_out
+    bufs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(bufs, pad)
+    parts = []
+    for r in range(world):
+        lo, hi = shard_range(n_total, r, world)
+        parts.append(bufs[r][:hi - lo])
+    return torch.cat(parts, 0)
+
+
+def idw_composite(rgb, origins, centroid, power=4):
+    """Block-NeRF style compositing of per-block renders (eval_block_nerf.py:95-98,123-127): every rank holds one block,
+    renders the same rays, and the frame is sum_b w_b rgb_b / sum_b w_b with w_b = ||o - c_b||^-p (all-reduce SUM)."""
+    w = (origins - centroid).norm(dim=-1, keepdim=True).clamp_min(1e-8).pow(-power)
+    num = rgb * w
+    den = w.clone()
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(num)
+        dist.all_reduce(den)
+    return num / den

@@ -91,9 +91,10 @@ class March(torch.autograd.Function):
         scratch = torch.empty(N // 1024 + 4, dtype=torch.int64, device=dev)
         with ops._Guard(rays_o) as lib:
             st = stream_of(rays_o)
-            check(lib.ubn_march_density_fwd(ptr(rays_o), ptr(rays_d), ptr(t_table), ptr(density_grid), ddesc,
-                                            ptr(mask_world), cfg, c_i64(N), ptr(dens), ptr(alpha), ptr(weight), ptr(T),
-                                            ptr(flags), ptr(last), ptr(nkeep), st))
+            with _cabi.timed('march_density_fwd'):
+                check(lib.ubn_march_density_fwd(ptr(rays_o), ptr(rays_d), ptr(t_table), ptr(density_grid), ddesc,
+                                                ptr(mask_world), cfg, c_i64(N), ptr(dens), ptr(alpha), ptr(weight), ptr(T),
+                                                ptr(flags), ptr(last), ptr(nkeep), st))
             check(lib.ubn_exclusive_scan_i32(ptr(nkeep), c_i64(N), ptr(offsets), ptr(scratch), st))
             # compacted size: known without a host sync when nothing can be masked out
             M = N * S if dense_known else int(offsets[N].item())
@@ -106,10 +107,11 @@ class March(torch.autograd.Function):
             step_id = torch.empty(M, dtype=torch.int64, device=dev)
             o_t = torch.empty(M, **f32)
             o_inner = torch.empty(M, dtype=torch.bool, device=dev)
-            check(lib.ubn_march_feature_fwd(ptr(rays_o), ptr(rays_d), ptr(t_table), ptr(k0_grid), kdesc, cfg, c_i64(N),
-                                            ptr(flags), ptr(offsets), ptr(dens), ptr(alpha), ptr(weight), ptr(feat),
-                                            ptr(o_dens), ptr(o_alpha), ptr(o_weight), ptr(ray_id), ptr(step_id), ptr(o_t),
-                                            ptr(o_inner), st))
+            with _cabi.timed('march_feature_fwd'):
+                check(lib.ubn_march_feature_fwd(ptr(rays_o), ptr(rays_d), ptr(t_table), ptr(k0_grid), kdesc, cfg, c_i64(N),
+                                                ptr(flags), ptr(offsets), ptr(dens), ptr(alpha), ptr(weight), ptr(feat),
+                                                ptr(o_dens), ptr(o_alpha), ptr(o_weight), ptr(ray_id), ptr(step_id),
+                                                ptr(o_t), ptr(o_inner), st))
         ctx.save_for_backward(rays_o, rays_d, t_table, dens, alpha, weight, T, flags, last, offsets)
         ctx.cfg, ctx.ddesc, ctx.kdesc = cfg, ddesc, kdesc
         ctx.dmeta = (density_grid.shape, density_grid.stride())
@@ -130,12 +132,14 @@ class March(torch.autograd.Function):
             st = stream_of(rays_o)
             if ctx.needs_input_grad[1] and g_feat is not None:
                 grad_k = torch.empty_strided(*ctx.kmeta, dtype=torch.float32, device=dev).zero_()
-                check(lib.ubn_march_feature_bwd(ptr(rays_o), ptr(rays_d), ptr(t_table), ctx.kdesc, ctx.cfg, c_i64(N),
-                                                ptr(flags), ptr(offsets), ptr(g_feat), ptr(grad_k), st))
+                with _cabi.timed('march_feature_bwd'):
+                    check(lib.ubn_march_feature_bwd(ptr(rays_o), ptr(rays_d), ptr(t_table), ctx.kdesc, ctx.cfg, c_i64(N),
+                                                    ptr(flags), ptr(offsets), ptr(g_feat), ptr(grad_k), st))
             if ctx.needs_input_grad[0]:
                 grad_d = torch.empty_strided(*ctx.dmeta, dtype=torch.float32, device=dev).zero_()
-                check(lib.ubn_march_density_bwd(ptr(rays_o), ptr(rays_d), ptr(t_table), ctx.ddesc, ctx.cfg, c_i64(N),
-                                                ptr(dens), ptr(alpha), ptr(weight), ptr(T), ptr(flags), ptr(last),
-                                                ptr(offsets), ptr(g_weight), ptr(g_alpha), ptr(g_dens), ptr(g_last),
-                                                ptr(grad_d), st))
+                with _cabi.timed('march_density_bwd'):
+                    check(lib.ubn_march_density_bwd(ptr(rays_o), ptr(rays_d), ptr(t_table), ctx.ddesc, ctx.cfg, c_i64(N),
+                                                    ptr(dens), ptr(alpha), ptr(weight), ptr(T), ptr(flags), ptr(last),
+                                                    ptr(offsets), ptr(g_weight), ptr(g_alpha), ptr(g_dens), ptr(g_last),
+                                                    ptr(grad_d), st))
         return grad_d, grad_k, None, None, None, None, None, None, None, None

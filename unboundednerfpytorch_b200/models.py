@@ -498,3 +498,132 @@ class DirectContractedVoxGO(_ContractedBase):
         rgb = self._shade(k0, viewdirs, ray_id)
         return self._finish(N, dev, weights, alphainv_last, density, alpha, rgb, ray_id, step_id, t, inner_mask, n_max,
                             is_train, render_kwargs)
+
+
+# ======================================================================================================
+class DirectVoxGO(nn.Module):
+    """Bounded-scene model (FourierGrid/dvgo.py:26-425): ragged AABB sampling (sample_pts_on_rays) instead of the
+    contracted schedule; depth = sum w * step_id.  Composed from the drop-in ops (BASELINE config 1 family)."""
+
+    def __init__(self, xyz_min, xyz_max, num_voxels=0, num_voxels_base=0, alpha_init=None, mask_cache_path=None,
+                 mask_cache_thres=1e-3, mask_cache_world_size=None, fast_color_thres=0, density_type='DenseGrid',
+                 k0_type='DenseGrid', density_config={}, k0_config={}, rgbnet_dim=0, rgbnet_direct=False,
+                 rgbnet_full_implicit=False, rgbnet_depth=3, rgbnet_width=128, viewbase_pe=4, **kwargs):
+        super().__init__()
+        if rgbnet_full_implicit:
+            raise NotImplementedError('rgbnet_full_implicit is outside the hot-path scope')
+        self.register_buffer('xyz_min', torch.as_tensor(np.asarray(xyz_min), dtype=torch.float32))
+        self.register_buffer('xyz_max', torch.as_tensor(np.asarray(xyz_max), dtype=torch.float32))
+        self.fast_color_thres = fast_color_thres
+        self.num_voxels_base = num_voxels_base
+        self.voxel_size_base = _cube_root_size(self.xyz_min, self.xyz_max, num_voxels_base)
+        self.alpha_init = alpha_init
+        self.register_buffer('act_shift', torch.FloatTensor([np.log(1 / (1 - alpha_init) - 1)]))
+        self._set_grid_resolution(num_voxels)
+        self.density_type, self.density_config, self.k0_type, self.k0_config = density_type, density_config, k0_type, k0_config
+        self.density = G.DenseGrid(channels=1, world_size=self.world_size, xyz_min=self.xyz_min, xyz_max=self.xyz_max)
+        self.rgbnet_kwargs = dict(rgbnet_dim=rgbnet_dim, rgbnet_direct=rgbnet_direct, rgbnet_full_implicit=rgbnet_full_implicit,
+                                  rgbnet_depth=rgbnet_depth, rgbnet_width=rgbnet_width, viewbase_pe=viewbase_pe)
+        self.rgbnet_direct = rgbnet_direct
+        if rgbnet_dim <= 0:
+            self.k0_dim, self.rgbnet = 3, None
+        else:
+            self.k0_dim = rgbnet_dim
+            self.register_buffer('viewfreq', torch.FloatTensor([(2 ** i) for i in range(viewbase_pe)]))
+            dim0 = 3 + 3 * viewbase_pe * 2 + (rgbnet_dim if rgbnet_direct else rgbnet_dim - 3)
+            self.rgbnet = _make_rgbnet(dim0, rgbnet_width, rgbnet_depth)
+        self.k0 = G.DenseGrid(channels=self.k0_dim, world_size=self.world_size, xyz_min=self.xyz_min, xyz_max=self.xyz_max)
+        self.mask_cache_path, self.mask_cache_thres = mask_cache_path, mask_cache_thres
+        if mask_cache_world_size is None:
+            mask_cache_world_size = self.world_size
+        if mask_cache_path:
+            raise NotImplementedError('coarse-checkpoint mask cache needs a device at construction; build MaskGrid(path=...) '
+                                      'and assign model.mask_cache instead')
+        self.mask_cache = G.MaskGrid(path=None, mask=torch.ones([int(v) for v in mask_cache_world_size], dtype=torch.bool),
+                                     xyz_min=self.xyz_min, xyz_max=self.xyz_max)
+
+    def _set_grid_resolution(self, num_voxels):
+        self.num_voxels = num_voxels
+        self.voxel_size = _cube_root_size(self.xyz_min, self.xyz_max, num_voxels)
+        self.world_size = ((self.xyz_max - self.xyz_min) / self.voxel_size).long()
+        self.voxel_size_ratio = self.voxel_size / self.voxel_size_base
+
+    def get_kwargs(self):
+        return {
+            'xyz_min': self.xyz_min.cpu().numpy(), 'xyz_max': self.xyz_max.cpu().numpy(), 'num_voxels': self.num_voxels,
+            'num_voxels_base': self.num_voxels_base, 'alpha_init': self.alpha_init, 'voxel_size_ratio': self.voxel_size_ratio,
+            'mask_cache_path': self.mask_cache_path, 'mask_cache_thres': self.mask_cache_thres,
+            'mask_cache_world_size': list(self.mask_cache.mask.shape), 'fast_color_thres': self.fast_color_thres,
+            'density_type': self.density_type, 'k0_type': self.k0_type, 'density_config': self.density_config,
+            'k0_config': self.k0_config, **self.rgbnet_kwargs,
+        }
+
+    def activate_density(self, density, interval=None):
+        interval = interval if interval is not None else self.voxel_size_ratio
+        shape = density.shape
+        return Raw2Alpha.apply(density.flatten().contiguous(), self.act_shift, interval).reshape(shape)
+
+    def density_total_variation_add_grad(self, weight, dense_mode):
+        w = weight * float(self.world_size.max()) / 128
+        self.density.total_variation_add_grad(w, w, w, dense_mode)
+
+    def k0_total_variation_add_grad(self, weight, dense_mode):
+        w = weight * float(self.world_size.max()) / 128
+        self.k0.total_variation_add_grad(w, w, w, dense_mode)
+
+    def sample_ray(self, rays_o, rays_d, near, far, stepsize, **render_kwargs):
+        """dvgo.py:306-328."""
+        from . import ops
+        far = 1e9
+        stepdist = stepsize * float(self.voxel_size)
+        ray_pts, mask_outbbox, ray_id, step_id, N_steps, t_min, t_max = ops.sample_pts_on_rays(
+            rays_o.contiguous(), rays_d.contiguous(), self.xyz_min, self.xyz_max, near, far, stepdist)
+        mask_inbbox = ~mask_outbbox
+        return ray_pts[mask_inbbox], ray_id[mask_inbbox], step_id[mask_inbbox]
+
+    def hit_coarse_geo(self, rays_o, rays_d, near, far, stepsize, **render_kwargs):
+        """dvgo.py:292-304."""
+        from . import ops
+        shape = rays_o.shape[:-1]
+        rays_o = rays_o.reshape(-1, 3).contiguous()
+        rays_d = rays_d.reshape(-1, 3).contiguous()
+        ray_pts, mask_outbbox, ray_id = ops.sample_pts_on_rays(rays_o, rays_d, self.xyz_min, self.xyz_max, near, 1e9,
+                                                               stepsize * float(self.voxel_size))[:3]
+        mask_inbbox = ~mask_outbbox
+        hit = torch.zeros([len(rays_o)], dtype=torch.bool, device=rays_o.device)
+        hit[ray_id[mask_inbbox][self.mask_cache(ray_pts[mask_inbbox])]] = 1
+        return hit.reshape(shape)
+
+    def forward(self, rays_o, rays_d, viewdirs, global_step=None, **render_kwargs):
+        assert len(rays_o.shape) == 2 and rays_o.shape[-1] == 3, 'Only suuport point queries in [N, 3] format'
+        N, dev = len(rays_o), rays_o.device
+        ray_pts, ray_id, step_id = self.sample_ray(rays_o=rays_o, rays_d=rays_d, **render_kwargs)
+        interval = render_kwargs['stepsize'] * self.voxel_size_ratio
+        if self.mask_cache is not None:
+            mask = self.mask_cache(ray_pts)
+            ray_pts, ray_id, step_id = ray_pts[mask], ray_id[mask], step_id[mask]
+        density = self.density(ray_pts)
+        alpha = self.activate_density(density, interval)
+        if self.fast_color_thres > 0:
+            mask = (alpha > self.fast_color_thres)
+            ray_pts, ray_id, step_id, density, alpha = ray_pts[mask], ray_id[mask], step_id[mask], density[mask], alpha[mask]
+        weights, alphainv_last = Alphas2Weights.apply(alpha.contiguous(), ray_id.contiguous(), N)
+        if self.fast_color_thres > 0:
+            mask = (weights > self.fast_color_thres)
+            weights, alpha, ray_pts, ray_id, step_id = weights[mask], alpha[mask], ray_pts[mask], ray_id[mask], step_id[mask]
+        k0 = self.k0(ray_pts)
+        if self.rgbnet is None:
+            rgb = torch.sigmoid(k0)
+        else:
+            k0_view = k0 if self.rgbnet_direct else k0[:, 3:]
+            emb = _view_embed(viewdirs, self.viewfreq).flatten(0, -2)[ray_id]
+            logit = self.rgbnet(torch.cat([k0_view, emb], -1))
+            rgb = torch.sigmoid(logit if self.rgbnet_direct else logit + k0[:, :3])
+        rgb_marched = torch.zeros([N, 3], device=dev).index_add_(0, ray_id, weights.unsqueeze(-1) * rgb)
+        rgb_marched = rgb_marched + alphainv_last.unsqueeze(-1) * render_kwargs['bg']
+        ret = {'alphainv_last': alphainv_last, 'weights': weights, 'rgb_marched': rgb_marched, 'raw_alpha': alpha,
+               'raw_rgb': rgb, 'ray_id': ray_id}
+        if render_kwargs.get('render_depth', False):
+            with torch.no_grad():
+                ret['depth'] = torch.zeros([N], device=dev).index_add_(0, ray_id, weights * step_id)
+        return ret
