@@ -106,6 +106,13 @@ int ubn_alpha2weight_backward(const float* alpha, const float* weight, const flo
                               int64_t n_pts, int64_t n_rays, const float* grad_weights,
                               const float* grad_last, float* grad, void* stream);
 
+/* torch_scatter.segment_coo(src, index, out=zeros, reduce='sum') on a sorted index, as the reference uses it for
+ * the composite (dvgo.py:401,418; dcvgo.py:345,354,377; FourierGrid_model.py:640,666): out[r, 0:k] = sum of the
+ * rows src[i, 0:k] with ray_id[i] == r (k <= 4).  Deterministic (no atomics).  i_start / i_end: int64[n_rays] scratch
+ * that receives the segment bounds.  out[n_rays, k] is fully written (0 for rays without points). */
+int ubn_segment_sum(const float* src, int64_t k, const int64_t* ray_id, int64_t n_pts, int64_t n_rays,
+                    int64_t* i_start, int64_t* i_end, float* out, void* stream);
+
 /* ---- total_variation_cuda (FourierGrid/cuda/total_variation.cpp:22-24) ----------------------- */
 /* total_variation_cuda.total_variation_add_grad   total_variation.cpp:13-20 / total_variation_kernel.cu:14-67.
  * param/grad: logical [lead, sz_i, sz_j, sz_k, inner] row-major in MEMORY.  Reference layout

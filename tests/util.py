@@ -13,6 +13,8 @@ def load_golden(name):
 
 
 def assert_close(a, b, rtol=RTOL, atol=1e-6, what=''):
+    if isinstance(rtol, str):              # allow assert_close(a, b, 'name') like assert_equal
+        rtol, what = RTOL, rtol
     a, b = a.detach().float().cpu(), b.detach().float().cpu()
     assert a.shape == b.shape, f'{what}: shape {tuple(a.shape)} vs {tuple(b.shape)}'
     if a.numel() == 0:

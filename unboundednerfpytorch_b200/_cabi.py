@@ -54,6 +54,7 @@ _SIGNATURES = {
     'ubn_raw2alpha_backward': [c_p, c_p, c_f, c_p, c_i64, c_p, c_p],
     'ubn_alpha2weight': [c_p, c_p, c_i64, c_i64, c_p, c_p, c_p, c_p, c_p, c_p],
     'ubn_alpha2weight_backward': [c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_i64, c_p, c_p, c_p, c_p],
+    'ubn_segment_sum': [c_p, c_i64, c_p, c_i64, c_i64, c_p, c_p, c_p, c_p],
     'ubn_total_variation_add_grad': [c_p, c_p, c_f, c_f, c_f, c_i64, c_i64, c_i64, c_i64, c_i64, c_int, c_p],
     'ubn_adam_upd': [c_p, c_p, c_p, c_p, c_p, c_i64, c_int, c_f, c_f, c_f, c_f, c_int, c_p],
     'ubn_tv_adam_fused': [c_p, c_p, c_p, c_p, c_f, c_f, c_f, c_i64, c_i64, c_i64, c_i64, c_i64, c_int, c_int,

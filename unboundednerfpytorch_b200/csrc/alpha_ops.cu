@@ -276,3 +276,63 @@ int ubn_alpha2weight_backward(const float* alpha, const float* weight, const flo
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// segment_sum: out[r, :] = sum over the (sorted) segment of ray r of src[i, :]  -- the reduction the
+// reference takes from torch_scatter.segment_coo(reduce='sum') (dvgo.py:401,418; dcvgo.py:345,354,377;
+// FourierGrid_model.py:640,666).  One warp per ray: lanes stride over the segment (coalesced rows of K
+// floats), per-lane partial sums, xor-shuffle tree -> deterministic (no atomics), any K <= 4.
+// ------------------------------------------------------------------------------------------------
+namespace ubn {
+
+template <int K>
+__global__ void __launch_bounds__(128) k_segment_sum(const float* __restrict__ src, const int64_t* __restrict__ i_start,
+                                                     const int64_t* __restrict__ i_end, int64_t n_rays,
+                                                     float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t ray = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (ray >= n_rays) return;
+  const int64_t s = i_start[ray], e = i_end[ray];
+  float acc[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) acc[k] = 0.f;
+  for (int64_t i = s + lane; i < e; i += 32) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc[k] += src[i * K + k];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) out[ray * K + k] = acc[k];
+  }
+}
+
+}  // namespace ubn
+
+extern "C" int ubn_segment_sum(const float* src, int64_t k, const int64_t* ray_id, int64_t n_pts, int64_t n_rays,
+                               int64_t* i_start, int64_t* i_end, float* out, void* stream) {
+  using namespace ubn;
+  cudaStream_t st = as_stream(stream);
+  if (n_rays <= 0) return 0;
+  if (k < 1 || k > 4) return finish(cudaErrorInvalidValue);
+  // bounds (empty rays keep [0,0) -> sum 0); alphainv_last slot of k_init_rays is reused as a dummy via out
+  k_init_rays<<<blocks_for(n_rays, 256), 256, 0, st>>>(n_rays, out, i_start, i_end);
+  UBN_LAUNCH_CHECK();
+  if (n_pts > 0) {
+    k_segment_bounds<<<blocks_for(n_pts, 256), 256, 0, st>>>(ray_id, n_pts, i_start, i_end);
+    UBN_LAUNCH_CHECK();
+  }
+  const unsigned nb = blocks_for(n_rays, 4);
+  switch (k) {
+    case 1: k_segment_sum<1><<<nb, 128, 0, st>>>(src, i_start, i_end, n_rays, out); break;
+    case 2: k_segment_sum<2><<<nb, 128, 0, st>>>(src, i_start, i_end, n_rays, out); break;
+    case 3: k_segment_sum<3><<<nb, 128, 0, st>>>(src, i_start, i_end, n_rays, out); break;
+    default: k_segment_sum<4><<<nb, 128, 0, st>>>(src, i_start, i_end, n_rays, out); break;
+  }
+  UBN_LAUNCH_CHECK();
+  return 0;
+}

@@ -120,10 +120,14 @@ static AdamHyper make_hyper(int step, float beta1, float beta2, float lr, float 
 
 template <int kMode>
 __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, float perlr, const AdamHyper& h) {
-  m = h.beta1 * m + (1 - h.beta1) * g;
-  v = h.beta2 * v + (1 - h.beta2) * g * g;
-  if (kMode == 2) p -= h.step_size * perlr * m / (sqrtf(v) + h.eps);
-  else            p -= h.step_size * m / (sqrtf(v) + h.eps);
+  // Spelled with explicit roundings so that the fma contraction is the one nvcc picks for the reference's
+  // expressions (verified in its SASS: m' = fma(m, b1, (1-b1)*g); v' = fma(v, b2, ((1-b2)*g)*g)) -> bit-identical
+  // parameters / moments to the reference extension on the same inputs.
+  m = __fmaf_rn(m, h.beta1, __fmul_rn(__fsub_rn(1.f, h.beta1), g));
+  v = __fmaf_rn(v, h.beta2, __fmul_rn(__fmul_rn(__fsub_rn(1.f, h.beta2), g), g));
+  const float den = __fadd_rn(__fsqrt_rn(v), h.eps);
+  if (kMode == 2) p = __fsub_rn(p, __fdiv_rn(__fmul_rn(__fmul_rn(h.step_size, perlr), m), den));
+  else            p = __fsub_rn(p, __fdiv_rn(__fmul_rn(h.step_size, m), den));
 }
 
 // vectorised (float4) main body + scalar tail

@@ -55,13 +55,22 @@ struct Ray {
   float ox, oy, oz, dx, dy, dz;   // normalised origin, unit direction
 };
 
+// ||v|| exactly as torch's CUDA reduction evaluates x.norm(dim=-1) on 3-vectors: the lanes of the reduced
+// dimension are combined by a shuffle tree, i.e. sqrt((x*x + z*z) + y*y) with every product and sum rounded
+// separately (probed on B200: 0 mismatches in 2^20 random vectors; the "natural" orders mismatch in 12-15 %).
+// The reference runs these norms as torch ops (dcvgo.py:240,253,288; FourierGrid_model.py:523,537), so matching
+// them bit-for-bit keeps the threshold decisions downstream (inner mask, cumdist, mask-cache rounding) identical.
+__device__ __forceinline__ float norm3_torch(float x, float y, float z) {
+  return sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(z, z)), __fmul_rn(y, y)));
+}
+
 // rays_o = (o - center) / radius ; rays_d = d / ||d||     (torch elementwise: no fma contraction)
 __device__ __forceinline__ Ray load_ray(const float* __restrict__ o, const float* __restrict__ d, const MarchParams& p) {
   Ray r;
   r.ox = __fdiv_rn(__fsub_rn(o[0], p.cx), p.rx);
   r.oy = __fdiv_rn(__fsub_rn(o[1], p.cy), p.ry);
   r.oz = __fdiv_rn(__fsub_rn(o[2], p.cz), p.rz);
-  const float n = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2])));
+  const float n = norm3_torch(d[0], d[1], d[2]);
   r.dx = __fdiv_rn(d[0], n);
   r.dy = __fdiv_rn(d[1], n);
   r.dz = __fdiv_rn(d[2], n);
@@ -74,7 +83,7 @@ __device__ __forceinline__ bool sample_point(const Ray& r, float t, const MarchP
   y = __fadd_rn(r.oy, __fmul_rn(r.dy, t));
   z = __fadd_rn(r.oz, __fmul_rn(r.dz, t));
   float n;
-  if (p.l2norm) n = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));
+  if (p.l2norm) n = norm3_torch(x, y, z);
   else          n = fmaxf(fmaxf(fabsf(x), fabsf(y)), fabsf(z));
   const bool inner = (n <= 1.f);
   if (!inner) {
@@ -138,7 +147,7 @@ __global__ void __launch_bounds__(32 * kMarchWarps) k_march_density_fwd(
         float x1, y1, z1;
         sample_point(r, t_table[s + 1], p, x1, y1, z1);
         const float ex = __fsub_rn(x1, x), ey = __fsub_rn(y1, y), ez = __fsub_rn(z1, z);
-        dist = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez)));
+        dist = norm3_torch(ex, ey, ez);
       }
       bool over_here = false;   // result for dist index s (applies to sample s+1)
       const int n_d = min(32, S - 1 - base);

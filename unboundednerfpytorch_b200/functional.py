@@ -85,9 +85,44 @@ class Alphas2Weights(torch.autograd.Function):
         return grad, None, None
 
 
+class SegmentSum(torch.autograd.Function):
+    """out[r] = sum of src rows whose (sorted) ray_id == r.  Forward: deterministic warp-per-ray reduction kernel
+    (libubnerf_b200: ubn_segment_sum); backward: grad_src[i] = grad_out[ray_id[i]] (a gather)."""
+
+    @staticmethod
+    def forward(ctx, src, ray_id, n_rays):
+        from . import _cabi
+        from ._cabi import c_i64, check, ptr, stream_of
+        if not src.is_cuda:
+            raise RuntimeError('src must be a CUDA tensor')
+        squeeze = src.dim() == 1
+        s2 = (src.unsqueeze(-1) if squeeze else src).contiguous().float()
+        k = s2.shape[1]
+        ray_id = ray_id.contiguous()
+        out = torch.empty(n_rays, k, dtype=torch.float32, device=src.device)
+        i_s = torch.empty(n_rays, dtype=torch.int64, device=src.device)
+        i_e = torch.empty(n_rays, dtype=torch.int64, device=src.device)
+        with ops._Guard(src) as lib:
+            check(lib.ubn_segment_sum(ptr(s2), c_i64(k), ptr(ray_id), c_i64(s2.shape[0]), c_i64(n_rays), ptr(i_s), ptr(i_e),
+                                      ptr(out), stream_of(src)))
+        ctx.save_for_backward(ray_id)
+        ctx.squeeze = squeeze
+        return out.squeeze(-1) if squeeze else out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        (ray_id,) = ctx.saved_tensors
+        return g[ray_id], None, None
+
+
+def segment_sum(src, ray_id, n_rays):
+    return SegmentSum.apply(src, ray_id, n_rays)
+
+
 def segment_coo(src, index, out, reduce='sum'):
     """torch_scatter.segment_coo(reduce='sum') for sorted ``index`` (call sites dvgo.py:401,418;
-    dcvgo.py:345,354,377; FourierGrid_model.py:640,666): accumulate rows of ``src`` into ``out``."""
+    dcvgo.py:345,354,377; FourierGrid_model.py:640,666): out += per-segment sums of the rows of ``src``."""
     if reduce != 'sum':
         raise NotImplementedError(reduce)
-    return out.index_add_(0, index, src)
+    return out + segment_sum(src, index, out.shape[0]).reshape(out.shape)

@@ -18,7 +18,7 @@ import torch.nn.functional as F
 
 from . import grid as G
 from . import march
-from .functional import Alphas2Weights, Raw2Alpha, host_scalar
+from .functional import Alphas2Weights, Raw2Alpha, host_scalar, segment_sum
 
 
 def _cube_root_size(xyz_min, xyz_max, num_voxels):
@@ -288,7 +288,7 @@ class FourierGridModel(_ContractedBase):
         (weights, alphainv_last, alpha, density, k0, ray_id, step_id, t, inner), t_table = self._march(
             rays_o, rays_d, render_kwargs['stepsize'])
         rgb = self._shade(k0, viewdirs, ray_id)
-        rgb_marched = torch.zeros([N, 3], device=rays_o.device).index_add_(0, ray_id, weights.unsqueeze(-1) * rgb)
+        rgb_marched = segment_sum(weights.unsqueeze(-1) * rgb, ray_id, N)
         if render_kwargs.get('rand_bkgd', False):
             rgb_marched = rgb_marched + alphainv_last.unsqueeze(-1) * torch.rand_like(rgb_marched)
         s = 1 - 1 / (1 + t)
@@ -297,7 +297,7 @@ class FourierGridModel(_ContractedBase):
                't': t, 's': s}
         if render_kwargs.get('render_depth', False):
             with torch.no_grad():
-                ret['depth'] = torch.zeros([N], device=rays_o.device).index_add_(0, ray_id, weights * s)
+                ret['depth'] = segment_sum(weights * s, ray_id, N)
         return ret
 
     def forward_ops(self, rays_o, rays_d, viewdirs, global_step=None, is_train=False, **render_kwargs):
@@ -330,7 +330,7 @@ class FourierGridModel(_ContractedBase):
             t, density, alpha = t.reshape(-1), density.reshape(-1), alpha.reshape(-1)
         k0 = self.k0(ray_pts)
         rgb = self._shade(k0, viewdirs, ray_id)
-        rgb_marched = torch.zeros([N, 3], device=dev).index_add_(0, ray_id, weights.unsqueeze(-1) * rgb)
+        rgb_marched = segment_sum(weights.unsqueeze(-1) * rgb, ray_id, N)
         if render_kwargs.get('rand_bkgd', False):
             rgb_marched = rgb_marched + alphainv_last.unsqueeze(-1) * torch.rand_like(rgb_marched)
         s = 1 - 1 / (1 + t)
@@ -338,7 +338,7 @@ class FourierGridModel(_ContractedBase):
                'raw_alpha': alpha, 'raw_rgb': rgb, 'ray_id': ray_id, 'step_id': step_id, 'n_max': n_max, 't': t, 's': s}
         if render_kwargs.get('render_depth', False):
             with torch.no_grad():
-                ret['depth'] = torch.zeros([N], device=dev).index_add_(0, ray_id, weights * s)
+                ret['depth'] = segment_sum(weights * s, ray_id, N)
         return ret
 
 
@@ -436,19 +436,19 @@ class DirectContractedVoxGO(_ContractedBase):
 
     def _finish(self, N, dev, weights, alphainv_last, density, alpha, rgb, ray_id, step_id, t, inner_mask, n_max,
                 is_train, render_kwargs):
-        rgb_marched = torch.zeros([N, 3], device=dev).index_add_(0, ray_id, weights.unsqueeze(-1) * rgb)
+        rgb_marched = segment_sum(weights.unsqueeze(-1) * rgb, ray_id, N)
         if render_kwargs.get('rand_bkgd', False) and is_train:
             rgb_marched = rgb_marched + alphainv_last.unsqueeze(-1) * torch.rand_like(rgb_marched)
         else:
             rgb_marched = rgb_marched + alphainv_last.unsqueeze(-1) * render_kwargs['bg']
-        wsum_mid = torch.zeros([N], device=dev).index_add_(0, ray_id[inner_mask], weights[inner_mask])
+        wsum_mid = segment_sum(weights[inner_mask], ray_id[inner_mask], N)
         s = 1 - 1 / (1 + t)
         ret = {'alphainv_last': alphainv_last, 'weights': weights, 'wsum_mid': wsum_mid, 'rgb_marched': rgb_marched,
                'raw_density': density, 'raw_alpha': alpha, 'raw_rgb': rgb, 'ray_id': ray_id, 'step_id': step_id,
                'n_max': n_max, 't': t, 's': s}
         if render_kwargs.get('render_depth', False):
             with torch.no_grad():
-                ret['depth'] = torch.zeros([N], device=dev).index_add_(0, ray_id, weights * s)
+                ret['depth'] = segment_sum(weights * s, ray_id, N)
         return ret
 
     def forward(self, rays_o, rays_d, viewdirs, global_step=None, is_train=False, **render_kwargs):
@@ -619,11 +619,11 @@ class DirectVoxGO(nn.Module):
             emb = _view_embed(viewdirs, self.viewfreq).flatten(0, -2)[ray_id]
             logit = self.rgbnet(torch.cat([k0_view, emb], -1))
             rgb = torch.sigmoid(logit if self.rgbnet_direct else logit + k0[:, :3])
-        rgb_marched = torch.zeros([N, 3], device=dev).index_add_(0, ray_id, weights.unsqueeze(-1) * rgb)
+        rgb_marched = segment_sum(weights.unsqueeze(-1) * rgb, ray_id, N)
         rgb_marched = rgb_marched + alphainv_last.unsqueeze(-1) * render_kwargs['bg']
         ret = {'alphainv_last': alphainv_last, 'weights': weights, 'rgb_marched': rgb_marched, 'raw_alpha': alpha,
                'raw_rgb': rgb, 'ray_id': ray_id}
         if render_kwargs.get('render_depth', False):
             with torch.no_grad():
-                ret['depth'] = torch.zeros([N], device=dev).index_add_(0, ray_id, weights * step_id)
+                ret['depth'] = segment_sum(weights * step_id, ray_id, N)
         return ret
