@@ -233,6 +233,28 @@ int ubn_march_density_bwd(const float* rays_o, const float* rays_d, const float*
                           const float* g_weight, const float* g_alpha, const float* g_density,
                           const float* g_last, float* grad_density_grid, void* stream);
 
+/* ---- rgbnet: rgb = sigmoid(rgbnet(cat[k0_feat, viewdirs_emb[ray_id]])) (FourierGrid_model.py:231-242,631-637;
+ *      dcvgo.py:103-114,337-342) for the 3-layer, width-128, 12-feature configuration every shipped config uses.
+ * The per-ray part of layer 1 is hoisted by the host: view_bias[n_rays,128] = emb(viewdirs) . W1[:,12:]^T + b1, so the
+ * kernel sees W1k = W1[:, :12] ([128,12] row-major), W2 [128,128], b2 [128], W3 [3,128], b3 [3] (nn.Linear layout).
+ * fp32 arithmetic; activations stay on chip.  h1_save / h2_save: NULL for inference, or [n_pts,128] buffers that
+ * receive the post-ReLU hidden activations for ubn_rgbnet_bwd. */
+int ubn_rgbnet_fwd(const float* feat, const float* view_bias, const int64_t* ray_id, const float* W1k, const float* W2,
+                   const float* b2, const float* W3, const float* b3, int64_t n_pts, float* rgb, float* h1_save,
+                   float* h2_save, void* stream);
+/* Same contract on the tensor cores: the two 128-wide layers run as tcgen05.mma (kind::tf32, M=128 sample tiles,
+ * accumulators and the layer-2 A operand in tensor memory).  single_pass = 0: 3xTF32 split accumulation (fp32-grade,
+ * meets the 1e-5 parity gate); single_pass = 1: one TF32 pass (~1e-3 relative; fast preview only). */
+int ubn_rgbnet_fwd_tc(const float* feat, const float* view_bias, const int64_t* ray_id, const float* W1k, const float* W2,
+                      const float* b2, const float* W3, const float* b3, int64_t n_pts, float* rgb, float* h1_save,
+                      float* h2_save, int single_pass, void* stream);
+/* Backward of the above wrt feat (grad_feat[n_pts,12], fully written) and, ACCUMULATED into zero-initialised buffers,
+ * view_bias (grad_view_bias[n_rays,128]), W1k, W2, b2, W3, b3.  ray_id must be sorted. */
+int ubn_rgbnet_bwd(const float* feat, const int64_t* ray_id, const float* W1k, const float* W2, const float* W3,
+                   const float* rgb, const float* h1_save, const float* h2_save, const float* grad_rgb, int64_t n_pts,
+                   float* grad_feat, float* grad_view_bias, float* grad_W1k, float* grad_W2, float* grad_b2,
+                   float* grad_W3, float* grad_b3, void* stream);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

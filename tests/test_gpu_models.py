@@ -115,7 +115,11 @@ def test_model_vs_cpu_oracle_seeded(oracle, flavor, world, F_, thres, mean, norm
     for k in FLOAT_KEYS:
         # raw_density: interpolated N(0,1) grid values that cancel towards 0 in the slab mean; its error is set by fp32
         # rounding of the sin/cos-warped sample coordinate (x (X-1)/2 x grid slope), i.e. absolute, not relative
-        atol = 5e-5 if k == 'raw_density' else 2e-6
+        # ... and of the ray direction itself: torch-CPU and torch-CUDA evaluate d/||d|| differently in the last bit, the
+        # kernel follows torch-CUDA (what the reference runs), the oracle runs torch-CPU; one ulp of d is amplified by
+        # t (<= 192) x 2^(F-1) x (X-1)/2 on the way to a voxel index.  Tight raw_density parity is asserted against the
+        # op-by-op CUDA composition in test_full_size_properties_8192x512.
+        atol = (2e-3 if F_ >= 3 else 5e-5) if k == 'raw_density' else 2e-6
         assert_close(ret[k], ref[k].reshape(ret[k].shape), rtol=2e-5, atol=atol, what=k)
     g = torch.Generator().manual_seed(5)
     lw = dict(rgb=torch.randn(N, 3, generator=g), last=torch.randn(N, generator=g))
@@ -126,7 +130,7 @@ def test_model_vs_cpu_oracle_seeded(oracle, flavor, world, F_, thres, mean, norm
         # scatter weights inherit the fp32 rounding of the (sin/cos-warped, x(X-1)/2) sample coordinate: up to ~1e-5..1e-4
         # absolute on a trilinear weight for the 2^3-frequency slabs, times the per-sample gradient (~ scale)
         scale = theirs.abs().max().item() + 1e-12
-        assert_close(mine, theirs, rtol=5e-5, atol=(3e-4 if F_ >= 3 else 1e-5) * scale + 1e-9, what='grad ' + nm)
+        assert_close(mine, theirs, rtol=5e-5, atol=(1e-3 if F_ >= 3 else 1e-5) * scale + 1e-9, what='grad ' + nm)
 
 
 @pytest.mark.parametrize('flavor', ['fouriergrid', 'dcvgo'])
@@ -152,7 +156,7 @@ def test_full_size_properties_8192x512(flavor):
     in_b, in_a = torch.isin(ka, kb), torch.isin(kb, ka)
     flips = int((~in_b).sum() + (~in_a).sum())
     assert flips <= 1e-4 * ka.numel(), f'{flips} membership flips out of {ka.numel()}'
-    for k in ('weights', 'raw_alpha'):
+    for k in ('weights', 'raw_alpha', 'raw_density'):
         assert_close(a[k][in_b], b[k].reshape(-1)[in_a], rtol=2e-5, atol=2e-6, what=k + ' fused vs ops')
     for k in ('rgb_marched', 'alphainv_last', 'depth'):
         bad = ((a[k] - b[k]).abs() > 2e-6 + 2e-5 * b[k].abs()).reshape(N, -1).any(-1)
@@ -192,3 +196,36 @@ def test_training_step_reduces_loss():
         losses.append(loss.item())
     assert losses[-1] < 0.999 * losses[0] and all(b <= a * 1.0001 for a, b in zip(losses, losses[1:])), losses
     assert all(torch.isfinite(p).all() for p in student.parameters())
+
+
+@pytest.mark.parametrize('mode', ['simt', 'tc3', 'tc1'])
+def test_fused_rgbnet_vs_torch(mode, monkeypatch):
+    """csrc/shade.cu (fp32 FFMA) and csrc/shade_tc.cu (tcgen05: 3xTF32 fp32-grade, single-pass TF32 preview) vs the torch
+    nn.Sequential they replace: forward and every gradient."""
+    from unboundednerfpytorch_b200 import models, shade as shade_mod
+    monkeypatch.setattr(shade_mod, 'MODE', mode)
+    fwd_tol = dict(rtol=1e-5, atol=1e-6) if mode != 'tc1' else dict(rtol=5e-3, atol=5e-3)
+    torch.manual_seed(3)
+    net = models._make_rgbnet(39, 128, 3).to(DEV)
+    with torch.no_grad():
+        net[3].bias.normal_(0, 0.1)
+    for M, n_rays in ((1, 1), (77, 5), (300, 300), (20000, 37)):
+        g = torch.Generator().manual_seed(M)
+        k0 = torch.randn(M, 12, generator=g).to(DEV).requires_grad_(True)
+        emb = torch.randn(n_rays, 27, generator=g).to(DEV)
+        ray_id = torch.sort(torch.randint(0, n_rays, (M,), generator=g))[0].to(DEV)
+        gr = torch.randn(M, 3, generator=g).to(DEV)
+        ref = torch.sigmoid(net(torch.cat([k0, emb[ray_id]], -1)))
+        net.zero_grad(); k0.grad = None
+        (ref * gr).sum().backward()
+        want = [k0.grad.clone()] + [p.grad.clone() for p in net.parameters()]
+        net.zero_grad(); k0.grad = None
+        out = shade_mod.shade(net, k0, emb, ray_id)
+        assert_close(out, ref, what=f'rgb M={M} {mode}', **fwd_tol)
+        if mode == 'tc1':
+            continue
+        (out * gr).sum().backward()
+        got = [k0.grad] + [p.grad for p in net.parameters()]
+        for a, b, nm in zip(got, want, ['k0', 'W1', 'b1', 'W2', 'b2', 'W3', 'b3']):
+            scale = b.abs().max().item() + 1e-12
+            assert_close(a, b, rtol=2e-5, atol=2e-6 * scale + 1e-9, what=f'grad {nm} M={M}')

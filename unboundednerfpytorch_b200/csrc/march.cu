@@ -87,7 +87,9 @@ __device__ __forceinline__ bool sample_point(const Ray& r, float t, const MarchP
   else          n = fmaxf(fmaxf(fabsf(x), fabsf(y)), fabsf(z));
   const bool inner = (n <= 1.f);
   if (!inner) {
-    const float f = __fsub_rn(p.B, __fdiv_rn(p.A, n));
+    // torch evaluates `bg_len / norm` (Python scalar / tensor) as norm.reciprocal() * bg_len -- Tensor.__rtruediv__ --
+    // i.e. two roundings; reproduced here so contracted points match the reference's torch ops bit-for-bit
+    const float f = __fsub_rn(p.B, __fmul_rn(__frcp_rn(n), p.A));
     x = __fmul_rn(__fdiv_rn(x, n), f);
     y = __fmul_rn(__fdiv_rn(y, n), f);
     z = __fmul_rn(__fdiv_rn(z, n), f);

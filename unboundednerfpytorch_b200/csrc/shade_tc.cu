@@ -1,0 +1,348 @@
+// shade_tc.cu -- rgbnet forward on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a only.
+//
+// Same contract as k_shade_fwd (shade.cu): rgb = sigmoid(W3 relu(W2 relu(W1k x + vb[ray]) + b2) + b3), one persistent
+// CTA per SM, 128-sample tiles, weights resident in shared memory -- but the two wide layers run as tcgen05.mma
+// (M = 128 samples, N = 128 hidden units, kind::tf32, fp32 accumulation in tensor memory):
+//
+//   layer 1   D1[128x128] (TMEM)  =  X[128x16]  (smem, K-major)  x  W1k^T          (B = W1k [N][K] smem, K-major)
+//   epilogue  each of the 128 threads owns one TMEM lane = one sample row: tcgen05.ld the row, + vb[ray], ReLU,
+//             split, tcgen05.st back into TMEM as the A operand of layer 2 (activations never touch smem / HBM)
+//   layer 2   D2[128x128] (TMEM)  =  H1[128x128] (TMEM, "TS" form)  x  W2^T         (B = W2 [N][K] smem, K-major)
+//   epilogue  tcgen05.ld the row, + b2, ReLU, 3 dot products with W3 on the CUDA cores (N = 3 is too thin for an MMA),
+//             sigmoid, 12-byte coalesced store.
+//
+// Precision: a single TF32 (or BF16) pass has ~1e-3 relative error -- two orders of magnitude above the 1e-5 parity
+// gate.  Every operand is therefore split into hi = tf32(x) and lo = x - hi (exact in fp32) and each product is the
+// 3-term sum hi*hi + lo*hi + hi*lo accumulated in fp32 ("3xTF32", error ~2^-21), at 1/3 of the TF32 tensor rate -- still
+// ~5x the fp32 CUDA-core rate of the FFMA version.  UBN_RGBNET_TF32X1 (mode 1) runs the single-pass variant.
+//
+// Shared-memory operand layout: the canonical no-swizzle K-major UMMA layout: 8-row x 16-byte core matrices, rows of a
+// core matrix 16 B apart, next 8 rows at SBO = 128 B, next 16 bytes of K at LBO = 128 rows * 16 B = 2048 B; i.e. a
+// [K/4 panels][128 rows][4 floats] array.  Descriptor bit layout per cute/arch/mma_sm100_desc.hpp (studied, not copied).
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace ubn {
+
+namespace tc {
+
+constexpr int kRows = 128;              // tile rows = TMEM lanes = threads
+constexpr int kHidden = 128;
+constexpr int kFeat = 12;
+constexpr int kK1 = 16;                 // layer-1 K padded to a multiple of 8
+constexpr uint32_t kPanelBytes = kRows * 16;   // one 16-byte K-slice of all 128 rows
+constexpr uint32_t kLBO = kPanelBytes;  // K-direction core-matrix stride
+constexpr uint32_t kSBO = 128;          // M/N-direction 8-row-group stride
+
+// smem plan (bytes)
+constexpr uint32_t oW2hi = 0;
+constexpr uint32_t oW2lo = oW2hi + (kHidden / 4) * kPanelBytes;     // 64 KB each
+constexpr uint32_t oW1hi = oW2lo + (kHidden / 4) * kPanelBytes;
+constexpr uint32_t oW1lo = oW1hi + (kK1 / 4) * kPanelBytes;         // 8 KB each
+constexpr uint32_t oA1hi = oW1lo + (kK1 / 4) * kPanelBytes;
+constexpr uint32_t oA1lo = oA1hi + (kK1 / 4) * kPanelBytes;
+constexpr uint32_t oW3 = oA1lo + (kK1 / 4) * kPanelBytes;           // [3][128] fp32
+constexpr uint32_t oB2 = oW3 + 3 * kHidden * 4;
+constexpr uint32_t oBar = oB2 + kHidden * 4;                        // mbarrier (8 B) + tmem base (4 B)
+constexpr uint32_t kSmemBytes = oBar + 16;
+
+// TMEM column plan (512 columns x 128 lanes x 32 bit)
+constexpr uint32_t cD1 = 0, cA2hi = 128, cA2lo = 256, cD2 = 384;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+  // start address [0,14), LBO [16,30), SBO [32,46) (all >> 4), descriptor version 1 at [46,48), no swizzle
+  return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)(kLBO >> 4) << 16) | ((uint64_t)(kSBO >> 4) << 32) |
+         (1ull << 46);
+}
+
+// instruction descriptor: D = fp32 (c_format 1 @4), A = B = TF32 (format 2 @7, @10), K-major both, N>>3 @17, M>>4 @24
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kHidden >> 3) << 17) | ((uint32_t)(kRows >> 4) << 24);
+
+__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(kIdesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(kIdesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void mma_commit(uint32_t bar_smem) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_smem) : "memory");
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t bar_smem, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_smem), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar_smem, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}\n" ::"r"(bar_smem),
+      "r"(parity)
+      : "memory");
+}
+
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// 32 lanes x 32 columns: thread t of the warp gets lane (warp base + t), 32 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t tf32_hi_bits(float x) { return __float_as_uint(x) & 0xFFFFE000u; }
+
+// write one weight matrix W[N=128][K] (row-major, K contiguous) into the hi / lo K-major panel arrays
+__device__ void stage_weights(const float* __restrict__ W, int K, int Kpad, uint8_t* hi, uint8_t* lo, int tid, int nthreads) {
+  for (int i = tid; i < kHidden * Kpad; i += nthreads) {
+    const int n = i / Kpad, k = i % Kpad;
+    const float w = (k < K) ? W[n * K + k] : 0.f;
+    const uint32_t hb = tf32_hi_bits(w);
+    const float l = w - __uint_as_float(hb);
+    const uint32_t off = (uint32_t)(k >> 2) * kPanelBytes + (uint32_t)n * 16 + (uint32_t)(k & 3) * 4;
+    *reinterpret_cast<uint32_t*>(hi + off) = hb;
+    *reinterpret_cast<float*>(lo + off) = l;
+  }
+}
+
+template <bool kSave, bool kThreePass>
+__global__ void __launch_bounds__(kRows, 1) k_shade_fwd_tc(
+    const float* __restrict__ feat, const float* __restrict__ vb, const int64_t* __restrict__ ray_id,
+    const float* __restrict__ W1k, const float* __restrict__ W2, const float* __restrict__ b2,
+    const float* __restrict__ W3, const float* __restrict__ b3, int64_t n_pts, float* __restrict__ rgb,
+    float* __restrict__ h1_out, float* __restrict__ h2_out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5;
+  float* sW3 = reinterpret_cast<float*>(smem + oW3);
+  float* sB2 = reinterpret_cast<float*>(smem + oB2);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + oBar);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + oBar + 8);
+  const uint32_t bar_addr = smem_u32(bar);
+
+  // ---- one-time setup: weights (split hi/lo, K-major panels), barrier, TMEM ----
+  stage_weights(W2, kHidden, kHidden, smem + oW2hi, smem + oW2lo, tid, kRows);
+  stage_weights(W1k, kFeat, kK1, smem + oW1hi, smem + oW1lo, tid, kRows);
+  for (int i = tid; i < 3 * kHidden; i += kRows) sW3[i] = W3[i];
+  sB2[tid] = b2[tid];
+  if (tid == 0) {
+    mbar_init(bar_addr, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t lane_base = (uint32_t)(warp * 32) << 16;      // this warp's TMEM lane quarter
+  const float b3x = b3[0], b3y = b3[1], b3z = b3[2];
+  uint32_t phase = 0;
+
+  const uint64_t dW1hi = make_desc(smem_u32(smem + oW1hi)), dW1lo = make_desc(smem_u32(smem + oW1lo));
+  const uint64_t dA1hi = make_desc(smem_u32(smem + oA1hi)), dA1lo = make_desc(smem_u32(smem + oA1lo));
+  const uint64_t dW2hi = make_desc(smem_u32(smem + oW2hi)), dW2lo = make_desc(smem_u32(smem + oW2lo));
+  constexpr uint64_t kStep = (uint64_t)((2 * kPanelBytes) >> 4);   // one K=8 step = two 16-byte panels
+
+  const int64_t n_tiles = (n_pts + kRows - 1) / kRows;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t row = tile * kRows + tid;
+    const bool live = row < n_pts;
+    // ---- stage the X tile: row `tid`, 12 features (+4 zero pad), split hi / lo ----
+    {
+      float x[kK1];
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        float4 v = make_float4(0, 0, 0, 0);
+        if (live) v = *reinterpret_cast<const float4*>(feat + row * kFeat + q * 4);
+        x[q * 4] = v.x; x[q * 4 + 1] = v.y; x[q * 4 + 2] = v.z; x[q * 4 + 3] = v.w;
+      }
+      x[12] = x[13] = x[14] = x[15] = 0.f;
+#pragma unroll
+      for (int p = 0; p < kK1 / 4; ++p) {
+        uint4 hi;
+        float4 lo;
+        hi.x = tf32_hi_bits(x[p * 4]); hi.y = tf32_hi_bits(x[p * 4 + 1]); hi.z = tf32_hi_bits(x[p * 4 + 2]); hi.w = tf32_hi_bits(x[p * 4 + 3]);
+        lo.x = x[p * 4] - __uint_as_float(hi.x); lo.y = x[p * 4 + 1] - __uint_as_float(hi.y);
+        lo.z = x[p * 4 + 2] - __uint_as_float(hi.z); lo.w = x[p * 4 + 3] - __uint_as_float(hi.w);
+        *reinterpret_cast<uint4*>(smem + oA1hi + p * kPanelBytes + tid * 16) = hi;
+        *reinterpret_cast<float4*>(smem + oA1lo + p * kPanelBytes + tid * 16) = lo;
+      }
+    }
+    const int64_t my_ray = live ? ray_id[row] : 0;
+    fence_async_smem();        // generic-proxy smem writes -> visible to the tensor core (async proxy)
+    tc_fence_before();
+    __syncthreads();
+    // ---- layer 1 MMA (one thread issues) ----
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int ks = 0; ks < kK1 / 8; ++ks) {
+        mma_ss(tmem + cD1, dA1hi + ks * kStep, dW1hi + ks * kStep, ks > 0);
+        if (kThreePass) {
+          mma_ss(tmem + cD1, dA1lo + ks * kStep, dW1hi + ks * kStep, 1);
+          mma_ss(tmem + cD1, dA1hi + ks * kStep, dW1lo + ks * kStep, 1);
+        }
+      }
+      mma_commit(bar_addr);
+    }
+    mbar_wait(bar_addr, phase);
+    phase ^= 1;
+    tc_fence_after();
+    // ---- epilogue 1: + vb[ray], ReLU, split, back into TMEM as the layer-2 A operand ----
+#pragma unroll 1
+    for (int c = 0; c < kHidden / 32; ++c) {
+      float v[32];
+      tmem_ld32(tmem + lane_base + cD1 + c * 32, v);
+      uint32_t hi[32], lo[32];
+      const float4* vrow = reinterpret_cast<const float4*>(vb + my_ray * kHidden + c * 32);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 bias = __ldg(vrow + q);
+        float h0 = fmaxf(v[q * 4] + bias.x, 0.f), h1v = fmaxf(v[q * 4 + 1] + bias.y, 0.f);
+        float h2v = fmaxf(v[q * 4 + 2] + bias.z, 0.f), h3 = fmaxf(v[q * 4 + 3] + bias.w, 0.f);
+        if (kSave && live) *reinterpret_cast<float4*>(h1_out + row * kHidden + c * 32 + q * 4) = make_float4(h0, h1v, h2v, h3);
+        const float hs[4] = {h0, h1v, h2v, h3};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const uint32_t hb = tf32_hi_bits(hs[e]);
+          hi[q * 4 + e] = hb;
+          lo[q * 4 + e] = __float_as_uint(hs[e] - __uint_as_float(hb));
+        }
+      }
+      tmem_st32(tmem + lane_base + cA2hi + c * 32, hi);
+      if (kThreePass) tmem_st32(tmem + lane_base + cA2lo + c * 32, lo);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    __syncthreads();
+    // ---- layer 2 MMA: A from TMEM ----
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll 4
+      for (int ks = 0; ks < kHidden / 8; ++ks) {
+        mma_ts(tmem + cD2, tmem + cA2hi + ks * 8, dW2hi + ks * kStep, ks > 0);
+        if (kThreePass) {
+          mma_ts(tmem + cD2, tmem + cA2lo + ks * 8, dW2hi + ks * kStep, 1);
+          mma_ts(tmem + cD2, tmem + cA2hi + ks * 8, dW2lo + ks * kStep, 1);
+        }
+      }
+      mma_commit(bar_addr);
+    }
+    mbar_wait(bar_addr, phase);
+    phase ^= 1;
+    tc_fence_after();
+    // ---- epilogue 2: + b2, ReLU, layer 3 on CUDA cores, sigmoid ----
+    float p0 = 0.f, p1 = 0.f, p2 = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < kHidden / 32; ++c) {
+      float v[32];
+      tmem_ld32(tmem + lane_base + cD2 + c * 32, v);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 bb = *reinterpret_cast<const float4*>(sB2 + c * 32 + q * 4);
+        const float4 wa = *reinterpret_cast<const float4*>(sW3 + c * 32 + q * 4);
+        const float4 wb = *reinterpret_cast<const float4*>(sW3 + kHidden + c * 32 + q * 4);
+        const float4 wc = *reinterpret_cast<const float4*>(sW3 + 2 * kHidden + c * 32 + q * 4);
+        const float h0 = fmaxf(v[q * 4] + bb.x, 0.f), h1v = fmaxf(v[q * 4 + 1] + bb.y, 0.f);
+        const float h2v = fmaxf(v[q * 4 + 2] + bb.z, 0.f), h3 = fmaxf(v[q * 4 + 3] + bb.w, 0.f);
+        if (kSave && live) *reinterpret_cast<float4*>(h2_out + row * kHidden + c * 32 + q * 4) = make_float4(h0, h1v, h2v, h3);
+        p0 = fmaf(h3, wa.w, fmaf(h2v, wa.z, fmaf(h1v, wa.y, fmaf(h0, wa.x, p0))));
+        p1 = fmaf(h3, wb.w, fmaf(h2v, wb.z, fmaf(h1v, wb.y, fmaf(h0, wb.x, p1))));
+        p2 = fmaf(h3, wc.w, fmaf(h2v, wc.z, fmaf(h1v, wc.y, fmaf(h0, wc.x, p2))));
+      }
+    }
+    if (live) {
+      float* o = rgb + row * 3;
+      o[0] = 1.f / (1.f + expf(-(p0 + b3x)));
+      o[1] = 1.f / (1.f + expf(-(p1 + b3y)));
+      o[2] = 1.f / (1.f + expf(-(p2 + b3z)));
+    }
+    // all TMEM reads of this tile are complete (wait::ld inside tmem_ld32) before the next tile's MMAs overwrite D1 / D2
+    tc_fence_before();
+    __syncthreads();
+  }
+
+  // ---- teardown ----
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+  }
+}
+
+}  // namespace tc
+}  // namespace ubn
+
+using namespace ubn;
+
+extern "C" int ubn_rgbnet_fwd_tc(const float* feat, const float* view_bias, const int64_t* ray_id, const float* W1k,
+                                 const float* W2, const float* b2, const float* W3, const float* b3, int64_t n_pts,
+                                 float* rgb, float* h1_save, float* h2_save, int single_pass, void* stream) {
+  if (n_pts <= 0) return 0;
+  const bool save = h1_save != nullptr && h2_save != nullptr;
+  const int64_t n_tiles = (n_pts + tc::kRows - 1) / tc::kRows;
+  const unsigned grid = (unsigned)std::min<int64_t>(kNumSMs, n_tiles);
+  cudaStream_t st = as_stream(stream);
+#define UBN_TC_LAUNCH(SAVE, THREE)                                                                                   \
+  do {                                                                                                               \
+    cudaError_t e = cudaFuncSetAttribute(tc::k_shade_fwd_tc<SAVE, THREE>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                         (int)tc::kSmemBytes);                                                       \
+    if (e != cudaSuccess) return finish(e);                                                                          \
+    tc::k_shade_fwd_tc<SAVE, THREE><<<grid, tc::kRows, tc::kSmemBytes, st>>>(feat, view_bias, ray_id, W1k, W2, b2, W3, b3, \
+                                                                              n_pts, rgb, h1_save, h2_save);          \
+  } while (0)
+  if (save) {
+    if (single_pass) UBN_TC_LAUNCH(true, false); else UBN_TC_LAUNCH(true, true);
+  } else {
+    if (single_pass) UBN_TC_LAUNCH(false, false); else UBN_TC_LAUNCH(false, true);
+  }
+#undef UBN_TC_LAUNCH
+  UBN_LAUNCH_CHECK();
+  return 0;
+}

@@ -18,6 +18,7 @@ import torch.nn.functional as F
 
 from . import grid as G
 from . import march
+from . import shade as shade_mod
 from .functional import Alphas2Weights, Raw2Alpha, host_scalar, segment_sum
 
 
@@ -143,8 +144,10 @@ class _ContractedBase(nn.Module):
     def _shade(self, k0, viewdirs, ray_id):
         if self.rgbnet is None:
             return torch.sigmoid(k0)
-        emb = _view_embed(viewdirs, self.viewfreq).flatten(0, -2)[ray_id]
-        return torch.sigmoid(self.rgbnet(torch.cat([k0, emb], -1)))
+        emb = _view_embed(viewdirs, self.viewfreq).flatten(0, -2)
+        if shade_mod.supported(self.rgbnet, k0.shape[-1]):
+            return shade_mod.shade(self.rgbnet, k0, emb, ray_id)          # fused on-chip MLP (csrc/shade.cu)
+        return torch.sigmoid(self.rgbnet(torch.cat([k0, emb[ray_id]], -1)))   # other widths / depths: torch (cuBLAS)
 
     def density_total_variation_add_grad(self, weight, dense_mode):
         w = weight * self._tv_world_max(self.density) / 128

@@ -1,0 +1,78 @@
+"""rgbnet (feature -> RGB MLP) as one fused kernel per direction (csrc/shade.cu) behind an autograd.Function.
+
+rgb = sigmoid(rgbnet(cat[k0, viewdirs_emb[ray_id]]))   (FourierGrid_model.py:631-637, dcvgo.py:337-342)
+
+The view-direction half of the first Linear is constant along a ray, so the host folds it into a per-ray bias table
+``vb = emb(viewdirs) @ W1[:, 12:].T + b1`` ([N,128], one tiny GEMM that torch differentiates for dW1[:,12:], db1) and the
+kernel runs the per-sample part: 12 -> 128 -> 128 -> 3 with the activations resident on chip, fp32 arithmetic.
+"""
+import torch
+
+import os
+
+from . import _cabi, ops
+from ._cabi import c_i64, c_int, check, ptr, stream_of
+
+# forward engine: 'tc3' = tcgen05 3xTF32 (fp32-grade), 'tc1' = tcgen05 single TF32 pass (preview), 'simt' = fp32 FFMA
+MODE = os.environ.get('UBN_RGBNET_MODE', 'simt')
+
+
+class _ShadeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feat, vb, ray_id, W1k, W2, b2, W3, b3):
+        feat, vb, ray_id = feat.contiguous(), vb.contiguous(), ray_id.contiguous()
+        W1k, W2, b2, W3, b3 = (t.contiguous() for t in (W1k, W2, b2, W3, b3))
+        M = feat.shape[0]
+        dev = feat.device
+        rgb = torch.empty(M, 3, dtype=torch.float32, device=dev)
+        need_grad = any(ctx.needs_input_grad)
+        h1 = torch.empty(M, 128, dtype=torch.float32, device=dev) if need_grad else None
+        h2 = torch.empty(M, 128, dtype=torch.float32, device=dev) if need_grad else None
+        with ops._Guard(feat) as lib:
+            with _cabi.timed('rgbnet_fwd'):
+                if MODE in ('tc3', 'tc1'):
+                    check(lib.ubn_rgbnet_fwd_tc(ptr(feat), ptr(vb), ptr(ray_id), ptr(W1k), ptr(W2), ptr(b2), ptr(W3), ptr(b3),
+                                                c_i64(M), ptr(rgb), ptr(h1), ptr(h2), c_int(1 if MODE == 'tc1' else 0),
+                                                stream_of(feat)))
+                else:
+                    check(lib.ubn_rgbnet_fwd(ptr(feat), ptr(vb), ptr(ray_id), ptr(W1k), ptr(W2), ptr(b2), ptr(W3), ptr(b3),
+                                             c_i64(M), ptr(rgb), ptr(h1), ptr(h2), stream_of(feat)))
+        if need_grad:
+            ctx.save_for_backward(feat, ray_id, W1k, W2, W3, rgb, h1, h2)
+            ctx.n_rays = vb.shape[0]
+        return rgb
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_rgb):
+        feat, ray_id, W1k, W2, W3, rgb, h1, h2 = ctx.saved_tensors
+        dev = feat.device
+        M = feat.shape[0]
+        g_rgb = g_rgb.contiguous()
+        g_feat = torch.empty_like(feat)
+        z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
+        g_vb, gW1k, gW2, gb2, gW3, gb3 = z(ctx.n_rays, 128), z(128, 12), z(128, 128), z(128), z(3, 128), z(3)
+        with ops._Guard(feat) as lib:
+            with _cabi.timed('rgbnet_bwd'):
+                check(lib.ubn_rgbnet_bwd(ptr(feat), ptr(ray_id), ptr(W1k), ptr(W2), ptr(W3), ptr(rgb), ptr(h1), ptr(h2),
+                                         ptr(g_rgb), c_i64(M), ptr(g_feat), ptr(g_vb), ptr(gW1k), ptr(gW2), ptr(gb2),
+                                         ptr(gW3), ptr(gb3), stream_of(feat)))
+        return g_feat, g_vb, None, gW1k, gW2, gb2, gW3, gb3
+
+
+def supported(rgbnet, k0_dim):
+    """3-layer, width-128 rgbnet on 12 features (rgbnet_depth=3, rgbnet_width=128, rgbnet_dim=12: every shipped config)."""
+    try:
+        l1, l2, l3 = rgbnet[0], rgbnet[2][0], rgbnet[3]
+    except Exception:
+        return False
+    return (len(rgbnet) == 4 and k0_dim == 12 and l1.weight.shape[0] == 128 and tuple(l2.weight.shape) == (128, 128)
+            and tuple(l3.weight.shape) == (3, 128) and l1.weight.is_cuda and l1.weight.dtype == torch.float32)
+
+
+def shade(rgbnet, k0, view_emb, ray_id):
+    """k0 [M,12], view_emb [N,27] (cat[v, sin, cos]), ray_id [M] sorted -> rgb [M,3]."""
+    l1, l2, l3 = rgbnet[0], rgbnet[2][0], rgbnet[3]
+    kd = k0.shape[1]
+    vb = torch.addmm(l1.bias, view_emb, l1.weight[:, kd:].t())
+    return _ShadeFn.apply(k0, vb, ray_id, l1.weight[:, :kd], l2.weight, l2.bias, l3.weight, l3.bias)
