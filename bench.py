@@ -183,6 +183,7 @@ def main():
     ap.add_argument('--workload', default='truck', choices=['truck', 'bicycle'])
     ap.add_argument('--cpu-rays', type=int, default=256, help='ray sample of the CPU baseline (bounded)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--only-timed', action='store_true', help='warm-up + timed region only (for ncu captures)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
 
@@ -292,6 +293,13 @@ def main():
     ktimes = _cabi.TIMER.summary()
     _cabi.TIMER = None
     clk = clocks.stop() if rank == 0 else None
+    if args.only_timed:
+        if rank == 0:
+            print(json.dumps({'only_timed': True, 'ms_per_step': ms_total / args.steps, 'gpu_launches': launches,
+                              'kernels_ms': {k: round(v[0], 4) for k, v in ktimes.items()}}))
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return
     for i in range(2):
         e2e_step(i)
     ms_e2e = timed_region(e2e_step, args.steps)

@@ -20,82 +20,9 @@
 // index-like outputs (which samples are listed / scanned / kept) stay bit-exact.
 #include <algorithm>
 
-#include "trilinear.cuh"
+#include "march_common.cuh"
 
 namespace ubn {
-
-struct MarchParams {
-  float cx, cy, cz, rx, ry, rz;   // scene center / radius
-  float B, A;                     // contraction constants
-  int l2norm;
-  int S;
-  float shift, interval, thres;
-  int use_cumdist;
-  float cumdist_thres;
-  int use_mask;
-  int msz[3];
-  float mscale[3], mshift[3];
-};
-
-static MarchParams make_params(const UbnMarchCfg* c) {
-  MarchParams p;
-  p.cx = c->scene_center[0]; p.cy = c->scene_center[1]; p.cz = c->scene_center[2];
-  p.rx = c->scene_radius[0]; p.ry = c->scene_radius[1]; p.rz = c->scene_radius[2];
-  p.B = c->contract_B; p.A = c->contract_A;
-  p.l2norm = c->contracted_norm;
-  p.S = c->n_samples;
-  p.shift = c->act_shift; p.interval = c->interval; p.thres = c->fast_color_thres;
-  p.use_cumdist = c->use_cumdist; p.cumdist_thres = c->cumdist_thres;
-  p.use_mask = c->use_maskcache;
-  for (int a = 0; a < 3; ++a) { p.msz[a] = c->mask_sz[a]; p.mscale[a] = c->mask_scale[a]; p.mshift[a] = c->mask_shift[a]; }
-  return p;
-}
-
-struct Ray {
-  float ox, oy, oz, dx, dy, dz;   // normalised origin, unit direction
-};
-
-// ||v|| exactly as torch's CUDA reduction evaluates x.norm(dim=-1) on 3-vectors: the lanes of the reduced
-// dimension are combined by a shuffle tree, i.e. sqrt((x*x + z*z) + y*y) with every product and sum rounded
-// separately (probed on B200: 0 mismatches in 2^20 random vectors; the "natural" orders mismatch in 12-15 %).
-// The reference runs these norms as torch ops (dcvgo.py:240,253,288; FourierGrid_model.py:523,537), so matching
-// them bit-for-bit keeps the threshold decisions downstream (inner mask, cumdist, mask-cache rounding) identical.
-__device__ __forceinline__ float norm3_torch(float x, float y, float z) {
-  return sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(z, z)), __fmul_rn(y, y)));
-}
-
-// rays_o = (o - center) / radius ; rays_d = d / ||d||     (torch elementwise: no fma contraction)
-__device__ __forceinline__ Ray load_ray(const float* __restrict__ o, const float* __restrict__ d, const MarchParams& p) {
-  Ray r;
-  r.ox = __fdiv_rn(__fsub_rn(o[0], p.cx), p.rx);
-  r.oy = __fdiv_rn(__fsub_rn(o[1], p.cy), p.ry);
-  r.oz = __fdiv_rn(__fsub_rn(o[2], p.cz), p.rz);
-  const float n = norm3_torch(d[0], d[1], d[2]);
-  r.dx = __fdiv_rn(d[0], n);
-  r.dy = __fdiv_rn(d[1], n);
-  r.dz = __fdiv_rn(d[2], n);
-  return r;
-}
-
-// contracted sample position at parameter t; returns inner flag (norm <= 1)
-__device__ __forceinline__ bool sample_point(const Ray& r, float t, const MarchParams& p, float& x, float& y, float& z) {
-  x = __fadd_rn(r.ox, __fmul_rn(r.dx, t));
-  y = __fadd_rn(r.oy, __fmul_rn(r.dy, t));
-  z = __fadd_rn(r.oz, __fmul_rn(r.dz, t));
-  float n;
-  if (p.l2norm) n = norm3_torch(x, y, z);
-  else          n = fmaxf(fmaxf(fabsf(x), fabsf(y)), fabsf(z));
-  const bool inner = (n <= 1.f);
-  if (!inner) {
-    // torch evaluates `bg_len / norm` (Python scalar / tensor) as norm.reciprocal() * bg_len -- Tensor.__rtruediv__ --
-    // i.e. two roundings; reproduced here so contracted points match the reference's torch ops bit-for-bit
-    const float f = __fsub_rn(p.B, __fmul_rn(__frcp_rn(n), p.A));
-    x = __fmul_rn(__fdiv_rn(x, n), f);
-    y = __fmul_rn(__fdiv_rn(y, n), f);
-    z = __fmul_rn(__fdiv_rn(z, n), f);
-  }
-  return inner;
-}
 
 __device__ __forceinline__ float grid_density(const GridView& g, float x, float y, float z) {
   const float nx = norm_coord(x, g.mn[0], g.len[0]);
@@ -110,8 +37,6 @@ __device__ __forceinline__ float grid_density(const GridView& g, float x, float 
   }
   return (g.P > 1) ? acc / (float)g.P : acc;
 }
-
-constexpr int kMarchWarps = 4;
 
 // ------------------------------------------------------------------------------------------------
 // pass A forward
@@ -399,6 +324,13 @@ __global__ void __launch_bounds__(32 * kMarchWarps) k_march_density_bwd(
   }
 }
 
+// second-generation feature kernels (march_feature.cu); -1 = configuration not covered, use the generic kernel
+int march_feature_v2(bool backward, const float* rays_o, const float* rays_d, const float* t_table, const GridView& g,
+                     const MarchParams& p, int64_t n_rays, const uint8_t* flags, const int64_t* offsets,
+                     const float* density, const float* alpha, const float* weight, float* feat, float* grad_grid,
+                     float* o_density, float* o_alpha, float* o_weight, int64_t* o_ray_id, int64_t* o_step_id, float* o_t,
+                     uint8_t* o_inner, cudaStream_t st);
+
 static bool feature_grid_ok(const GridView& g) {
   return g.sc == 1 && g.sv == g.C && (g.C == 4 || g.C == 8 || g.C == 12 || g.C == 16) && g.P <= 16 &&
          ((uintptr_t)g.data & 15) == 0 && (g.sp % 4) == 0;
@@ -434,6 +366,12 @@ int ubn_march_feature_fwd(const float* rays_o, const float* rays_d, const float*
   const GridView g = make_view(k0_grid, k0_desc);
   if (!feature_grid_ok(g) || ((uintptr_t)k0_feat & 15)) return finish(cudaErrorInvalidValue);
   const MarchParams p = make_params(cfg);
+  {
+    const int e = march_feature_v2(false, rays_o, rays_d, t_table, g, p, n_rays, flags, offsets, density, alpha, weight,
+                                   k0_feat, nullptr, out_density, out_alpha, out_weight, ray_id, step_id, out_t, out_inner,
+                                   as_stream(stream));
+    if (e >= 0) return e;
+  }
   const size_t smem = sizeof(float4) * kMarchWarps * 32 * g.P;
   k_march_feature<false><<<blocks_for(n_rays, kMarchWarps), 32 * kMarchWarps, smem, as_stream(stream)>>>(
       rays_o, rays_d, t_table, g, p, n_rays, flags, offsets, density, alpha, weight, k0_feat, nullptr, out_density,
@@ -449,6 +387,12 @@ int ubn_march_feature_bwd(const float* rays_o, const float* rays_d, const float*
   const GridView g = make_view(grad_k0, k0_desc);
   if (!feature_grid_ok(g) || ((uintptr_t)grad_feat & 15)) return finish(cudaErrorInvalidValue);
   const MarchParams p = make_params(cfg);
+  {
+    const int e = march_feature_v2(true, rays_o, rays_d, t_table, g, p, n_rays, flags, offsets, nullptr, nullptr, nullptr,
+                                   const_cast<float*>(grad_feat), grad_k0, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                   nullptr, nullptr, as_stream(stream));
+    if (e >= 0) return e;
+  }
   const size_t smem = sizeof(float4) * kMarchWarps * 32 * g.P;
   k_march_feature<true><<<blocks_for(n_rays, kMarchWarps), 32 * kMarchWarps, smem, as_stream(stream)>>>(
       rays_o, rays_d, t_table, g, p, n_rays, flags, offsets, nullptr, nullptr, nullptr, const_cast<float*>(grad_feat),

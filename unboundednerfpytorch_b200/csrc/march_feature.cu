@@ -1,0 +1,235 @@
+// march_feature.cu -- pass B of the fused march (feature-grid read for the surviving samples and its adjoint),
+// second generation.  Same outputs as k_march_feature in march.cu (kept as the generic fallback); restructured after
+// the first ncu capture (profiles/r01_*): the first version ran at 43 % of the algorithmic roofline with an L1 hit
+// rate below 1 % (its per-warp staging buffers forced a 200 KB shared-memory carve-out and every sample touched all P
+// slabs before the next sample re-touched the same voxels) and one load in flight per warp.  Here:
+//   * no shared memory at all: the per-(sample, slab) cell (base voxel + 3 fractions) lives in the registers of the
+//     lane that owns the sample and is broadcast with warp shuffles -> the whole 228 KB stays L1;
+//   * samples are processed in groups of 8 with the slab loop OUTSIDE the sample loop, so the 8 corner records of
+//     consecutive samples (which share 4-8 corners at half-voxel steps) are re-read while still in L1;
+//   * the 8 loads of a group are issued back to back (independent) before their FMAs: 8x the memory-level parallelism;
+//   * cells are pre-clamped (base in [0, size-2], fraction in [0,1]) by the owning lane, so no per-corner bounds
+//     predicate is needed: contracted / Fourier-warped coordinates never leave [-1,1] (asserted by the host side).
+// Lane roles in the cooperative phase: corner = lane >> 2 (bit2 = x, bit1 = y, bit0 = z), quad = lane & 3 (channels
+// 4*quad .. 4*quad+3 of the C-channel voxel record); C in {4, 8, 12, 16}, channels-last grid.
+#include <cstdlib>
+
+#include "march_common.cuh"
+
+namespace ubn {
+
+struct CellR {
+  int v;            // base voxel index  (x0*Y + y0)*Z + z0, pre-clamped
+  float fx, fy, fz; // fractions in [0,1]
+};
+
+__device__ __forceinline__ CellR make_cell(float cx, float cy, float cz, int X, int Y, int Z) {
+  CellR c;
+  const float x0 = fminf(fmaxf(floorf(cx), 0.f), (float)(X - 2));
+  const float y0 = fminf(fmaxf(floorf(cy), 0.f), (float)(Y - 2));
+  const float z0 = fminf(fmaxf(floorf(cz), 0.f), (float)(Z - 2));
+  c.fx = cx - x0; c.fy = cy - y0; c.fz = cz - z0;
+  c.v = ((int)x0 * Y + (int)y0) * Z + (int)z0;
+  return c;
+}
+
+template <int kP, bool kBackward, int kGroup>
+__global__ void __launch_bounds__(32 * kMarchWarps, (kGroup <= 4 ? 4 : 3)) k_march_feature_v2(
+    const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float* __restrict__ t_table,
+    GridView g, MarchParams p, int64_t n_rays, const uint8_t* __restrict__ flags,
+    const int64_t* __restrict__ offsets, const float* __restrict__ density, const float* __restrict__ alpha,
+    const float* __restrict__ weight, float* __restrict__ feat /* out (fwd) or grad in (bwd) */,
+    float* __restrict__ grad_grid, float* __restrict__ o_density, float* __restrict__ o_alpha,
+    float* __restrict__ o_weight, int64_t* __restrict__ o_ray_id, int64_t* __restrict__ o_step_id,
+    float* __restrict__ o_t, uint8_t* __restrict__ o_inner) {
+  const int lane = threadIdx.x & 31;
+  const int64_t ray = (int64_t)blockIdx.x * kMarchWarps + (threadIdx.x >> 5);
+  if (ray >= n_rays) return;
+  int64_t out_base = offsets[ray];
+  const int64_t out_end = offsets[ray + 1];
+  if (out_base == out_end) return;
+  const int corner = lane >> 2, quad = lane & 3;
+  const bool bx = corner & 4, by = corner & 2, bz = corner & 1;
+  const bool quad_on = quad < (g.C >> 2);
+  // this lane's constant offset inside a cell: corner displacement + channel quad
+  const int lane_off = (((bx ? 1 : 0) * g.Y + (by ? 1 : 0)) * g.Z + (bz ? 1 : 0)) * g.C + quad * 4;
+  const Ray r = load_ray(rays_o + 3 * ray, rays_d + 3 * ray, p);
+  const int S = p.S;
+  const float inv_p = 1.f;   // the slab mean is applied as a division below (matches torch mean(0))
+
+  for (int base = 0; base < S && out_base < out_end; base += 32) {
+    const int s = base + lane;
+    const uint8_t f = (s < S) ? flags[ray * S + s] : 0;
+    const bool keep = (f & UBN_FLAG_KEEP) != 0;
+    const unsigned km = __ballot_sync(0xffffffffu, keep);
+    if (km == 0) continue;
+    const int n_here = __popc(km);
+    const int rank = __popc(km & ((1u << lane) - 1));
+
+    // ---- lane = sample: the P cells of my sample (registers) + compacted per-survivor records ----
+    CellR cell[kP];
+    {
+      float x = 0, y = 0, z = 0, t = 0;
+      if (keep) {
+        t = t_table[s];
+        sample_point(r, t, p, x, y, z);
+      }
+      const float nx = norm_coord(x, g.mn[0], g.len[0]);
+      const float ny = norm_coord(y, g.mn[1], g.len[1]);
+      const float nz = norm_coord(z, g.mn[2], g.len[2]);
+#pragma unroll
+      for (int sl = 0; sl < kP; ++sl)
+        cell[sl] = make_cell(src_index(fourier_gamma(sl, nx), g.X), src_index(fourier_gamma(sl, ny), g.Y),
+                             src_index(fourier_gamma(sl, nz), g.Z), g.X, g.Y, g.Z);
+      if (!kBackward && keep) {
+        const int64_t o = out_base + rank;
+        const int64_t i = ray * S + s;
+        o_density[o] = density[i];
+        o_alpha[o] = alpha[i];
+        o_weight[o] = weight[i];
+        o_ray_id[o] = ray;
+        o_step_id[o] = s;
+        o_t[o] = t;
+        o_inner[o] = (f & UBN_FLAG_INNER) ? 1 : 0;
+      }
+    }
+    // compact: slot i (i-th survivor of the chunk) must be readable from lane i
+    if (km != 0xffffffffu) {
+      const int src = __fns(km, 0, lane + 1) & 31;   // lane holding the (lane+1)-th set bit (garbage when lane >= n_here)
+#pragma unroll
+      for (int sl = 0; sl < kP; ++sl) {
+        cell[sl].v = __shfl_sync(0xffffffffu, cell[sl].v, src);
+        cell[sl].fx = __shfl_sync(0xffffffffu, cell[sl].fx, src);
+        cell[sl].fy = __shfl_sync(0xffffffffu, cell[sl].fy, src);
+        cell[sl].fz = __shfl_sync(0xffffffffu, cell[sl].fz, src);
+      }
+    }
+
+    // ---- cooperative phase: groups of kGroup survivors, slab loop outside the sample loop ----
+    for (int g0 = 0; g0 < n_here; g0 += kGroup) {
+      float4 acc[kGroup];
+      float4 gin[kGroup];
+#pragma unroll
+      for (int j = 0; j < kGroup; ++j) {
+        acc[j] = make_float4(0, 0, 0, 0);
+        gin[j] = make_float4(0, 0, 0, 0);
+        if (kBackward) {
+          if (quad_on && g0 + j < n_here) gin[j] = *reinterpret_cast<const float4*>(feat + (out_base + g0 + j) * g.C + quad * 4);
+          if (kP > 1) { gin[j].x = gin[j].x / (float)kP; gin[j].y = gin[j].y / (float)kP; gin[j].z = gin[j].z / (float)kP; gin[j].w = gin[j].w / (float)kP; }
+        }
+      }
+#pragma unroll
+      for (int sl = 0; sl < kP; ++sl) {
+        const float* slab = g.data + sl * g.sp + lane_off;
+        float wgt[kGroup];
+        int64_t off[kGroup];
+#pragma unroll
+        for (int j = 0; j < kGroup; ++j) {
+          const int src = (g0 + j) & 31;
+          const int v = __shfl_sync(0xffffffffu, cell[sl].v, src);
+          const float fx = __shfl_sync(0xffffffffu, cell[sl].fx, src);
+          const float fy = __shfl_sync(0xffffffffu, cell[sl].fy, src);
+          const float fz = __shfl_sync(0xffffffffu, cell[sl].fz, src);
+          // (wz * wy) * wx, the product order of ATen's tnw..bse corner weights
+          wgt[j] = ((bz ? fz : 1.f - fz) * (by ? fy : 1.f - fy)) * (bx ? fx : 1.f - fx);
+          off[j] = (int64_t)v * g.C;
+        }
+        if (!kBackward) {
+          float4 val[kGroup];
+#pragma unroll
+          for (int j = 0; j < kGroup; ++j) {
+            val[j] = make_float4(0, 0, 0, 0);
+            if (quad_on && g0 + j < n_here) val[j] = __ldg(reinterpret_cast<const float4*>(slab + off[j]));
+          }
+#pragma unroll
+          for (int j = 0; j < kGroup; ++j) {
+            acc[j].x = fmaf(val[j].x, wgt[j], acc[j].x); acc[j].y = fmaf(val[j].y, wgt[j], acc[j].y);
+            acc[j].z = fmaf(val[j].z, wgt[j], acc[j].z); acc[j].w = fmaf(val[j].w, wgt[j], acc[j].w);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < kGroup; ++j)
+            if (quad_on && g0 + j < n_here)
+              red_add_v4(grad_grid + sl * g.sp + lane_off + off[j],
+                         make_float4(wgt[j] * gin[j].x, wgt[j] * gin[j].y, wgt[j] * gin[j].z, wgt[j] * gin[j].w));
+        }
+      }
+      if (!kBackward) {
+#pragma unroll
+        for (int j = 0; j < kGroup; ++j) {
+#pragma unroll
+          for (int o = 4; o < 32; o <<= 1) {
+            acc[j].x += __shfl_xor_sync(0xffffffffu, acc[j].x, o);
+            acc[j].y += __shfl_xor_sync(0xffffffffu, acc[j].y, o);
+            acc[j].z += __shfl_xor_sync(0xffffffffu, acc[j].z, o);
+            acc[j].w += __shfl_xor_sync(0xffffffffu, acc[j].w, o);
+          }
+        }
+        // lane (corner j, quad) writes sample j's channel quad: 8 samples x 48 B = one contiguous 384-byte run
+#pragma unroll
+        for (int j = 0; j < kGroup; ++j) {
+          if (corner == j && quad_on && g0 + j < n_here) {
+            float4 v = acc[j];
+            if (kP > 1) { v.x = v.x / (float)kP; v.y = v.y / (float)kP; v.z = v.z / (float)kP; v.w = v.w / (float)kP; }
+            *reinterpret_cast<float4*>(feat + (out_base + g0 + j) * g.C + quad * 4) = v;
+          }
+        }
+      }
+    }
+    out_base += n_here;
+  }
+  (void)inv_p;
+}
+
+template <int kP, int kGroup>
+static int launch_v2(bool backward, const float* rays_o, const float* rays_d, const float* t_table, const GridView& g,
+                     const MarchParams& p, int64_t n_rays, const uint8_t* flags, const int64_t* offsets,
+                     const float* density, const float* alpha, const float* weight, float* feat, float* grad_grid,
+                     float* o_density, float* o_alpha, float* o_weight, int64_t* o_ray_id, int64_t* o_step_id, float* o_t,
+                     uint8_t* o_inner, cudaStream_t st) {
+  const unsigned nb = blocks_for(n_rays, kMarchWarps);
+  if (backward)
+    k_march_feature_v2<kP, true, kGroup><<<nb, 32 * kMarchWarps, 0, st>>>(rays_o, rays_d, t_table, g, p, n_rays, flags, offsets,
+                                                                 density, alpha, weight, feat, grad_grid, o_density, o_alpha,
+                                                                 o_weight, o_ray_id, o_step_id, o_t, o_inner);
+  else
+    k_march_feature_v2<kP, false, kGroup><<<nb, 32 * kMarchWarps, 0, st>>>(rays_o, rays_d, t_table, g, p, n_rays, flags, offsets,
+                                                                  density, alpha, weight, feat, grad_grid, o_density, o_alpha,
+                                                                  o_weight, o_ray_id, o_step_id, o_t, o_inner);
+  UBN_LAUNCH_CHECK();
+  return 0;
+}
+
+// returns -1 when this configuration is not covered (caller falls back to the generic kernel)
+int march_feature_v2(bool backward, const float* rays_o, const float* rays_d, const float* t_table, const GridView& g,
+                     const MarchParams& p, int64_t n_rays, const uint8_t* flags, const int64_t* offsets,
+                     const float* density, const float* alpha, const float* weight, float* feat, float* grad_grid,
+                     float* o_density, float* o_alpha, float* o_weight, int64_t* o_ray_id, int64_t* o_step_id, float* o_t,
+                     uint8_t* o_inner, cudaStream_t st) {
+  if (g.X < 2 || g.Y < 2 || g.Z < 2) return -1;
+  if ((int64_t)g.X * g.Y * g.Z * g.C >= (1ll << 31)) return -1;   // 32-bit voxel offsets inside a slab
+  static int impl = -1;   // UBN_FEATURE_IMPL: 0 = generic kernel (march.cu), 1 = groups of 8, 2 = groups of 4 (default)
+  if (impl < 0) {
+    const char* e = getenv("UBN_FEATURE_IMPL");
+    impl = e ? atoi(e) : 2;
+  }
+  if (impl == 0) return -1;
+  const bool g8 = impl == 1;
+#define UBN_V2(P)                                                                                                       \
+  case P:                                                                                                               \
+    return g8 ? launch_v2<P, 8>(backward, rays_o, rays_d, t_table, g, p, n_rays, flags, offsets, density, alpha, weight, \
+                                feat, grad_grid, o_density, o_alpha, o_weight, o_ray_id, o_step_id, o_t, o_inner, st)    \
+              : launch_v2<P, 4>(backward, rays_o, rays_d, t_table, g, p, n_rays, flags, offsets, density, alpha, weight, \
+                                feat, grad_grid, o_density, o_alpha, o_weight, o_ray_id, o_step_id, o_t, o_inner, st)
+  switch (g.P) {
+    UBN_V2(1);
+    UBN_V2(3);
+    UBN_V2(5);
+    UBN_V2(7);
+    UBN_V2(9);
+    default: return -1;
+  }
+#undef UBN_V2
+}
+
+}  // namespace ubn

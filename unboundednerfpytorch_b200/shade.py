@@ -14,7 +14,7 @@ from . import _cabi, ops
 from ._cabi import c_i64, c_int, check, ptr, stream_of
 
 # forward engine: 'tc3' = tcgen05 3xTF32 (fp32-grade), 'tc1' = tcgen05 single TF32 pass (preview), 'simt' = fp32 FFMA
-MODE = os.environ.get('UBN_RGBNET_MODE', 'simt')
+MODE = os.environ.get('UBN_RGBNET_MODE', 'tc3')
 
 
 class _ShadeFn(torch.autograd.Function):
