@@ -77,7 +77,7 @@ class ClockSampler:
              'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
         try:
             self.proc = subprocess.Popen(['nvidia-smi', f'--id={self.index}', f'--query-gpu={q}', '--format=csv,noheader,nounits',
-                                          '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          '-lms', '50'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -85,7 +85,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(',')])
+            self.rows.append([c.strip() for c in line.split(',')] + [time.time()])
+
+    def mark(self):
+        """Timestamp the start of the timed region: only samples taken after it are reported (fallback: all)."""
+        self.t0 = time.time()
 
     def stop(self):
         if self.proc is None:
@@ -95,6 +99,10 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
+        t0 = getattr(self, 't0', 0.0)
+        timed = [r for r in self.rows if len(r) >= 8 and r[-1] >= t0]
+        if len(timed) >= 2:
+            self.rows = timed
         sm = sorted(float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace('.', '').isdigit())
         mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace('.', '').isdigit()]
         reasons = set()
@@ -177,7 +185,7 @@ def cpu_reference_step(flavor, kwargs, stepsize, n_rays, threads, steps, warmup)
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='truck', choices=['truck', 'bicycle'])
@@ -281,11 +289,13 @@ def main():
         loss = train_step(ro, rd, vd, target, it[0])
         return loss.item()                                   # D2H read of the step's result
 
-    for i in range(args.warmup):
-        dev_step(i)
     clocks = ClockSampler(local)
     if rank == 0:
-        clocks.start()
+        clocks.start()                 # started before the warm-up (nvidia-smi needs ~1 s to produce its first row)
+    for i in range(args.warmup):
+        dev_step(i)
+    torch.cuda.synchronize()
+    clocks.mark()
     _cabi.TIMER = _cabi.KernelTimer()
     _cabi.reset_launch_count()
     ms_total = timed_region(dev_step, args.steps)
