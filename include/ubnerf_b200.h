@@ -255,6 +255,16 @@ int ubn_rgbnet_bwd(const float* feat, const int64_t* ray_id, const float* W1k, c
                    float* grad_feat, float* grad_view_bias, float* grad_W1k, float* grad_W2, float* grad_b2,
                    float* grad_W3, float* grad_b3, void* stream);
 
+/* Tensor-core backward, in two launches with the same net effect as ubn_rgbnet_bwd:
+ *  ubn_rgbnet_bwd_tc_data : dZ2 -> dH1 = dZ2.W2 (tcgen05, A in tensor memory) -> dZ1 -> dz1_out[n_pts,128]; and
+ *                           grad_W2 += dZ2^T.H1 (tcgen05 over shared-memory MN-major chunks; 3xTF32 split).
+ *  ubn_rgbnet_bwd_small   : from dz1: grad_feat, grad_view_bias (accumulated), grad_W1k, and grad_b2 / grad_W3 / grad_b3. */
+int ubn_rgbnet_bwd_tc_data(const float* W2, const float* W3, const float* rgb, const float* h1_save, const float* h2_save,
+                           const float* grad_rgb, int64_t n_pts, float* dz1_out, float* grad_W2, void* stream);
+int ubn_rgbnet_bwd_small(const float* feat, const int64_t* ray_id, const float* W1k, const float* W3, const float* rgb,
+                         const float* h2_save, const float* grad_rgb, const float* dz1, int64_t n_pts, float* grad_feat,
+                         float* grad_view_bias, float* grad_W1k, float* grad_b2, float* grad_W3, float* grad_b3, void* stream);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

@@ -198,11 +198,13 @@ def test_training_step_reduces_loss():
     assert all(torch.isfinite(p).all() for p in student.parameters())
 
 
-@pytest.mark.parametrize('mode', ['simt', 'tc3', 'tc1'])
+@pytest.mark.parametrize('mode', ['simt', 'tc3', 'tc1', 'tc3+tcbwd'])
 def test_fused_rgbnet_vs_torch(mode, monkeypatch):
     """csrc/shade.cu (fp32 FFMA) and csrc/shade_tc.cu (tcgen05: 3xTF32 fp32-grade, single-pass TF32 preview) vs the torch
     nn.Sequential they replace: forward and every gradient."""
     from unboundednerfpytorch_b200 import models, shade as shade_mod
+    monkeypatch.setattr(shade_mod, 'BWD_MODE', 'tc3' if mode.endswith('tcbwd') else 'simt')
+    mode = mode.split('+')[0]
     monkeypatch.setattr(shade_mod, 'MODE', mode)
     fwd_tol = dict(rtol=1e-5, atol=1e-6) if mode != 'tc1' else dict(rtol=5e-3, atol=5e-3)
     torch.manual_seed(3)

@@ -428,6 +428,172 @@ __global__ void __launch_bounds__(kThreads, 1) k_shade_bwd(
   }
 }
 
+
+// ---- small gradients for the tensor-core backward (shade_tc.cu) ------------------------------------------------------
+// k_shade_bwd_tc produces dZ1 [M,128] (HBM) and dW2; everything else is thin and memory-bound and is finished here on
+// the CUDA cores from dZ1, H2, X and dz3:  db2, dW3, db3 (from dZ2 recomputed on the fly), dvb[ray] (per-ray sums of
+// dZ1), dW1k = dZ1^T X, dX = dZ1 W1k.
+struct SmallSmem {
+  static constexpr int kRow = kW + 4;
+  static constexpr int oDZ = 0;                               // dZ1s[s][k]  64 x 132
+  static constexpr int oX = oDZ + kBwdTile * kRow;            // Xs[s][k']   64 x 12
+  static constexpr int oW1 = oX + kBwdTile * kF;              // W1k[j][k']  128 x 12
+  static constexpr int oW3 = oW1 + kW * kF;                   // W3[c][j]
+  static constexpr int oDz3 = oW3 + 3 * kW;
+  static constexpr int oRay = oDz3 + kBwdTile * 4;
+  static constexpr int kFloats = oRay + kBwdTile;
+};
+
+__global__ void __launch_bounds__(kThreads, 2) k_shade_bwd_small(
+    const float* __restrict__ feat, const int64_t* __restrict__ ray_id, const float* __restrict__ W1k,
+    const float* __restrict__ W3, const float* __restrict__ rgb, const float* __restrict__ h2,
+    const float* __restrict__ g_rgb, const float* __restrict__ dz1, int64_t n_pts, float* __restrict__ g_feat,
+    float* __restrict__ g_vb, float* __restrict__ gW1k, float* __restrict__ gb2, float* __restrict__ gW3,
+    float* __restrict__ gb3) {
+  extern __shared__ __align__(16) float sm[];
+  float* sDZ = sm + SmallSmem::oDZ;
+  float* sX = sm + SmallSmem::oX;
+  float* sW1 = sm + SmallSmem::oW1;
+  float* sW3 = sm + SmallSmem::oW3;
+  float* sDz3 = sm + SmallSmem::oDz3;
+  int* sRay = reinterpret_cast<int*>(sm + SmallSmem::oRay);
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  constexpr int R = SmallSmem::kRow;
+  for (int i = tid; i < kW * kF; i += kThreads) sW1[i] = W1k[i];
+  for (int i = tid; i < 3 * kW; i += kThreads) sW3[i] = W3[i];
+  __syncthreads();
+  float w3[3][8];
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) w3[c][jj] = sW3[c * kW + jj * 16 + tx];
+  float aB2[8], aW3[3][8], aW1[6], aB3[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int jj = 0; jj < 8; ++jj) { aB2[jj] = 0.f; aW3[0][jj] = aW3[1][jj] = aW3[2][jj] = 0.f; }
+#pragma unroll
+  for (int q = 0; q < 6; ++q) aW1[q] = 0.f;
+  float run[8];
+  int run_ray = -1;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) run[q] = 0.f;
+
+  const int64_t n_tiles = (n_pts + kBwdTile - 1) / kBwdTile;
+  const int64_t per_cta = (n_tiles + gridDim.x - 1) / gridDim.x;
+  const int64_t tile_end = min(n_tiles, (int64_t)(blockIdx.x + 1) * per_cta);
+  for (int64_t tile = (int64_t)blockIdx.x * per_cta; tile < tile_end; ++tile) {
+    const int64_t base = tile * kBwdTile;
+    const int n_here = (int)min((int64_t)kBwdTile, n_pts - base);
+    for (int i = tid; i < kBwdTile * (kW / 4); i += kThreads) {
+      const int s = i / (kW / 4), q = i % (kW / 4);
+      float4 v = make_float4(0, 0, 0, 0);
+      if (s < n_here) v = __ldg(reinterpret_cast<const float4*>(dz1 + (base + s) * kW + q * 4));
+      *reinterpret_cast<float4*>(sDZ + s * R + q * 4) = v;
+    }
+    for (int i = tid; i < kBwdTile * kF; i += kThreads) {
+      const int s = i / kF;
+      sX[i] = (s < n_here) ? feat[base * kF + i] : 0.f;
+    }
+    if (tid < kBwdTile) {
+      const int s = tid;
+      float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+      int r = 0;
+      if (s < n_here) {
+        const float* o = rgb + (base + s) * 3;
+        const float* g = g_rgb + (base + s) * 3;
+        d0 = g[0] * (o[0] * (1.f - o[0]));
+        d1 = g[1] * (o[1] * (1.f - o[1]));
+        d2 = g[2] * (o[2] * (1.f - o[2]));
+        r = (int)ray_id[base + s];
+      }
+      sDz3[s * 4] = d0; sDz3[s * 4 + 1] = d1; sDz3[s * 4 + 2] = d2; sDz3[s * 4 + 3] = 0.f;
+      sRay[s] = r;
+      aB3[0] += d0; aB3[1] += d1; aB3[2] += d2;
+    }
+    __syncthreads();
+    // db2 / dW3 (hidden units j = jj*16 + tx, samples s = ty*4 + i)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int s = ty * 4 + i;
+      const float4 d = *reinterpret_cast<const float4*>(sDz3 + s * 4);
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        const float hv = (s < n_here) ? __ldg(h2 + (base + s) * kW + jj * 16 + tx) : 0.f;
+        const float dh = fmaf(d.z, w3[2][jj], fmaf(d.y, w3[1][jj], d.x * w3[0][jj]));
+        aB2[jj] += hv > 0.f ? dh : 0.f;
+        aW3[0][jj] = fmaf(d.x, hv, aW3[0][jj]);
+        aW3[1][jj] = fmaf(d.y, hv, aW3[1][jj]);
+        aW3[2][jj] = fmaf(d.z, hv, aW3[2][jj]);
+      }
+    }
+    // dvb: per-ray running sums of this thread's dZ1 rows (k = tx*8 + q)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int s = ty * 4 + i;
+      if (s < n_here) {
+        const float4 v0 = *reinterpret_cast<const float4*>(sDZ + s * R + tx * 8);
+        const float4 v1 = *reinterpret_cast<const float4*>(sDZ + s * R + tx * 8 + 4);
+        const int r = sRay[s];
+        if (r != run_ray) {
+          if (run_ray >= 0) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) atomicAdd(g_vb + (int64_t)run_ray * kW + tx * 8 + q, run[q]);
+          }
+          run_ray = r;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) run[q] = 0.f;
+        }
+        run[0] += v0.x; run[1] += v0.y; run[2] += v0.z; run[3] += v0.w;
+        run[4] += v1.x; run[5] += v1.y; run[6] += v1.z; run[7] += v1.w;
+      }
+    }
+    // dW1k, dX
+    {
+      const int j = tid & 127, k0 = 6 * (tid >> 7);
+#pragma unroll 4
+      for (int s = 0; s < kBwdTile; ++s) {
+        const float d = sDZ[s * R + j];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) aW1[q] = fmaf(d, sX[s * kF + k0 + q], aW1[q]);
+      }
+      const int s = tid >> 2, kk = 3 * (tid & 3);
+      float x0 = 0.f, x1 = 0.f, x2 = 0.f;
+#pragma unroll 4
+      for (int jx = 0; jx < kW; ++jx) {
+        const float d = sDZ[s * R + jx];
+        x0 = fmaf(d, sW1[jx * kF + kk], x0);
+        x1 = fmaf(d, sW1[jx * kF + kk + 1], x1);
+        x2 = fmaf(d, sW1[jx * kF + kk + 2], x2);
+      }
+      if (s < n_here) {
+        float* o = g_feat + (base + s) * kF + kk;
+        o[0] = x0; o[1] = x1; o[2] = x2;
+      }
+    }
+    __syncthreads();
+  }
+  if (run_ray >= 0) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) atomicAdd(g_vb + (int64_t)run_ray * kW + tx * 8 + q, run[q]);
+  }
+#pragma unroll
+  for (int jj = 0; jj < 8; ++jj) {
+    const int j = jj * 16 + tx;
+    atomicAdd(gb2 + j, aB2[jj]);
+    atomicAdd(gW3 + j, aW3[0][jj]);
+    atomicAdd(gW3 + kW + j, aW3[1][jj]);
+    atomicAdd(gW3 + 2 * kW + j, aW3[2][jj]);
+  }
+  {
+    const int j = tid & 127, k0 = 6 * (tid >> 7);
+#pragma unroll
+    for (int q = 0; q < 6; ++q) atomicAdd(gW1k + j * kF + k0 + q, aW1[q]);
+  }
+  if (tid < kBwdTile) {
+    atomicAdd(gb3, aB3[0]); atomicAdd(gb3 + 1, aB3[1]); atomicAdd(gb3 + 2, aB3[2]);
+  }
+}
+
 static int shade_grid() { return kNumSMs; }
 
 }  // namespace ubn
@@ -474,3 +640,19 @@ int ubn_rgbnet_bwd(const float* feat, const int64_t* ray_id, const float* W1k, c
 }
 
 }  // extern "C"
+
+
+extern "C" int ubn_rgbnet_bwd_small(const float* feat, const int64_t* ray_id, const float* W1k, const float* W3,
+                                    const float* rgb, const float* h2_save, const float* grad_rgb, const float* dz1,
+                                    int64_t n_pts, float* grad_feat, float* grad_view_bias, float* grad_W1k, float* grad_b2,
+                                    float* grad_W3, float* grad_b3, void* stream) {
+  if (n_pts <= 0) return 0;
+  const size_t smem = sizeof(float) * SmallSmem::kFloats;
+  cudaError_t e = cudaFuncSetAttribute(k_shade_bwd_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return finish(e);
+  k_shade_bwd_small<<<2 * kNumSMs, kThreads, smem, as_stream(stream)>>>(feat, ray_id, W1k, W3, rgb, h2_save, grad_rgb, dz1, n_pts,
+                                                                        grad_feat, grad_view_bias, grad_W1k, grad_b2, grad_W3,
+                                                                        grad_b3);
+  UBN_LAUNCH_CHECK();
+  return 0;
+}

@@ -316,6 +316,220 @@ __global__ void __launch_bounds__(kRows, 1) k_shade_fwd_tc(
   }
 }
 
+
+// =====================================================================================================================
+// Backward on the tensor cores (data gradient + the big weight gradient):
+//   dZ2 = (dz3 . W3) * [H2 > 0]                         per row, CUDA cores (rank-3 update), split hi/lo -> TMEM
+//   dH1 = dZ2 . W2            (TS MMA: A = dZ2 in TMEM, B = W2^T staged once per CTA as K-major hi/lo panels)
+//   dZ1 = dH1 * [H1 > 0]      epilogue, streamed to HBM for the small-gradient kernel (k_shade_bwd_small, shade.cu)
+//   dW2 += dZ2^T . H1         contraction over SAMPLES: both operands must present the sample index as K.  Per tile, 4
+//                             rounds of 32 samples: dZ2 (A, M = hidden j) and H1 (B, N = hidden k), hi and lo, are
+//                             staged K-major (transposing 4-byte stores), then 4 K-steps x 3 split passes of
+//                             tcgen05.mma accumulate into a TMEM region that persists for the whole kernel.  (The
+//                             no-swizzle MN-major descriptor form, which would allow 16-byte staging stores, returned
+//                             all-zero accumulators for kind::tf32 on this part and toolchain -- probed on hardware.)
+// TMEM: [0,128) dZ2 hi, [128,256) dZ2 lo, [256,384) dH1, [384,512) dW2 accumulator.
+// =====================================================================================================================
+namespace bw {
+constexpr uint32_t kChunkK = 32;                              // samples per dW2 round
+constexpr uint32_t kChunkBytes = (kChunkK / 4) * kPanelBytes; // 8 K-major panels = 16 KB per staged operand
+constexpr uint32_t oWThi = 0;                                 // W2^T K-major panels (B of the dH1 MMA)
+constexpr uint32_t oWTlo = oWThi + (kHidden / 4) * kPanelBytes;
+constexpr uint32_t oCAhi = oWTlo + (kHidden / 4) * kPanelBytes;
+constexpr uint32_t oCAlo = oCAhi + kChunkBytes;
+constexpr uint32_t oCBhi = oCAlo + kChunkBytes;
+constexpr uint32_t oCBlo = oCBhi + kChunkBytes;
+constexpr uint32_t oW3b = oCBlo + kChunkBytes;                // [3][128] fp32
+constexpr uint32_t oBarB = oW3b + 3 * kHidden * 4;
+constexpr uint32_t kSmemBytesB = oBarB + 16;
+constexpr uint32_t cZhi = 0, cZlo = 128, cDH = 256, cDW = 384;
+
+}  // namespace bw
+
+__global__ void __launch_bounds__(kRows, 1) k_shade_bwd_tc(
+    const float* __restrict__ W2, const float* __restrict__ W3, const float* __restrict__ rgb,
+    const float* __restrict__ h1, const float* __restrict__ h2, const float* __restrict__ g_rgb, int64_t n_pts,
+    float* __restrict__ dz1_out, float* __restrict__ gW2) {
+  using namespace bw;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float* sW3 = reinterpret_cast<float*>(smem + oW3b);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + oBarB);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + oBarB + 8);
+  const uint32_t bar_addr = smem_u32(bar);
+
+  // W2^T as the K-major B operand of dH1[s][k] = sum_j dZ2[s][j] W2[j][k]:  B[n = k][kk = j] = W2[j][k]
+  for (int i = tid; i < kHidden * kHidden; i += kRows) {
+    const int j = i / kHidden, k = i % kHidden;            // coalesced read of W2[j][k]
+    const float w = W2[i];
+    const uint32_t hb = tf32_hi_bits(w);
+    const uint32_t off = (uint32_t)(j >> 2) * kPanelBytes + (uint32_t)k * 16 + (uint32_t)(j & 3) * 4;
+    *reinterpret_cast<uint32_t*>(smem + oWThi + off) = hb;
+    *reinterpret_cast<float*>(smem + oWTlo + off) = w - __uint_as_float(hb);
+  }
+  for (int i = tid; i < 3 * kHidden; i += kRows) sW3[i] = W3[i];
+  if (tid == 0) {
+    mbar_init(bar_addr, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+  uint32_t phase = 0;
+  const uint64_t dWThi = make_desc(smem_u32(smem + oWThi)), dWTlo = make_desc(smem_u32(smem + oWTlo));
+  const uint64_t dCAhi = make_desc(smem_u32(smem + oCAhi)), dCAlo = make_desc(smem_u32(smem + oCAlo));
+  const uint64_t dCBhi = make_desc(smem_u32(smem + oCBhi)), dCBlo = make_desc(smem_u32(smem + oCBlo));
+  constexpr uint64_t kStepK = (uint64_t)((2 * kPanelBytes) >> 4);   // K-major operand: 8 K-elements = 2 panels
+  bool dw_started = false;
+
+  const int64_t n_tiles = (n_pts + kRows - 1) / kRows;
+  const int64_t per_cta = (n_tiles + gridDim.x - 1) / gridDim.x;
+  const int64_t tile_end = min(n_tiles, (int64_t)(blockIdx.x + 1) * per_cta);
+  for (int64_t tile = (int64_t)blockIdx.x * per_cta; tile < tile_end; ++tile) {
+    const int64_t row = tile * kRows + tid;
+    const bool live = row < n_pts;
+    float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+    if (live) {
+      const float* o = rgb + row * 3;
+      const float* g = g_rgb + row * 3;
+      d0 = g[0] * (o[0] * (1.f - o[0]));
+      d1 = g[1] * (o[1] * (1.f - o[1]));
+      d2 = g[2] * (o[2] * (1.f - o[2]));
+    }
+    // ---- dZ2 row -> TMEM (A operand of the dH1 MMA) ----
+#pragma unroll 1
+    for (int c = 0; c < kHidden / 32; ++c) {
+      uint32_t hi[32], lo[32];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        float4 hv = make_float4(0, 0, 0, 0);
+        if (live) hv = __ldg(reinterpret_cast<const float4*>(h2 + row * kHidden + c * 32 + q * 4));
+        const float4 wa = *reinterpret_cast<const float4*>(sW3 + c * 32 + q * 4);
+        const float4 wb = *reinterpret_cast<const float4*>(sW3 + kHidden + c * 32 + q * 4);
+        const float4 wc = *reinterpret_cast<const float4*>(sW3 + 2 * kHidden + c * 32 + q * 4);
+        const float z[4] = {hv.x > 0.f ? fmaf(d2, wc.x, fmaf(d1, wb.x, d0 * wa.x)) : 0.f,
+                            hv.y > 0.f ? fmaf(d2, wc.y, fmaf(d1, wb.y, d0 * wa.y)) : 0.f,
+                            hv.z > 0.f ? fmaf(d2, wc.z, fmaf(d1, wb.z, d0 * wa.z)) : 0.f,
+                            hv.w > 0.f ? fmaf(d2, wc.w, fmaf(d1, wb.w, d0 * wa.w)) : 0.f};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const uint32_t hb = tf32_hi_bits(z[e]);
+          hi[q * 4 + e] = hb;
+          lo[q * 4 + e] = __float_as_uint(z[e] - __uint_as_float(hb));
+        }
+      }
+      tmem_st32(tmem + lane_base + cZhi + c * 32, hi);
+      tmem_st32(tmem + lane_base + cZlo + c * 32, lo);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    __syncthreads();
+    // ---- dH1 = dZ2 . W2 ----
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll 4
+      for (int ks = 0; ks < kHidden / 8; ++ks) {
+        mma_ts(tmem + cDH, tmem + cZhi + ks * 8, dWThi + ks * kStepK, ks > 0);
+        mma_ts(tmem + cDH, tmem + cZlo + ks * 8, dWThi + ks * kStepK, 1);
+        mma_ts(tmem + cDH, tmem + cZhi + ks * 8, dWTlo + ks * kStepK, 1);
+      }
+      mma_commit(bar_addr);
+    }
+    mbar_wait(bar_addr, phase);
+    phase ^= 1;
+    tc_fence_after();
+    // ---- dZ1 = dH1 * [H1 > 0] -> HBM ----
+#pragma unroll 1
+    for (int c = 0; c < kHidden / 32; ++c) {
+      float v[32];
+      tmem_ld32(tmem + lane_base + cDH + c * 32, v);
+      if (live) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 hv = __ldg(reinterpret_cast<const float4*>(h1 + row * kHidden + c * 32 + q * 4));
+          float4 o;
+          o.x = hv.x > 0.f ? v[q * 4] : 0.f; o.y = hv.y > 0.f ? v[q * 4 + 1] : 0.f;
+          o.z = hv.z > 0.f ? v[q * 4 + 2] : 0.f; o.w = hv.w > 0.f ? v[q * 4 + 3] : 0.f;
+          *reinterpret_cast<float4*>(dz1_out + row * kHidden + c * 32 + q * 4) = o;
+        }
+      }
+    }
+    // ---- dW2 += dZ2^T . H1 : 4 rounds of 32 samples (K = sample index) ----
+    // Both operands are staged K-major: A[m = hidden j][k = sample], B[n = hidden k][k = sample]; element (row, s) lives at
+    // panel s/4, row*16 + (s%4)*4.  In round r the 8 rows 8r..8r+7 of every warp are staged by ALL 32 lanes of that
+    // warp: lane l serves row 8r + (l & 7) and the hidden units j = 4*jj + (l >> 3) (jj < 32) -- this assignment spreads the
+    // 4-byte stores over 16 banks x 2 panels (2-way conflict) instead of 8 lanes hammering 4 banks.
+#pragma unroll 1
+    for (int r = 0; r < 4; ++r) {
+      const int src = 8 * r + (lane & 7);
+      const float e0 = __shfl_sync(0xffffffffu, d0, src), e1 = __shfl_sync(0xffffffffu, d1, src), e2 = __shfl_sync(0xffffffffu, d2, src);
+      const int64_t row_s = tile * kRows + warp * 32 + src;
+      const bool live_s = row_s < n_pts;
+      const uint32_t s_local = (uint32_t)warp * 8 + (uint32_t)(lane & 7);
+      const uint32_t soff = (s_local >> 2) * kPanelBytes + (s_local & 3) * 4;
+      const int q = lane >> 3;
+#pragma unroll 8
+      for (int jj = 0; jj < kHidden / 4; ++jj) {
+        const int j = jj * 4 + q;
+        float hv2 = 0.f, hv1 = 0.f;
+        if (live_s) {
+          hv2 = __ldg(h2 + row_s * kHidden + j);
+          hv1 = __ldg(h1 + row_s * kHidden + j);
+        }
+        const float z = hv2 > 0.f ? fmaf(e2, sW3[2 * kHidden + j], fmaf(e1, sW3[kHidden + j], e0 * sW3[j])) : 0.f;
+        const uint32_t zh = tf32_hi_bits(z), hh = tf32_hi_bits(hv1);
+        const uint32_t off = soff + (uint32_t)j * 16;
+        *reinterpret_cast<uint32_t*>(smem + oCAhi + off) = zh;
+        *reinterpret_cast<float*>(smem + oCAlo + off) = z - __uint_as_float(zh);
+        *reinterpret_cast<uint32_t*>(smem + oCBhi + off) = hh;
+        *reinterpret_cast<float*>(smem + oCBlo + off) = hv1 - __uint_as_float(hh);
+      }
+      fence_async_smem();
+      tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < (int)(kChunkK / 8); ++ks) {
+          mma_ss(tmem + cDW, dCAhi + ks * kStepK, dCBhi + ks * kStepK, (dw_started || ks > 0) ? 1u : 0u);
+          mma_ss(tmem + cDW, dCAlo + ks * kStepK, dCBhi + ks * kStepK, 1);
+          mma_ss(tmem + cDW, dCAhi + ks * kStepK, dCBlo + ks * kStepK, 1);
+        }
+        mma_commit(bar_addr);
+      }
+      dw_started = true;
+      mbar_wait(bar_addr, phase);     // the chunk buffers are rewritten by the next round
+      phase ^= 1;
+      tc_fence_after();
+    }
+    tc_fence_before();
+    __syncthreads();
+  }
+
+  // ---- flush dW2: thread j owns row j of the accumulator ----
+  if (dw_started) {
+#pragma unroll 1
+    for (int c = 0; c < kHidden / 32; ++c) {
+      float v[32];
+      tmem_ld32(tmem + lane_base + cDW + c * 32, v);
+#pragma unroll
+      for (int e = 0; e < 32; ++e) atomicAdd(gW2 + tid * kHidden + c * 32 + e, v[e]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+  }
+}
+
 }  // namespace tc
 }  // namespace ubn
 
@@ -343,6 +557,22 @@ extern "C" int ubn_rgbnet_fwd_tc(const float* feat, const float* view_bias, cons
     if (single_pass) UBN_TC_LAUNCH(false, false); else UBN_TC_LAUNCH(false, true);
   }
 #undef UBN_TC_LAUNCH
+  UBN_LAUNCH_CHECK();
+  return 0;
+}
+
+
+extern "C" int ubn_rgbnet_bwd_tc_data(const float* W2, const float* W3, const float* rgb, const float* h1_save,
+                                      const float* h2_save, const float* grad_rgb, int64_t n_pts, float* dz1_out,
+                                      float* grad_W2, void* stream) {
+  if (n_pts <= 0) return 0;
+  const int64_t n_tiles = (n_pts + tc::kRows - 1) / tc::kRows;
+  const unsigned grid = (unsigned)std::min<int64_t>(kNumSMs, n_tiles);
+  cudaError_t e = cudaFuncSetAttribute(tc::k_shade_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)tc::bw::kSmemBytesB);
+  if (e != cudaSuccess) return finish(e);
+  tc::k_shade_bwd_tc<<<grid, tc::kRows, tc::bw::kSmemBytesB, as_stream(stream)>>>(W2, W3, rgb, h1_save, h2_save, grad_rgb,
+                                                                                  n_pts, dz1_out, grad_W2);
   UBN_LAUNCH_CHECK();
   return 0;
 }
