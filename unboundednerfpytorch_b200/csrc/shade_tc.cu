@@ -346,6 +346,7 @@ constexpr uint32_t cZhi = 0, cZlo = 128, cDH = 256, cDW = 384;
 
 }  // namespace bw
 
+template <bool kRounds>
 __global__ void __launch_bounds__(kRows, 1) k_shade_bwd_tc(
     const float* __restrict__ W2, const float* __restrict__ W3, const float* __restrict__ rgb,
     const float* __restrict__ h1, const float* __restrict__ h2, const float* __restrict__ g_rgb, int64_t n_pts,
@@ -403,14 +404,20 @@ __global__ void __launch_bounds__(kRows, 1) k_shade_bwd_tc(
       d1 = g[1] * (o[1] * (1.f - o[1]));
       d2 = g[2] * (o[2] * (1.f - o[2]));
     }
-    // ---- dZ2 row -> TMEM (A operand of the dH1 MMA) ----
-#pragma unroll 1
+    // ---- dZ2 row -> TMEM (A operand of the dH1 MMA).  The kernel is load-latency bound with 4 warps per SM, so the whole
+    //      512-byte H2 row is requested up front (32 independent 128-bit loads in flight per thread) ----
+    float4 hrow[kHidden / 4];
+#pragma unroll
+    for (int q = 0; q < kHidden / 4; ++q) {
+      hrow[q] = make_float4(0, 0, 0, 0);
+      if (live) hrow[q] = __ldg(reinterpret_cast<const float4*>(h2 + row * kHidden + q * 4));
+    }
+#pragma unroll
     for (int c = 0; c < kHidden / 32; ++c) {
       uint32_t hi[32], lo[32];
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        float4 hv = make_float4(0, 0, 0, 0);
-        if (live) hv = __ldg(reinterpret_cast<const float4*>(h2 + row * kHidden + c * 32 + q * 4));
+        const float4 hv = hrow[c * 8 + q];
         const float4 wa = *reinterpret_cast<const float4*>(sW3 + c * 32 + q * 4);
         const float4 wb = *reinterpret_cast<const float4*>(sW3 + kHidden + c * 32 + q * 4);
         const float4 wc = *reinterpret_cast<const float4*>(sW3 + 2 * kHidden + c * 32 + q * 4);
@@ -442,18 +449,24 @@ __global__ void __launch_bounds__(kRows, 1) k_shade_bwd_tc(
       }
       mma_commit(bar_addr);
     }
+    // the H1 row is requested while the tensor pipe works (the H2 registers are dead by now)
+#pragma unroll
+    for (int q = 0; q < kHidden / 4; ++q) {
+      hrow[q] = make_float4(0, 0, 0, 0);
+      if (live) hrow[q] = __ldg(reinterpret_cast<const float4*>(h1 + row * kHidden + q * 4));
+    }
     mbar_wait(bar_addr, phase);
     phase ^= 1;
     tc_fence_after();
     // ---- dZ1 = dH1 * [H1 > 0] -> HBM ----
-#pragma unroll 1
+#pragma unroll
     for (int c = 0; c < kHidden / 32; ++c) {
       float v[32];
       tmem_ld32(tmem + lane_base + cDH + c * 32, v);
       if (live) {
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          const float4 hv = __ldg(reinterpret_cast<const float4*>(h1 + row * kHidden + c * 32 + q * 4));
+          const float4 hv = hrow[c * 8 + q];
           float4 o;
           o.x = hv.x > 0.f ? v[q * 4] : 0.f; o.y = hv.y > 0.f ? v[q * 4 + 1] : 0.f;
           o.z = hv.z > 0.f ? v[q * 4 + 2] : 0.f; o.w = hv.w > 0.f ? v[q * 4 + 3] : 0.f;
@@ -467,7 +480,7 @@ __global__ void __launch_bounds__(kRows, 1) k_shade_bwd_tc(
     // warp: lane l serves row 8r + (l & 7) and the hidden units j = 4*jj + (l >> 3) (jj < 32) -- this assignment spreads the
     // 4-byte stores over 16 banks x 2 panels (2-way conflict) instead of 8 lanes hammering 4 banks.
 #pragma unroll 1
-    for (int r = 0; r < 4; ++r) {
+    for (int r = 0; kRounds && r < 4; ++r) {
       const int src = 8 * r + (lane & 7);
       const float e0 = __shfl_sync(0xffffffffu, d0, src), e1 = __shfl_sync(0xffffffffu, d1, src), e2 = __shfl_sync(0xffffffffu, d2, src);
       const int64_t row_s = tile * kRows + warp * 32 + src;
@@ -530,6 +543,133 @@ __global__ void __launch_bounds__(kRows, 1) k_shade_bwd_tc(
   }
 }
 
+
+// ---- dW2 += dZ2^T . H1 as its own split-K GEMM ----------------------------------------------------------------------
+// Round = 32 consecutive samples.  Warp w stages rows 4w..4w+3; lane l serves row (l & 3) and hidden units j = 8*jj + (l >> 2)
+// (jj < 16): for one store instruction the 32 lanes hit 32 distinct banks of one K-major panel (conflict free).
+// The kernel is global-load-latency bound (ncu: 75 % long-scoreboard stalls with one CTA per SM), so it is sized for
+// THREE co-resident CTAs per SM (66 KB smem, 128 TMEM columns each) and every thread prefetches the next round's 32 values
+// into registers before it waits for the tensor pipe to release the single staging buffer.
+namespace dw {
+constexpr int kThreadsDW = 256;
+constexpr uint32_t kK = 32;
+constexpr uint32_t kOpBytes = (kK / 4) * kPanelBytes;          // 16 KB per operand
+constexpr uint32_t oW3d = 4 * kOpBytes;                        // A hi, A lo, B hi, B lo
+constexpr uint32_t oBarD = oW3d + 3 * kHidden * 4;             // mbarrier + tmem slot
+constexpr uint32_t kSmemBytesD = oBarD + 16;
+constexpr int kCtasPerSM = 3;
+}  // namespace dw
+
+__global__ void __launch_bounds__(dw::kThreadsDW, dw::kCtasPerSM) k_shade_dw2_tc(
+    const float* __restrict__ W3, const float* __restrict__ rgb, const float* __restrict__ h1, const float* __restrict__ h2,
+    const float* __restrict__ g_rgb, int64_t n_pts, float* __restrict__ gW2) {
+  using namespace dw;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float* sW3 = reinterpret_cast<float*>(smem + oW3d);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + oBarD);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + oBarD + 8);
+  const uint32_t bar_addr = smem_u32(bar);
+  for (int i = tid; i < 3 * kHidden; i += kThreadsDW) sW3[i] = W3[i];
+  if (tid == 0) {
+    mbar_init(bar_addr, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  constexpr uint64_t kStepK = (uint64_t)((2 * kPanelBytes) >> 4);
+  const uint64_t dAhi = make_desc(smem_u32(smem)), dAlo = make_desc(smem_u32(smem + kOpBytes));
+  const uint64_t dBhi = make_desc(smem_u32(smem + 2 * kOpBytes)), dBlo = make_desc(smem_u32(smem + 3 * kOpBytes));
+
+  const int64_t n_rounds = (n_pts + kK - 1) / kK;
+  const int64_t per_cta = (n_rounds + gridDim.x - 1) / gridDim.x;
+  const int64_t r_begin = (int64_t)blockIdx.x * per_cta, r_end = min(n_rounds, r_begin + per_cta);
+  uint32_t phase = 0;
+  const uint32_t s_local = (uint32_t)warp * 4 + (uint32_t)(lane & 3);
+  const uint32_t soff = (s_local >> 2) * kPanelBytes + (s_local & 3) * 4;
+  const int q = lane >> 2;
+
+  float p2[kHidden / 8], p1[kHidden / 8], pd[3];     // prefetched h2 / h1 values and dz3 of my row for the coming round
+  auto prefetch = [&](int64_t rd) {
+    const int64_t row = rd * kK + s_local;
+    const bool live = rd < r_end && row < n_pts;
+    pd[0] = pd[1] = pd[2] = 0.f;
+    if (live) {
+      const float* o = rgb + row * 3;
+      const float* g = g_rgb + row * 3;
+      pd[0] = g[0] * (o[0] * (1.f - o[0]));
+      pd[1] = g[1] * (o[1] * (1.f - o[1]));
+      pd[2] = g[2] * (o[2] * (1.f - o[2]));
+    }
+#pragma unroll
+    for (int jj = 0; jj < kHidden / 8; ++jj) {
+      p2[jj] = live ? __ldg(h2 + row * kHidden + jj * 8 + q) : 0.f;
+      p1[jj] = live ? __ldg(h1 + row * kHidden + jj * 8 + q) : 0.f;
+    }
+  };
+  if (r_begin < r_end) prefetch(r_begin);
+  bool pending = false;
+  for (int64_t rd = r_begin; rd < r_end; ++rd) {
+    float c2[kHidden / 8], c1[kHidden / 8];
+#pragma unroll
+    for (int jj = 0; jj < kHidden / 8; ++jj) { c2[jj] = p2[jj]; c1[jj] = p1[jj]; }
+    const float d0 = pd[0], d1 = pd[1], d2 = pd[2];
+    prefetch(rd + 1);                       // loads for the next round fly while this round is staged and multiplied
+    if (pending) {                          // tensor pipe must have finished reading the staging buffer
+      mbar_wait(bar_addr, phase);
+      phase ^= 1;
+    }
+#pragma unroll
+    for (int jj = 0; jj < kHidden / 8; ++jj) {
+      const int j = jj * 8 + q;
+      const float z = c2[jj] > 0.f ? fmaf(d2, sW3[2 * kHidden + j], fmaf(d1, sW3[kHidden + j], d0 * sW3[j])) : 0.f;
+      const uint32_t zh = tf32_hi_bits(z), hh = tf32_hi_bits(c1[jj]);
+      const uint32_t off = soff + (uint32_t)j * 16;
+      *reinterpret_cast<uint32_t*>(smem + off) = zh;
+      *reinterpret_cast<float*>(smem + kOpBytes + off) = z - __uint_as_float(zh);
+      *reinterpret_cast<uint32_t*>(smem + 2 * kOpBytes + off) = hh;
+      *reinterpret_cast<float*>(smem + 3 * kOpBytes + off) = c1[jj] - __uint_as_float(hh);
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int ks = 0; ks < (int)(kK / 8); ++ks) {
+        mma_ss(tmem, dAhi + ks * kStepK, dBhi + ks * kStepK, (rd > r_begin || ks > 0) ? 1u : 0u);
+        mma_ss(tmem, dAlo + ks * kStepK, dBhi + ks * kStepK, 1);
+        mma_ss(tmem, dAhi + ks * kStepK, dBlo + ks * kStepK, 1);
+      }
+      mma_commit(bar_addr);
+    }
+    pending = true;
+  }
+  if (pending) {
+    mbar_wait(bar_addr, phase);
+    tc_fence_after();
+    if (warp < 4) {                        // warps 0..3 own TMEM lanes 32w..32w+31 = rows j of dW2
+#pragma unroll 1
+      for (int c = 0; c < kHidden / 32; ++c) {
+        float v[32];
+        tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c * 32, v);
+#pragma unroll
+        for (int e = 0; e < 32; ++e) atomicAdd(gW2 + tid * kHidden + c * 32 + e, v[e]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem) : "memory");
+}
+
 }  // namespace tc
 }  // namespace ubn
 
@@ -566,13 +706,26 @@ extern "C" int ubn_rgbnet_bwd_tc_data(const float* W2, const float* W3, const fl
                                       const float* h2_save, const float* grad_rgb, int64_t n_pts, float* dz1_out,
                                       float* grad_W2, void* stream) {
   if (n_pts <= 0) return 0;
-  const int64_t n_tiles = (n_pts + tc::kRows - 1) / tc::kRows;
-  const unsigned grid = (unsigned)std::min<int64_t>(kNumSMs, n_tiles);
-  cudaError_t e = cudaFuncSetAttribute(tc::k_shade_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)tc::bw::kSmemBytesB);
-  if (e != cudaSuccess) return finish(e);
-  tc::k_shade_bwd_tc<<<grid, tc::kRows, tc::bw::kSmemBytesB, as_stream(stream)>>>(W2, W3, rgb, h1_save, h2_save, grad_rgb,
-                                                                                  n_pts, dz1_out, grad_W2);
-  UBN_LAUNCH_CHECK();
+  cudaStream_t st = as_stream(stream);
+  {   // dH1 / dZ1 (TS-MMA chain)
+    const int64_t n_tiles = (n_pts + tc::kRows - 1) / tc::kRows;
+    const unsigned grid = (unsigned)std::min<int64_t>(kNumSMs, n_tiles);
+    cudaError_t e = cudaFuncSetAttribute(tc::k_shade_bwd_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)tc::bw::kSmemBytesB);
+    if (e != cudaSuccess) return finish(e);
+    tc::k_shade_bwd_tc<false><<<grid, tc::kRows, tc::bw::kSmemBytesB, st>>>(W2, W3, rgb, h1_save, h2_save, grad_rgb, n_pts,
+                                                                            dz1_out, grad_W2);
+    UBN_LAUNCH_CHECK();
+  }
+  {   // dW2 (split-K GEMM over all samples)
+    const int64_t n_rounds = (n_pts + tc::dw::kK - 1) / tc::dw::kK;
+    const unsigned grid = (unsigned)std::min<int64_t>((int64_t)kNumSMs * tc::dw::kCtasPerSM, n_rounds);
+    cudaError_t e = cudaFuncSetAttribute(tc::k_shade_dw2_tc, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)tc::dw::kSmemBytesD);
+    if (e != cudaSuccess) return finish(e);
+    tc::k_shade_dw2_tc<<<grid, tc::dw::kThreadsDW, tc::dw::kSmemBytesD, st>>>(W3, rgb, h1_save, h2_save, grad_rgb, n_pts,
+                                                                             grad_W2);
+    UBN_LAUNCH_CHECK();
+  }
   return 0;
 }

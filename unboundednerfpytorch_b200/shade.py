@@ -16,7 +16,7 @@ from ._cabi import c_i64, c_int, check, ptr, stream_of
 # forward engine: 'tc3' = tcgen05 3xTF32 (fp32-grade), 'tc1' = tcgen05 single TF32 pass (preview), 'simt' = fp32 FFMA
 MODE = os.environ.get('UBN_RGBNET_MODE', 'tc3')
 # backward engine: 'tc3' = tcgen05 3xTF32 for dH1 / dW2 + a thin CUDA-core kernel for the small gradients, 'simt' = fp32 FFMA
-BWD_MODE = os.environ.get('UBN_RGBNET_BWD_MODE', 'simt')
+BWD_MODE = os.environ.get('UBN_RGBNET_BWD_MODE', 'tc3')
 
 
 class _ShadeFn(torch.autograd.Function):
