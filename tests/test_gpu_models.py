@@ -231,3 +231,49 @@ def test_fused_rgbnet_vs_torch(mode, monkeypatch):
         for a, b, nm in zip(got, want, ['k0', 'W1', 'b1', 'W2', 'b2', 'W3', 'b3']):
             scale = b.abs().max().item() + 1e-12
             assert_close(a, b, rtol=2e-5, atol=2e-6 * scale + 1e-9, what=f'grad {nm} M={M}')
+
+
+def test_progressive_growing_and_occupancy_utilities(oracle):
+    """scale_volume_grid / update_occupancy_cache / voxel_count_views / hit_coarse_geo are consumers of
+    the trilinear read and of its adjoint; check them against torch-CPU restatements."""
+    import torch.nn.functional as F
+    from unboundednerfpytorch_b200 import grid as G
+    m, kw = _fresh_model('fouriergrid', 24, 2, 1e-4, 5, dens_mean=1.0, dens_std=3.0)
+    m = m.to(DEV)
+    g = torch.Generator().manual_seed(11)
+    # voxel_count_views: adjoint-of-ones counting vs torch F.grid_sample autograd on CPU
+    H = W = 12
+    ro = (torch.rand(2 * H, W, 3, generator=g) - 0.5)
+    rd = torch.randn(2 * H, W, 3, generator=g)
+    cnt = m.voxel_count_views(ro.flatten(0, 1).to(DEV), rd.flatten(0, 1).to(DEV), [H * W, H * W], near=0.0, far=1e9, stepsize=0.5,
+                              irregular_shape=True)
+    ws = [int(v) for v in m.world_size_density]
+    ref = torch.zeros(1, 1, *ws)
+    n_samples = int(torch.tensor([w + 1.0 for w in ws]).norm() / 0.5) + 1
+    rng = torch.arange(n_samples)[None].float()
+    for o_, d_ in zip(ro.flatten(0, 1).split(H * W), rd.flatten(0, 1).split(H * W)):
+        ones = torch.zeros(1, 1, *ws, requires_grad=True)
+        vec = torch.where(d_ == 0, torch.full_like(d_, 1e-6), d_)
+        a, b = (m.xyz_max.cpu() - o_) / vec, (m.xyz_min.cpu() - o_) / vec
+        t_min = torch.minimum(a, b).amax(-1).clamp(min=0.0, max=1e9)
+        interpx = t_min[..., None] + 0.5 * m.voxel_size_density.cpu() * rng / d_.norm(dim=-1, keepdim=True)
+        pts = o_[..., None, :] + d_[..., None, :] * interpx[..., None]
+        oracle.dense_grid_forward(ones, pts, m.xyz_min.cpu(), m.xyz_max.cpu()).sum().backward()
+        ref += (ones.grad > 1)
+    mism = (cnt.cpu() != ref).float().mean().item()
+    assert mism < 2e-3, mism            # voxels whose accumulated weight sits within float noise of the threshold 1
+    # scale_volume_grid keeps the layout contract and matches F.interpolate on CPU
+    before = m.k0.grid.detach().cpu().contiguous()
+    m.scale_volume_grid(30 ** 3, 30 ** 3)
+    want = F.interpolate(before, size=tuple(int(v) for v in m.world_size_rgb), mode='trilinear', align_corners=True)
+    assert m.k0.grid.stride()[1] == 1
+    assert_close(m.k0.grid, want, rtol=1e-5, atol=1e-6, what='scale_volume_grid')
+    # occupancy cache update only ever clears cells, and the render still runs afterwards
+    occ0 = m.mask_cache.mask.clone()
+    m.update_occupancy_cache()
+    assert (m.mask_cache.mask & ~occ0).sum() == 0
+    ro1, rd1, vd1 = seeded_rays(64, 3, DEV)
+    out = m(ro1, rd1, vd1, near=0., far=1e9, bg=1, rand_bkgd=False, stepsize=0.5)
+    assert torch.isfinite(out['rgb_marched']).all()
+    hit = m.hit_coarse_geo(ro1, rd1, near=0., far=1e9, stepsize=0.5)
+    assert hit.shape == (64,) and hit.dtype == torch.bool

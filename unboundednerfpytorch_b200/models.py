@@ -277,6 +277,64 @@ class FourierGridModel(_ContractedBase):
         alpha = F.max_pool3d(self.activate_density(dens), kernel_size=3, padding=1, stride=1)[0, 0]
         self.mask_cache.mask &= (alpha > self.fast_color_thres)
 
+    @torch.no_grad()
+    def maskout_near_cam_vox(self, cam_o, near_clip):
+        """FourierGrid_model.py:375-388: set the density of grid points closer than near_clip to any (embedded) camera
+        position to -100, slab by slab."""
+        dev = self.density.grid.device
+        ind_norm = ((cam_o.to(dev) - self.xyz_min) / (self.xyz_max - self.xyz_min)).flip((-1,)) * 2 - 1
+        F_ = self.density.nerf_pos_num_freq
+        freqs = 2 ** torch.linspace(0, F_ - 1, F_, device=dev)
+        emb = [ind_norm] + [f(fr * ind_norm) for fr in freqs for f in (torch.sin, torch.cos)]
+        ws = [int(v) for v in self.world_size_density]
+        axes = [torch.linspace(-1, 1, ws[a], device=dev) for a in range(3)]
+        xyz = torch.stack(torch.meshgrid(*axes, indexing='ij'), -1)
+        for i, cam in enumerate(emb):
+            nearest = torch.stack([(xyz.unsqueeze(-2) - co).pow(2).sum(-1).sqrt().amin(-1) for co in cam.split(10)]).amin(0)
+            self.density.grid[0][i][nearest <= near_clip] = -100      # same indexing as the reference (:388)
+
+    def voxel_count_views(self, rays_o_tr, rays_d_tr, imsz, near, far, stepsize, downrate=1, irregular_shape=False):
+        """FourierGrid_model.py:390-420: per-voxel number of training views, counted with the adjoint of the trilinear read
+        (ones(pts).sum().backward(); count += grad > 1) -- here the scatter kernel of libubnerf_b200."""
+        far = 1e9
+        dev = self.density.grid.device
+        n_samples = int(np.linalg.norm(np.array([int(v) for v in self.world_size_density]) + 1) / stepsize) + 1
+        rng = torch.arange(n_samples, device=dev)[None].float()
+        count = torch.zeros_like(self.density.get_dense_grid())
+        for rays_o_, rays_d_ in zip(rays_o_tr.split(imsz), rays_d_tr.split(imsz)):
+            ones = G.DenseGrid(1, self.world_size_density, self.xyz_min, self.xyz_max).to(dev)
+            if irregular_shape:
+                rays_o_, rays_d_ = rays_o_.split(10000), rays_d_.split(10000)
+            else:
+                rays_o_ = rays_o_[::downrate, ::downrate].to(dev).flatten(0, -2).split(10000)
+                rays_d_ = rays_d_[::downrate, ::downrate].to(dev).flatten(0, -2).split(10000)
+            for rays_o, rays_d in zip(rays_o_, rays_d_):
+                rays_o, rays_d = rays_o.to(dev), rays_d.to(dev)
+                vec = torch.where(rays_d == 0, torch.full_like(rays_d, 1e-6), rays_d)
+                rate_a = (self.xyz_max - rays_o) / vec
+                rate_b = (self.xyz_min - rays_o) / vec
+                t_min = torch.minimum(rate_a, rate_b).amax(-1).clamp(min=near, max=far)
+                step = stepsize * self.voxel_size_density * rng
+                interpx = t_min[..., None] + step / rays_d.norm(dim=-1, keepdim=True)
+                rays_pts = rays_o[..., None, :] + rays_d[..., None, :] * interpx[..., None]
+                ones(rays_pts).sum().backward()
+            with torch.no_grad():
+                count += (ones.grid.grad > 1)
+        return count
+
+    def hit_coarse_geo(self, rays_o, rays_d, near, far, stepsize, **render_kwargs):
+        """FourierGrid_model.py:495-507: does a ray hit the occupancy mask?"""
+        from . import ops
+        shape = rays_o.shape[:-1]
+        rays_o = rays_o.reshape(-1, 3).contiguous()
+        rays_d = rays_d.reshape(-1, 3).contiguous()
+        ray_pts, mask_outbbox, ray_id = ops.sample_pts_on_rays(rays_o, rays_d, self.xyz_min, self.xyz_max, near, 1e9,
+                                                               stepsize * float(self.voxel_size_density))[:3]
+        mask_inbbox = ~mask_outbbox
+        hit = torch.zeros([len(rays_o)], dtype=torch.bool, device=rays_o.device)
+        hit[ray_id[mask_inbbox][self.mask_cache(ray_pts[mask_inbbox])]] = 1
+        return hit.reshape(shape)
+
     def sample_ray(self, ori_rays_o, ori_rays_d, stepsize, is_train=False, **render_kwargs):
         """FourierGrid_model.py:509-552 return tuple (ray_pts, indexs, inner_mask, t, rays_d_extend)."""
         ray_pts, inner_mask, t = self._sample_dense(ori_rays_o, ori_rays_d, stepsize)
