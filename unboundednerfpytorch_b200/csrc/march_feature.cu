@@ -34,7 +34,7 @@ __device__ __forceinline__ CellR make_cell(float cx, float cy, float cz, int X, 
 }
 
 template <int kP, bool kBackward, int kGroup>
-__global__ void __launch_bounds__(32 * kMarchWarps, (kGroup <= 4 ? 4 : 3)) k_march_feature_v2(
+__global__ void __launch_bounds__(32 * kMarchWarps, (kGroup <= 1 ? 8 : (kGroup <= 2 ? 6 : (kGroup <= 4 ? 4 : 5)))) k_march_feature_v2(
     const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float* __restrict__ t_table,
     GridView g, MarchParams p, int64_t n_rays, const uint8_t* __restrict__ flags,
     const int64_t* __restrict__ offsets, const float* __restrict__ density, const float* __restrict__ alpha,
@@ -215,9 +215,15 @@ int march_feature_v2(bool backward, const float* rays_o, const float* rays_d, co
   }
   if (impl == 0) return -1;
   const bool g8 = impl == 1;
+  const bool g2 = impl == 3 || (impl == 2 && !backward);   // default: groups of 2 forward (occupancy), 4 backward
+  const bool g1 = impl == 4;
 #define UBN_V2(P)                                                                                                       \
   case P:                                                                                                               \
-    return g8 ? launch_v2<P, 8>(backward, rays_o, rays_d, t_table, g, p, n_rays, flags, offsets, density, alpha, weight, \
+    return g1 ? launch_v2<P, 1>(backward, rays_o, rays_d, t_table, g, p, n_rays, flags, offsets, density, alpha, weight, \
+                                feat, grad_grid, o_density, o_alpha, o_weight, o_ray_id, o_step_id, o_t, o_inner, st)    \
+         : g2 ? launch_v2<P, 2>(backward, rays_o, rays_d, t_table, g, p, n_rays, flags, offsets, density, alpha, weight, \
+                                feat, grad_grid, o_density, o_alpha, o_weight, o_ray_id, o_step_id, o_t, o_inner, st)    \
+         : g8 ? launch_v2<P, 8>(backward, rays_o, rays_d, t_table, g, p, n_rays, flags, offsets, density, alpha, weight, \
                                 feat, grad_grid, o_density, o_alpha, o_weight, o_ray_id, o_step_id, o_t, o_inner, st)    \
               : launch_v2<P, 4>(backward, rays_o, rays_d, t_table, g, p, n_rays, flags, offsets, density, alpha, weight, \
                                 feat, grad_grid, o_density, o_alpha, o_weight, o_ray_id, o_step_id, o_t, o_inner, st)
