@@ -367,3 +367,14 @@ def test_grid_sample_vs_torch_and_adjoint(oracle, C, F_, n):
     lhs = (out.detach().double() * y.double()).sum()
     rhs = (gg.detach().double() * gg.grad.double()).sum()
     assert abs(lhs - rhs) <= 1e-4 * max(1.0, abs(lhs)), (lhs, rhs)
+
+
+def test_host_scalar_cache_is_per_tensor_object():
+    """The cached `.item()` of act_shift must not leak to a new tensor that reuses the freed address."""
+    from unboundednerfpytorch_b200.functional import host_scalar
+    for k in range(8):
+        t = torch.tensor([float(k)], device=DEV)
+        assert host_scalar(t) == float(k)
+        t.add_(0.5)                                  # in-place update bumps the version
+        assert host_scalar(t) == float(k) + 0.5
+        del t

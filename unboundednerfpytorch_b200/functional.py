@@ -6,6 +6,8 @@ Python numbers or 1-element tensors (the reference passes ``self.act_shift``, a 
 its pybind float caster turns that into an implicit ``.item()`` on EVERY call, SURVEY.md 8b -- here the
 host value is cached per tensor version so steady-state calls do not synchronise).
 """
+import weakref
+
 import torch
 
 from . import ops
@@ -14,18 +16,17 @@ _scalar_cache = {}
 
 
 def host_scalar(v):
-    """float(v) with a (data_ptr, version) cache for device tensors."""
-    if isinstance(v, torch.Tensor):
-        if v.is_cuda:
-            key = (v.data_ptr(), v._version, v.device.index)
-            hit = _scalar_cache.get(key)
-            if hit is None:
-                if len(_scalar_cache) > 64:
-                    _scalar_cache.clear()
-                hit = float(v)
-                _scalar_cache[key] = hit
-            return hit
-        return float(v)
+    """float(v); for device tensors the D2H read is cached per tensor OBJECT (weakref + in-place version counter), so a
+    long-lived buffer such as `act_shift` costs one sync, and a new tensor that reuses a freed address never hits."""
+    if isinstance(v, torch.Tensor) and v.is_cuda:
+        hit = _scalar_cache.get(id(v))
+        if hit is not None and hit[0]() is v and hit[1] == v._version:
+            return hit[2]
+        if len(_scalar_cache) > 64:
+            _scalar_cache.clear()
+        val = float(v)
+        _scalar_cache[id(v)] = (weakref.ref(v), v._version, val)
+        return val
     return float(v)
 
 
