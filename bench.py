@@ -242,6 +242,7 @@ def main():
     opt = create_optimizer_or_freeze_model(model, cfg_train, global_step=0)
     rk = dict(near=0., far=1e9, bg=1, rand_bkgd=False, stepsize=stepsize)
     params = [p for p in model.parameters() if p.requires_grad]
+    tv_terms = model.tv_terms(1e-6 / N_RAYS, 1e-7 / N_RAYS, True)
 
     # every rank gets its own 8192-ray batch (weak scaling); host copies are pinned for the e2e leg
     host = [t.pin_memory() for t in synth_batch(N_RAYS, SEED + rank)]
@@ -252,11 +253,8 @@ def main():
         opt.zero_grad(set_to_none=True)
         loss = step_loss(ret, target, N_RAYS)
         loss.backward()
-        if world > 1:
-            ubdist.allreduce_grads(params)
-        model.density_total_variation_add_grad(1e-6 / N_RAYS, True)
-        model.k0_total_variation_add_grad(1e-7 / N_RAYS, True)
-        opt.step()
+        # all-reduce (N > 1) -> dense TV -> MaskedAdam; per slab, so the sweeps of slab p overlap the transfer of slab p+1
+        ubdist.reduce_tv_step(opt, tv_terms)
         return loss
 
     def sync_all():

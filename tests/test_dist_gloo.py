@@ -63,6 +63,67 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
+def _tail_worker(rank, world, port, q):
+    """reduce_tv_step (slab-pipelined all-reduce -> TV -> Adam) == allreduce_grads -> TV -> opt.step(), bit for bit.
+    The sweeps themselves are CUDA-only in the product, so on CPU the oracle's C restatement stands in for them."""
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    from oracle import cpu_ref
+    from unboundednerfpytorch_b200 import dist as D, ops
+    from unboundednerfpytorch_b200.masked_adam import MaskedAdam
+    for name in ('total_variation_add_grad', 'adam_upd', 'masked_adam_upd', 'adam_upd_with_perlr'):
+        setattr(ops, name, getattr(cpu_ref, name))
+    D.init_from_env(backend='gloo')
+    try:
+        def make():
+            torch.manual_seed(5)
+            grid9 = torch.nn.Parameter(torch.randn(3, 2, 4, 5, 6))      # 3 slabs -> 3 pipelined chunks
+            grid1 = torch.nn.Parameter(torch.randn(1, 2, 4, 4, 4))      # single slab -> reduced whole
+            lin = torch.nn.Parameter(torch.randn(7, 3))
+            opt = MaskedAdam([dict(params=[grid9, grid1], lr=0.1, skip_zero_grad=True),
+                              dict(params=[lin], lr=1e-3, skip_zero_grad=False)])
+            return (grid9, grid1, lin), opt
+        (pa, oa), (pb, ob) = make(), make()
+        for step in range(2):
+            g = torch.Generator().manual_seed(100 * step + rank)
+            for x, y in zip(pa, pb):
+                grad = torch.randn(x.shape, generator=g) * (torch.rand(x.shape, generator=g) > 0.5)
+                x.grad, y.grad = grad.clone(), grad.clone()
+            tv_a = {pa[0]: (0.3, 0.2, 0.1, step == 0), pa[1]: (0.05, 0.05, 0.05, False)}
+            D.reduce_tv_step(oa, tv_a)                                   # pipelined
+            D.allreduce_grads(pb)                                        # sequential restatement
+            ops.total_variation_add_grad(pb[0], pb[0].grad, 0.3, 0.2, 0.1, step == 0)
+            ops.total_variation_add_grad(pb[1], pb[1].grad, 0.05, 0.05, 0.05, False)
+            ob.step()
+            for x, y in zip(pa, pb):
+                assert torch.equal(x.grad, y.grad) and torch.equal(x.data, y.data)
+                assert oa.state[x]['step'] == ob.state[y]['step'] == step + 1
+                assert torch.equal(oa.state[x]['exp_avg'], ob.state[y]['exp_avg'])
+                assert torch.equal(oa.state[x]['exp_avg_sq'], ob.state[y]['exp_avg_sq'])
+        # replicas stay identical across ranks
+        chk = pa[0].data.clone()
+        dist.broadcast(chk, 0)
+        assert torch.equal(chk, pa[0].data)
+        q.put((rank, 'ok'))
+    except Exception as e:
+        import traceback
+        q.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_pipelined_reduce_tv_adam_tail_gloo_world2():
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_tail_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, 'ok'), (1, 'ok')], res
+
+
 def test_ray_sharding_and_grad_exchange_gloo_world2():
     ctx = mp.get_context('spawn')
     q = ctx.Queue()

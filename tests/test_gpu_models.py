@@ -277,3 +277,33 @@ def test_progressive_growing_and_occupancy_utilities(oracle):
     assert torch.isfinite(out['rgb_marched']).all()
     hit = m.hit_coarse_geo(ro1, rd1, near=0., far=1e9, stepsize=0.5)
     assert hit.shape == (64,) and hit.dtype == torch.bool
+
+
+def test_reduce_tv_step_single_process_matches_tv_then_step():
+    """dist.reduce_tv_step at world 1 == total_variation_add_grad on both grids + MaskedAdam.step() (run_train.py:281-289)."""
+    from unboundednerfpytorch_b200 import dist as D, models
+    from unboundednerfpytorch_b200.masked_adam import create_optimizer_or_freeze_model
+    outs = []
+    for use_tail in (False, True):
+        torch.manual_seed(3)
+        m = models.FourierGridModel(xyz_min=[-1.] * 3, xyz_max=[1.] * 3, num_voxels_density=20 ** 3,
+                                    num_voxels_base_density=20 ** 3, num_voxels_rgb=20 ** 3, num_voxels_base_rgb=20 ** 3,
+                                    num_voxels_viewdir=-1, alpha_init=1e-4, fast_color_thres=0, rgbnet_dim=12,
+                                    fourier_freq_num=2).to(DEV)
+        opt = create_optimizer_or_freeze_model(m, dict(lrate_density=0.1, lrate_k0=0.1, lrate_rgbnet=1e-3, lrate_decay=20,
+                                                       skip_zero_grad_fields=['density', 'k0']), 0)
+        g = torch.Generator().manual_seed(9)
+        for p in m.parameters():
+            if not p.requires_grad:
+                continue
+            grad = (torch.randn(p.shape, generator=g) * (torch.rand(p.shape, generator=g) > 0.5)).to(DEV)
+            p.grad = torch.empty_like(p, memory_format=torch.preserve_format).copy_(grad)     # same layout as the parameter
+        if use_tail:
+            D.reduce_tv_step(opt, m.tv_terms(1e-3, 1e-4, True))
+        else:
+            m.density_total_variation_add_grad(1e-3, True)
+            m.k0_total_variation_add_grad(1e-4, True)
+            opt.step()
+        outs.append({k: v.detach().clone() for k, v in m.state_dict().items()})
+    for k in outs[0]:
+        assert torch.equal(outs[0][k], outs[1][k]), k

@@ -55,6 +55,59 @@ def allreduce_grads(params, world=None):
         h.wait()
 
 
+def _memory_order(t):
+    """Contiguous view of a channels-last 5-D grid (or the tensor itself) for a collective."""
+    if not t.is_contiguous() and t.dim() == 5:
+        t = t.permute(0, 2, 3, 4, 1)
+    return t
+
+
+@torch.no_grad()
+def reduce_tv_step(opt, tv=None):
+    """Tail of a ray-sharded training step: gradient all-reduce -> total variation -> MaskedAdam, pipelined per slab.
+
+    ``tv`` maps a grid parameter to ``(wx, wy, wz, dense_mode)`` (the arguments of ``total_variation_add_grad``).
+    Single process: exactly ``total_variation_add_grad`` on every listed grid followed by ``opt.step()``.
+    Several ranks: every slab ``grid[p]`` of a [P,C,X,Y,Z] grid is one all-reduce issued up front on the collective
+    stream; the compute stream then waits slab by slab and runs TV + Adam on slab p while slabs p+1.. are still on the
+    wire.  This is legal because neither sweep couples slabs: TV differences stay inside a slab
+    (total_variation_kernel.cu:22-33 -- the leading dims are peeled off by the modulo chain) and Adam is elementwise,
+    so the result equals all-reduce-everything -> TV -> step() bit for bit.  Single-slab grids (DenseGrid) are reduced
+    whole; the smaller density grid goes first so its sweeps hide behind the k0 transfer."""
+    from . import ops
+    tv = tv or {}
+    world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+    work = []                                             # (group, param, slice-or-None)
+    for group in opt.param_groups:
+        group['skip_zero_grad']
+        for param in group['params']:
+            if param.grad is None:
+                continue
+            if world > 1 and param.dim() == 5 and param.shape[0] > 1 and param.grad.stride() == param.stride():
+                work.extend((group, param, slice(p, p + 1)) for p in range(param.shape[0]))
+            else:
+                work.append((group, param, None))
+    work.sort(key=lambda w: w[1].numel())                 # stable: small tensors first, slabs stay in order
+    handles = []
+    if world > 1:
+        for _, param, sl in work:
+            g = param.grad if sl is None else param.grad[sl]
+            handles.append(dist.all_reduce(_memory_order(g), op=dist.ReduceOp.SUM, async_op=True))
+    states = {}
+    for i, (group, param, sl) in enumerate(work):
+        if handles:
+            handles[i].wait()
+        if param in tv:
+            wx, wy, wz, dense = tv[param]
+            if sl is None:
+                ops.total_variation_add_grad(param, param.grad, wx, wy, wz, dense)
+            else:
+                ops.total_variation_add_grad(param[sl], param.grad[sl], wx, wy, wz, dense)
+        if id(param) not in states:
+            states[id(param)] = opt._begin(param)
+        opt._apply(group, param, states[id(param)], sl)
+
+
 def gather_frame(local_out, n_total, rank, world, dst=0):
     """Render path: every rank rendered its contiguous shard of a frame ([n_local, K] rgb/depth/...) -> all ranks get
     the assembled [n_total, K] tensor (one all_gather of at most ceil(n_total/world) rows per rank)."""

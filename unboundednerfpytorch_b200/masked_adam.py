@@ -27,38 +27,46 @@ class MaskedAdam(torch.optim.Optimizer):
         assert self.param_groups[0]['params'][0].shape == count.shape
         self.per_lr = count.float() / count.max()
 
+    def _begin(self, param):
+        """Per-parameter bookkeeping of one optimizer step (state allocation + step counter, masked_adam.py:52-58)."""
+        state = self.state[param]
+        if len(state) == 0:
+            state['step'] = 0
+            state['exp_avg'] = torch.zeros_like(param, memory_format=torch.preserve_format)
+            state['exp_avg_sq'] = torch.zeros_like(param, memory_format=torch.preserve_format)
+        state['step'] += 1
+        return state
+
+    def _apply(self, group, param, state, sl=None):
+        """Run the update kernel on `param` (or on its leading-dim slice `sl`, used by the slab-pipelined
+        multi-GPU tail in dist.reduce_tv_step) -- same dispatch as masked_adam.py:62-75."""
+        lr, (beta1, beta2), eps = group['lr'], group['betas'], group['eps']
+        grad = param.grad
+        if grad.stride() != param.stride():
+            grad = torch.empty_like(param, memory_format=torch.preserve_format).copy_(grad)
+        per_lr = None
+        if self.per_lr is not None and param.shape == self.per_lr.shape:
+            per_lr = self.per_lr
+            if per_lr.stride() != param.stride():
+                per_lr = torch.empty_like(param, memory_format=torch.preserve_format).copy_(per_lr)
+                self.per_lr = per_lr
+        cut = (lambda t: t) if sl is None else (lambda t: t[sl])
+        p, g, m, v = cut(param), cut(grad), cut(state['exp_avg']), cut(state['exp_avg_sq'])
+        if per_lr is not None:
+            ops.adam_upd_with_perlr(p, g, m, v, cut(per_lr), state['step'], beta1, beta2, lr, eps)
+        elif group['skip_zero_grad']:                     # KeyError when absent, like masked_adam.py:49
+            ops.masked_adam_upd(p, g, m, v, state['step'], beta1, beta2, lr, eps)
+        else:
+            ops.adam_upd(p, g, m, v, state['step'], beta1, beta2, lr, eps)
+
     @torch.no_grad()
     def step(self):
         for group in self.param_groups:
-            lr = group['lr']
-            beta1, beta2 = group['betas']
-            eps = group['eps']
-            skip_zero_grad = group['skip_zero_grad']      # KeyError when absent, like masked_adam.py:49
+            group['skip_zero_grad']                       # KeyError when absent, like masked_adam.py:49
             for param in group['params']:
                 if param.grad is None:
                     continue
-                state = self.state[param]
-                if len(state) == 0:
-                    state['step'] = 0
-                    state['exp_avg'] = torch.zeros_like(param, memory_format=torch.preserve_format)
-                    state['exp_avg_sq'] = torch.zeros_like(param, memory_format=torch.preserve_format)
-                state['step'] += 1
-                grad = param.grad
-                if grad.stride() != param.stride():
-                    grad = torch.empty_like(param, memory_format=torch.preserve_format).copy_(grad)
-                if self.per_lr is not None and param.shape == self.per_lr.shape:
-                    per_lr = self.per_lr
-                    if per_lr.stride() != param.stride():
-                        per_lr = torch.empty_like(param, memory_format=torch.preserve_format).copy_(per_lr)
-                        self.per_lr = per_lr
-                    ops.adam_upd_with_perlr(param, grad, state['exp_avg'], state['exp_avg_sq'], per_lr,
-                                            state['step'], beta1, beta2, lr, eps)
-                elif skip_zero_grad:
-                    ops.masked_adam_upd(param, grad, state['exp_avg'], state['exp_avg_sq'],
-                                        state['step'], beta1, beta2, lr, eps)
-                else:
-                    ops.adam_upd(param, grad, state['exp_avg'], state['exp_avg_sq'],
-                                 state['step'], beta1, beta2, lr, eps)
+                self._apply(group, param, self._begin(param))
 
 
 def create_optimizer_or_freeze_model(model, cfg_train, global_step):

@@ -157,6 +157,16 @@ class _ContractedBase(nn.Module):
         w = weight * self._tv_world_max(self.k0) / 128
         self.k0.total_variation_add_grad(w, w, w, dense_mode)
 
+    def tv_terms(self, weight_density=0., weight_k0=0., dense_mode=True):
+        """{grid parameter: (wx, wy, wz, dense_mode)} with the weights of the two methods above -- the form
+        dist.reduce_tv_step consumes to pipeline all-reduce / TV / Adam slab by slab."""
+        out = {}
+        for grid, weight in ((self.density, weight_density), (self.k0, weight_k0)):
+            if weight > 0:
+                w = weight * self._tv_world_max(grid) / 128
+                out[grid.grid] = (w, w, w, dense_mode)
+        return out
+
     @staticmethod
     def _tv_world_max(g):
         return float(max(g.grid.shape[2:]))
@@ -631,6 +641,15 @@ class DirectVoxGO(nn.Module):
     def k0_total_variation_add_grad(self, weight, dense_mode):
         w = weight * float(self.world_size.max()) / 128
         self.k0.total_variation_add_grad(w, w, w, dense_mode)
+
+    def tv_terms(self, weight_density=0., weight_k0=0., dense_mode=True):
+        """{grid parameter: (wx, wy, wz, dense_mode)} for dist.reduce_tv_step (same weights as the two methods above)."""
+        out = {}
+        for grid, weight in ((self.density, weight_density), (self.k0, weight_k0)):
+            if weight > 0:
+                w = weight * float(self.world_size.max()) / 128
+                out[grid.grid] = (w, w, w, dense_mode)
+        return out
 
     def sample_ray(self, rays_o, rays_d, near, far, stepsize, **render_kwargs):
         """dvgo.py:306-328."""
