@@ -195,6 +195,14 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
 
+    # fd 1 carries exactly one JSON line: native libraries (NCCL's "NCCL version ..." banner) write to stderr instead
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(json_fd, (json.dumps(obj) + '\n').encode())
+
     from unboundednerfpytorch_b200 import dist as ubdist
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -219,7 +227,7 @@ def main():
                 'cpu_baseline': {'value': v, 'unit': 'ray-samples/s', 'cores': cores, 'kind': 'port',
                                  'sample': f'{args.cpu_rays} of {N_RAYS} rays x {N_SAMPLES} samples, same grids, fwd+loss+bwd (no TV/Adam sweeps on CPU)'},
                 'e2e': {'value': v, 'unit': 'ray-samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
-        print(json.dumps(line))
+        emit(line)
         return
 
     # ------------------------------------------------------------------ our arm
@@ -248,13 +256,26 @@ def main():
     host = [t.pin_memory() for t in synth_batch(N_RAYS, SEED + rank)]
     dev_batch = [t.to(dev) for t in host]
 
+    tail_events = []
+
     def train_step(ro, rd, vd, target, it):
         ret = model(ro, rd, vd, global_step=it, is_train=True, **rk)
         opt.zero_grad(set_to_none=True)
         loss = step_loss(ret, target, N_RAYS)
         loss.backward()
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
         # all-reduce (N > 1) -> dense TV -> MaskedAdam; per slab, so the sweeps of slab p overlap the transfer of slab p+1
-        ubdist.reduce_tv_step(opt, tv_terms)
+        if os.environ.get('UBN_BENCH_TAIL', 'pipelined') == 'sequential':     # A/B switch: whole-tensor all-reduce first
+            if world > 1:
+                ubdist.allreduce_grads(params)
+            model.density_total_variation_add_grad(1e-6 / N_RAYS, True)
+            model.k0_total_variation_add_grad(1e-7 / N_RAYS, True)
+            opt.step()
+        else:
+            ubdist.reduce_tv_step(opt, tv_terms)
+        ev[1].record()
+        tail_events.append(ev)
         return loss
 
     def sync_all():
@@ -296,15 +317,17 @@ def main():
     clocks.mark()
     _cabi.TIMER = _cabi.KernelTimer()
     _cabi.reset_launch_count()
+    del tail_events[:]
     ms_total = timed_region(dev_step, args.steps)
+    tail_ms = sum(a.elapsed_time(b) for a, b in tail_events) / max(len(tail_events), 1)   # all-reduce + TV + Adam per step
     launches = _cabi.launch_count()
     ktimes = _cabi.TIMER.summary()
     _cabi.TIMER = None
     clk = clocks.stop() if rank == 0 else None
     if args.only_timed:
         if rank == 0:
-            print(json.dumps({'only_timed': True, 'ms_per_step': ms_total / args.steps, 'gpu_launches': launches,
-                              'kernels_ms': {k: round(v[0], 4) for k, v in ktimes.items()}}))
+            emit({'only_timed': True, 'ms_per_step': ms_total / args.steps, 'gpu_launches': launches,
+                  'kernels_ms': {k: round(v[0], 4) for k, v in ktimes.items()}})
         if world > 1:
             torch.distributed.destroy_process_group()
         return
@@ -363,6 +386,8 @@ def main():
             'e2e': {'value': samples_per_step / (ms_e2e / args.steps * 1e-3), 'unit': 'ray-samples/s',
                     'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4, 'ms_per_step': ms_e2e / args.steps},
             'gpu_launches': launches, 'roofline': roof,
+            'tail_ms': {'value': tail_ms, 'what': 'gradient all-reduce (N>1) + dense TV + MaskedAdam, per step',
+                        'mode': os.environ.get('UBN_BENCH_TAIL', 'pipelined')},
             'fwd_only': {'value': samples_per_step / (ms_fwd / args.steps * 1e-3), 'unit': 'ray-samples/s',
                          'ms_per_step': ms_fwd / args.steps}}
     if not args.no_cpu_baseline:
@@ -373,7 +398,7 @@ def main():
                                               f'{sec:.1f} s/step'}
         except Exception as e:                                           # never lose the GPU numbers to a CPU-side problem
             line['cpu_baseline'] = {'value': None, 'unit': 'ray-samples/s', 'cores': cores, 'kind': 'port', 'sample': f'failed: {e}'}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         torch.distributed.destroy_process_group()
 

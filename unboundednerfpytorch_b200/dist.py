@@ -20,7 +20,12 @@ def init_from_env(backend=None):
         backend = backend or ('nccl' if torch.cuda.is_available() else 'gloo')
         if backend == 'nccl':
             torch.cuda.set_device(local)
-            dist.init_process_group(backend=backend, device_id=torch.device('cuda', local))
+            opts = None
+            if os.environ.get('UBN_NCCL_HIGH_PRIORITY', '1') != '0':
+                # collectives run on a high-priority stream so that their few CTAs are placed ahead of the queued CTAs of
+                # the full-grid sweeps they overlap with (reduce_tv_step)
+                opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+            dist.init_process_group(backend=backend, device_id=torch.device('cuda', local), pg_options=opts)
         else:
             dist.init_process_group(backend=backend)
     return rank, world, local
