@@ -181,13 +181,78 @@ def cpu_reference_step(flavor, kwargs, stepsize, n_rays, threads, steps, warmup)
     return n_rays * S / (sum(times) / len(times)), sum(times) / len(times)
 
 
+def gpu_reference_step(flavor, kwargs, stepsize, steps, warmup, dev):
+    """"also time the patched reference CUDA path on the same B200 (the real competitor)".
+    The reference's GPU training step op for op: its Python algorithm (oracle.cpu_ref.model_forward on CUDA tensors: ATen
+    grid_sample, cuBLAS rgbnet, index_add for torch_scatter) + the reference's OWN CUDA extension compiled from
+    /root/reference into oracle/_ref (raw2alpha / alpha2weight / maskcache / cumdist / total_variation / masked Adam),
+    grids in the reference layout.  A baseline leg like cpu_baseline: nothing of this repo's library runs here.
+    Returns (ms_per_step, survivors) or None when oracle/_ref is absent."""
+    import importlib.util
+    import types
+    from oracle import cpu_ref
+    from unboundednerfpytorch_b200 import models
+    mods = {}
+    for name in ('render_utils_cuda', 'total_variation_cuda', 'adam_upd_cuda', 'ub360_utils_cuda'):
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'oracle', '_ref', name + '.so')
+        if not os.path.exists(path):
+            return None
+        spec = importlib.util.spec_from_file_location(name, path)
+        mods[name] = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mods[name])
+    ru = mods['render_utils_cuda']
+    ext = types.SimpleNamespace(raw2alpha=ru.raw2alpha, raw2alpha_backward=ru.raw2alpha_backward, alpha2weight=ru.alpha2weight,
+                                alpha2weight_backward=ru.alpha2weight_backward, maskcache_lookup=ru.maskcache_lookup,
+                                cumdist_thres=mods['ub360_utils_cuda'].cumdist_thres)
+    torch.manual_seed(SEED)
+    cls = models.FourierGridModel if flavor == 'fouriergrid' else models.DirectContractedVoxGO
+    m = cls(**kwargs)                                  # CPU tensors; shape / init recipe only
+    g = torch.Generator().manual_seed(SEED)
+    with torch.no_grad():
+        m.density.grid.copy_(torch.randn(m.density.grid.shape, generator=g))
+        m.k0.grid.copy_(torch.randn(m.k0.grid.shape, generator=g))
+    state = {k: v.detach().clone().contiguous() for k, v in m.state_dict().items()}     # reference layout [P,C,X,Y,Z]
+    del m
+    p = cpu_ref.params_from_state(flavor, kwargs, state, requires_grad=False)
+    for k, v in list(p.items()):
+        if torch.is_tensor(v):
+            p[k] = v.to(dev)
+    p['rgbnet'] = {k: v.to(dev).requires_grad_(True) for k, v in p['rgbnet'].items()}
+    for k in ('density_grid', 'k0_grid'):
+        p[k] = p[k].requires_grad_(True)
+    grids = [p['density_grid'], p['k0_grid']]
+    leaves = grids + list(p['rgbnet'].values())
+    adam = [(torch.zeros_like(x), torch.zeros_like(x)) for x in leaves]
+    ro, rd, vd, target = [t.to(dev) for t in synth_batch(N_RAYS, SEED)]
+    w_d = 1e-6 / N_RAYS * p['world_len'] / 128
+    w_k = 1e-7 / N_RAYS * p['world_len'] / 128
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for it in range(1, warmup + steps + 1):
+        if it == warmup + 1:
+            torch.cuda.synchronize()
+            e0.record()
+        for x in leaves:
+            x.grad = None
+        ret = cpu_ref.model_forward(flavor, p, ro, rd, vd, stepsize, bg=1, rand_bkgd=False, render_depth=False, ext=ext)
+        step_loss(ret, target, N_RAYS).backward()
+        with torch.no_grad():
+            mods['total_variation_cuda'].total_variation_add_grad(grids[0], grids[0].grad, w_d, w_d, w_d, True)
+            mods['total_variation_cuda'].total_variation_add_grad(grids[1], grids[1].grad, w_k, w_k, w_k, True)
+            for i, (x, (m1, m2)) in enumerate(zip(leaves, adam)):
+                fn = mods['adam_upd_cuda'].masked_adam_upd if i < 2 else mods['adam_upd_cuda'].adam_upd
+                fn(x, x.grad.contiguous(), m1, m2, it, 0.9, 0.99, 0.1 if i < 2 else 1e-3, 1e-8)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps, int(ret['weights'].numel())
+
+
 # ----------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
-    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference', 'reference-gpu'])
     ap.add_argument('--workload', default='truck', choices=['truck', 'bicycle'])
     ap.add_argument('--cpu-rays', type=int, default=256, help='ray sample of the CPU baseline (bounded)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -230,7 +295,24 @@ def main():
         emit(line)
         return
 
-    # ------------------------------------------------------------------ our arm
+    # ------------------------------------------------------------------ informative: the reference's GPU path on this B200
+    if args.impl == 'reference-gpu':
+        if rank != 0:
+            return
+        dev = torch.device('cuda', 0)
+        out = gpu_reference_step(flavor, kwargs, stepsize, max(args.steps, 1), max(args.warmup, 1), dev)
+        if out is None:
+            emit({'impl': 'reference-gpu', 'unavailable': 'oracle/_ref not built (needs /root/reference at build time)'})
+            return
+        ms, surv = out
+        emit({'impl': 'reference-gpu', 'metric': 'ray-samples/sec (fwd+bwd train step) 8192x512',
+              'value': N_RAYS * N_SAMPLES / (ms * 1e-3), 'unit': 'ray-samples/s', 'n_gpus': 1, 'steps': args.steps,
+              'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'dtype': 'f32', 'data': 'synthetic',
+              'config': config, 'survivors': surv,
+              'what': "reference algorithm op by op on CUDA: ATen grid_sample + cuBLAS rgbnet + the reference's own CUDA "
+                      "extension (oracle/_ref) for raw2alpha / alpha2weight / TV / masked Adam; none of this repo's kernels"})
+        return
+
     if not torch.cuda.is_available():
         raise SystemExit('bench.py --impl ours needs a GPU (no CPU fallback exists)')
     rank, world, local = ubdist.init_from_env()

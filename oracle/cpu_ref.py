@@ -360,54 +360,73 @@ def rgbnet_forward(feat, w):
 # --------------------------------------------------------------------------------------
 # autograd wrappers over the C oracle (dvgo.py:430-488 semantics) and full model forwards
 # --------------------------------------------------------------------------------------
-class _Raw2Alpha(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, density, shift, interval):
-        exp_d, alpha = raw2alpha(density, shift, interval)
-        ctx.save_for_backward(exp_d)
-        ctx.interval = float(interval)
-        return alpha
+def _autograd_fns(ext):
+    """Raw2Alpha / Alphas2Weights autograd Functions (dvgo.py:430-488) over `ext`: this module (the C restatement, CPU) or a
+    namespace holding the reference's own CUDA extension functions from oracle/_ref (GPU leg of the oracle)."""
+    if id(ext) in _fn_cache:
+        return _fn_cache[id(ext)][1]
 
-    @staticmethod
-    def backward(ctx, g):
-        return raw2alpha_backward(ctx.saved_tensors[0], g.contiguous(), ctx.interval), None, None
+    class _Raw2Alpha(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, density, shift, interval):
+            exp_d, alpha = ext.raw2alpha(density, shift, interval)
+            ctx.save_for_backward(exp_d)
+            ctx.interval = float(interval)
+            return alpha
+
+        @staticmethod
+        def backward(ctx, g):
+            return ext.raw2alpha_backward(ctx.saved_tensors[0], g.contiguous(), ctx.interval), None, None
+
+    class _Alphas2Weights(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, alpha, ray_id, n_rays):
+            w, T, last, i_s, i_e = ext.alpha2weight(alpha, ray_id, n_rays)
+            ctx.save_for_backward(alpha, w, T, last, i_s, i_e)
+            ctx.n_rays = n_rays
+            return w, last
+
+        @staticmethod
+        def backward(ctx, gw, gl):
+            alpha, w, T, last, i_s, i_e = ctx.saved_tensors
+            return ext.alpha2weight_backward(alpha, w, T, last, i_s, i_e, ctx.n_rays, gw.contiguous(), gl.contiguous()), None, None
+
+    _fn_cache[id(ext)] = (ext, (_Raw2Alpha, _Alphas2Weights))      # keeps ext alive so the id stays unique
+    return _fn_cache[id(ext)][1]
 
 
-class _Alphas2Weights(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, alpha, ray_id, n_rays):
-        w, T, last, i_s, i_e = alpha2weight(alpha, ray_id, n_rays)
-        ctx.save_for_backward(alpha, w, T, last, i_s, i_e)
-        ctx.n_rays = n_rays
-        return w, last
-
-    @staticmethod
-    def backward(ctx, gw, gl):
-        alpha, w, T, last, i_s, i_e = ctx.saved_tensors
-        return alpha2weight_backward(alpha, w, T, last, i_s, i_e, ctx.n_rays, gw.contiguous(), gl.contiguous()), None, None
+_fn_cache = {}
 
 
 def model_forward(flavor, p, rays_o, rays_d, viewdirs, stepsize, bg=1, rand_bkgd=False, is_train=False,
-                  render_depth=True):
+                  render_depth=True, ext=None):
     """CPU restatement of FourierGridModel.forward (flavor='fouriergrid', FourierGrid_model.py:554-672) and
     DirectContractedVoxGO.forward (flavor='dcvgo', dcvgo.py:264-384).
 
     p: dict(density_grid [Pd,1,X,Y,Z], k0_grid [Pk,C,X,Y,Z], rgbnet=dict(W1,b1,W2,b2,W3,b3)|None, act_shift,
             scene_center[3], scene_radius[3], bg_len, contracted_norm, fast_color_thres, voxel_size_ratio,
             world_len, freq_density, freq_k0, viewfreq, mask (bool [X,Y,Z], dcvgo), mask_scale, mask_shift)
-    Tensors with requires_grad=True in p receive gradients through the returned dict."""
+    Tensors with requires_grad=True in p receive gradients through the returned dict.
+
+    Device-agnostic: with CPU tensors and ext=None the CUDA-only ops come from the C restatement in this module; with CUDA
+    tensors and ext = the reference's own extension functions (oracle/_ref) this is the reference's GPU path op for op
+    (ATen grid_sample, cuBLAS rgbnet, index_add in place of torch_scatter)."""
+    import sys
+    ext = ext if ext is not None else sys.modules[__name__]
+    _Raw2Alpha, _Alphas2Weights = _autograd_fns(ext)
+    dev = rays_o.device
     N = rays_o.shape[0]
     bg_len = p['bg_len']
-    gmin = torch.tensor([-1., -1., -1.]) - bg_len
-    gmax = torch.tensor([1., 1., 1.]) + bg_len
+    gmin = torch.tensor([-1., -1., -1.], device=dev) - bg_len
+    gmax = torch.tensor([1., 1., 1.], device=dev) + bg_len
     t_boundary = 1.5 if flavor == 'fouriergrid' else 2.0
-    t = contracted_t_schedule(p['world_len'], stepsize, bg_len, t_boundary)
+    t = contracted_t_schedule(p['world_len'], stepsize, bg_len, t_boundary).to(dev)
     ray_pts, inner_mask = contracted_sample_ray(rays_o, rays_d, p['scene_center'], p['scene_radius'], t, bg_len,
                                                 p['contracted_norm'])
     S = len(t)
     interval = stepsize * float(p['voxel_size_ratio'])
-    ray_id = torch.arange(N).view(-1, 1).expand(N, S).flatten()
-    step_id = torch.arange(S).view(1, -1).expand(N, S).flatten()
+    ray_id = torch.arange(N, device=dev).view(-1, 1).expand(N, S).flatten()
+    step_id = torch.arange(S, device=dev).view(1, -1).expand(N, S).flatten()
     tt = t[None].repeat(N, 1)
     thres = p['fast_color_thres']
 
@@ -421,10 +440,10 @@ def model_forward(flavor, p, rays_o, rays_d, viewdirs, stepsize, bg=1, rand_bkgd
         mask = inner_mask.clone()
         dist_thres = (2 + 2 * bg_len) / p['world_len'] * stepsize * 0.95
         dist = (ray_pts[:, 1:] - ray_pts[:, :-1]).norm(dim=-1)
-        mask[:, 1:] |= cumdist_thres(dist, dist_thres)
+        mask[:, 1:] |= ext.cumdist_thres(dist.contiguous(), dist_thres)
         ray_pts, inner_mask, tt = ray_pts[mask], inner_mask[mask], tt[mask]
         ray_id, step_id = ray_id[mask.flatten()], step_id[mask.flatten()]
-        mask = maskcache_lookup(p['mask'], ray_pts.contiguous(), p['mask_scale'], p['mask_shift'])
+        mask = ext.maskcache_lookup(p['mask'], ray_pts.contiguous(), p['mask_scale'], p['mask_shift'])
         ray_pts, inner_mask, tt, ray_id, step_id = ray_pts[mask], inner_mask[mask], tt[mask], ray_id[mask], step_id[mask]
     else:
         ray_pts, inner_mask, tt = ray_pts.reshape(-1, 3), inner_mask.reshape(-1), tt.reshape(-1)
@@ -445,7 +464,7 @@ def model_forward(flavor, p, rays_o, rays_d, viewdirs, stepsize, bg=1, rand_bkgd
     else:
         emb = view_embedding(viewdirs, p['viewfreq']).flatten(0, -2)[ray_id]
         rgb = torch.sigmoid(rgbnet_forward(torch.cat([k0, emb], -1), p['rgbnet']))
-    rgb_marched = torch.zeros(N, 3).index_add_(0, ray_id, weights.unsqueeze(-1) * rgb)
+    rgb_marched = torch.zeros(N, 3, device=dev).index_add_(0, ray_id, weights.unsqueeze(-1) * rgb)
     if flavor == 'dcvgo':
         if rand_bkgd and is_train:
             rgb_marched = rgb_marched + alphainv_last.unsqueeze(-1) * torch.rand_like(rgb_marched)
@@ -457,10 +476,10 @@ def model_forward(flavor, p, rays_o, rays_d, viewdirs, stepsize, bg=1, rand_bkgd
     ret = dict(alphainv_last=alphainv_last, weights=weights, rgb_marched=rgb_marched, raw_density=density, raw_alpha=alpha,
                raw_rgb=rgb, ray_id=ray_id, step_id=step_id, n_max=S, t=tt, s=s)
     if flavor == 'dcvgo':
-        ret['wsum_mid'] = torch.zeros(N).index_add_(0, ray_id[inner_mask], weights[inner_mask])
+        ret['wsum_mid'] = torch.zeros(N, device=dev).index_add_(0, ray_id[inner_mask], weights[inner_mask])
     if render_depth:
         with torch.no_grad():
-            ret['depth'] = torch.zeros(N).index_add_(0, ray_id, weights * s)
+            ret['depth'] = torch.zeros(N, device=dev).index_add_(0, ray_id, weights * s)
     return ret
 
 

@@ -247,7 +247,8 @@ def test_cumdist_thres(ops, oracle, n_rays, n_pts):
 
 
 @pytest.mark.parametrize('shape,layout', [((1, 1, 5, 6, 7), 'ref'), ((1, 12, 9, 8, 10), 'ref'), ((9, 12, 6, 5, 7), 'cl'),
-                                          ((1, 3, 33, 20, 41), 'cl')])
+                                          ((1, 3, 33, 20, 41), 'cl'), ((2, 12, 20, 9, 11), 'cl'),
+                                          ((1, 12, 40, 70, 11), 'cl'), ((3, 4, 17, 33, 40), 'cl')])
 def test_total_variation(ops, oracle, shape, layout):
     from unboundednerfpytorch_b200 import grid as G
     g = torch.Generator().manual_seed(sum(shape))

@@ -6,6 +6,9 @@
 // a11/a12), so they are written as HBM-streaming kernels: 32-bit magic-number index decomposition
 // (no 64-bit div/mod per element), 128-bit accesses where the layout allows, and no write traffic for
 // elements masked Adam leaves untouched.
+#include <algorithm>
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace ubn {
@@ -90,6 +93,98 @@ __device__ __forceinline__ float tv_term(const float* __restrict__ param, int64_
   add += (c.i == 0 ? 0 : wz * clamp1(p - param[m - g.si]));
   add += (c.i == g.i.d - 1 ? 0 : wz * clamp1(p - param[m + g.si]));
   return add;
+}
+
+// Same sum as tv_term with the six neighbour values already in registers (h* = neighbour exists).
+__device__ __forceinline__ float tv_term_vals(float p, float km, float kp, float jm, float jp, float im, float ip,
+                                              bool hkm, bool hkp, bool hjm, bool hjp, bool him, bool hip, float wy,
+                                              float wz) {
+  float add = 0;
+  add += (!hkm ? 0 : wz * clamp1(p - km));
+  add += (!hkp ? 0 : wz * clamp1(p - kp));
+  add += (!hjm ? 0 : wy * clamp1(p - jm));
+  add += (!hjp ? 0 : wy * clamp1(p - jp));
+  add += (!him ? 0 : wz * clamp1(p - im));
+  add += (!hip ? 0 : wz * clamp1(p - ip));
+  return add;
+}
+
+// 2.5-D streaming TV for channels-last grids (inner % 4 == 0, memory [lead][i][j][k][inner]).
+// The element-per-thread kernel above fetches five of its seven parameter values from L2 (the j and i neighbours are
+// 7 KB / 1 MB away and belong to CTAs on other SMs): ~28 B of L2->SM traffic per element, which is what bounds it.
+// Here a CTA owns a tile of `tj` full (k, inner) rows of one slab and walks the i axis: a thread keeps the i-1 / i / i+1
+// values of its float4 column in registers, so every parameter value is requested from L2 once (as "next"); the k and
+// j neighbours of the current plane were brought into L1 by this CTA one iteration earlier.  Only the two halo rows
+// of the tile come from other CTAs' territory.  Arithmetic is tv_term's, element for element.
+constexpr int kTvsThreads = 512;
+constexpr int kTvsCols = 2;      // float4 columns per thread
+
+struct TvStreamShape {
+  int sz_i, sz_j, row4, inner4;  // row4 = sz_k * inner / 4 float4 per (i, j) row; inner4 = inner / 4
+  int tj, n_jt, seg_len, n_seg;  // rows per tile, tiles along j, planes per i-segment, segments
+};
+
+template <bool kDense>
+__global__ void __launch_bounds__(kTvsThreads, 2) k_total_variation_stream(const float4* __restrict__ param,
+                                                                           float4* __restrict__ grad, float wy,
+                                                                           float wz, TvStreamShape s) {
+  int b = blockIdx.x;
+  const int seg = b % s.n_seg; b /= s.n_seg;
+  const int jt = b % s.n_jt;
+  const int lead = b / s.n_jt;
+  const int j0 = jt * s.tj;
+  const int rows = min(s.tj, s.sz_j - j0);
+  const int i0 = seg * s.seg_len;
+  const int i1 = min(i0 + s.seg_len, s.sz_i);
+  const int64_t plane4 = (int64_t)s.sz_j * s.row4;
+  const int64_t base = ((int64_t)lead * s.sz_i + i0) * plane4 + (int64_t)j0 * s.row4;
+  const int cols = rows * s.row4;
+
+  int64_t off[kTvsCols];
+  bool live[kTvsCols], hkm[kTvsCols], hkp[kTvsCols], hjm[kTvsCols], hjp[kTvsCols];
+  float4 prev[kTvsCols], cur[kTvsCols];
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int c = 0; c < kTvsCols; ++c) {
+    const int col = threadIdx.x + c * kTvsThreads;
+    live[c] = col < cols;
+    const int jj = live[c] ? col / s.row4 : 0;
+    const int r = live[c] ? col - jj * s.row4 : 0;
+    off[c] = base + (int64_t)jj * s.row4 + r;
+    hkm[c] = r >= s.inner4;
+    hkp[c] = r < s.row4 - s.inner4;
+    hjm[c] = j0 + jj > 0;
+    hjp[c] = j0 + jj < s.sz_j - 1;
+    prev[c] = (live[c] && i0 > 0) ? param[off[c] - plane4] : zero4;
+    cur[c] = live[c] ? param[off[c]] : zero4;
+  }
+  for (int i = i0; i < i1; ++i) {
+    const bool him = i > 0, hip = i < s.sz_i - 1;
+    float4 next[kTvsCols], g[kTvsCols];
+#pragma unroll
+    for (int c = 0; c < kTvsCols; ++c) {     // the two long-latency streams first
+      next[c] = (live[c] && hip) ? param[off[c] + plane4] : zero4;
+      g[c] = live[c] ? grad[off[c]] : zero4;
+    }
+#pragma unroll
+    for (int c = 0; c < kTvsCols; ++c) {
+      if (!live[c]) continue;
+      const float4 p = cur[c];
+      const float4 km = hkm[c] ? param[off[c] - s.inner4] : zero4;
+      const float4 kp = hkp[c] ? param[off[c] + s.inner4] : zero4;
+      const float4 jm = hjm[c] ? param[off[c] - s.row4] : zero4;
+      const float4 jp = hjp[c] ? param[off[c] + s.row4] : zero4;
+      float4 o = g[c];
+      if (kDense || o.x != 0) o.x = o.x + tv_term_vals(p.x, km.x, kp.x, jm.x, jp.x, prev[c].x, next[c].x, hkm[c], hkp[c], hjm[c], hjp[c], him, hip, wy, wz);
+      if (kDense || o.y != 0) o.y = o.y + tv_term_vals(p.y, km.y, kp.y, jm.y, jp.y, prev[c].y, next[c].y, hkm[c], hkp[c], hjm[c], hjp[c], him, hip, wy, wz);
+      if (kDense || o.z != 0) o.z = o.z + tv_term_vals(p.z, km.z, kp.z, jm.z, jp.z, prev[c].z, next[c].z, hkm[c], hkp[c], hjm[c], hjp[c], him, hip, wy, wz);
+      if (kDense || o.w != 0) o.w = o.w + tv_term_vals(p.w, km.w, kp.w, jm.w, jp.w, prev[c].w, next[c].w, hkm[c], hkp[c], hjm[c], hjp[c], him, hip, wy, wz);
+      if (kDense || g[c].x != 0 || g[c].y != 0 || g[c].z != 0 || g[c].w != 0) grad[off[c]] = o;
+      prev[c] = p;
+      cur[c] = next[c];
+      off[c] += plane4;
+    }
+  }
 }
 
 template <bool kDense, bool kWide>
@@ -248,6 +343,39 @@ static int launch_adam_zero(float* param, float* grad, float* m, float* v, int64
   return 0;
 }
 
+// UBN_TV_IMPL=0 forces the element-per-thread kernel (A/B and parity tests).
+static bool tv_stream_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("UBN_TV_IMPL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+static bool launch_tv_stream(const float* param, float* grad, float wy, float wz, int64_t lead, int64_t sz_i,
+                             int64_t sz_j, int64_t sz_k, int64_t inner, bool dense, cudaStream_t st) {
+  if (!tv_stream_enabled() || inner % 4 != 0 || sz_i < 8) return false;
+  if ((((uintptr_t)param) | ((uintptr_t)grad)) & 15) return false;
+  const int64_t row4 = sz_k * inner / 4;
+  if (row4 > kTvsThreads * kTvsCols || row4 < 32) return false;
+  TvStreamShape s;
+  s.sz_i = (int)sz_i; s.sz_j = (int)sz_j; s.row4 = (int)row4; s.inner4 = (int)(inner / 4);
+  s.tj = (int)std::max<int64_t>(1, (kTvsThreads * kTvsCols) / row4);
+  s.n_jt = (int)((sz_j + s.tj - 1) / s.tj);
+  // enough CTAs for ~8 waves of 2 x 148 resident CTAs, segments no shorter than 16 planes (one halo plane each)
+  const int64_t tiles = lead * s.n_jt;
+  int64_t n_seg = (8 * 2 * 148 + tiles - 1) / tiles;
+  n_seg = std::max<int64_t>(1, std::min<int64_t>(n_seg, sz_i / 16));
+  s.seg_len = (int)((sz_i + n_seg - 1) / n_seg);
+  s.n_seg = (int)((sz_i + s.seg_len - 1) / s.seg_len);
+  const int64_t nb = tiles * s.n_seg;
+  if (nb > 0x7fffffffll) return false;
+  if (dense) k_total_variation_stream<true><<<(unsigned)nb, kTvsThreads, 0, st>>>((const float4*)param, (float4*)grad, wy, wz, s);
+  else       k_total_variation_stream<false><<<(unsigned)nb, kTvsThreads, 0, st>>>((const float4*)param, (float4*)grad, wy, wz, s);
+  return true;
+}
+
 static int launch_tv(const float* param, float* grad, float wy, float wz, const GridShape& g, bool dense,
                      cudaStream_t st) {
   const bool wide = g.n >= (1ll << 31);
@@ -277,6 +405,10 @@ int ubn_total_variation_add_grad(const float* param, float* grad, float wx, floa
   if (g.n <= 0) return 0;
   wy /= 6;   // host-side pre-division, total_variation_kernel.cu:45-47
   wz /= 6;
+  if (launch_tv_stream(param, grad, wy, wz, lead, sz_i, sz_j, sz_k, inner, dense_mode != 0, as_stream(stream))) {
+    UBN_LAUNCH_CHECK();
+    return 0;
+  }
   return launch_tv(param, grad, wy, wz, g, dense_mode != 0, as_stream(stream));
 }
 
