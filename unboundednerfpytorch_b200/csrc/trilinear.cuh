@@ -108,6 +108,33 @@ __device__ __forceinline__ void trilerp1_scatter(float* __restrict__ slab, int64
   }
 }
 
+// 64-bit vector reduction (sm_90+): two consecutive floats at an 8-byte aligned address in one L2 atomic operation
+__device__ __forceinline__ void red_add_v2(float* addr, float a, float b) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
+}
+
+// trilerp1_scatter for unit voxel stride: the two z corners of an (x, y) edge are adjacent floats, so when both are
+// inside and the lower one is 8-byte aligned they go out as ONE vector reduction (the scatter is bound by the number of
+// L2 atomic operations, not by bytes).  Same addends as the scalar form.
+__device__ __forceinline__ void trilerp1_scatter_pairs(float* __restrict__ slab, int X, int Y, int Z, float cx, float cy,
+                                                       float cz, float g) {
+  const Cell c = locate(cx, cy, cz);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int bx = e >> 1, by = e & 1;
+    const bool in0 = corner_inside(c, bx, by, 0, X, Y, Z), in1 = corner_inside(c, bx, by, 1, X, Y, Z);
+    if (!(in0 || in1)) continue;
+    float* a = slab + ((int64_t)(c.x0 + bx) * Y + (c.y0 + by)) * Z + c.z0;
+    const float w0 = corner_weight(c, bx, by, 0) * g, w1 = corner_weight(c, bx, by, 1) * g;
+    if (in0 && in1 && ((reinterpret_cast<uintptr_t>(a) & 7) == 0)) {
+      red_add_v2(a, w0, w1);
+    } else {
+      if (in0) atomicAdd(a, w0);
+      if (in1) atomicAdd(a + 1, w1);
+    }
+  }
+}
+
 // 128-bit vector reduction (sm_90+): one instruction adds 4 consecutive floats at a 16-byte aligned address
 __device__ __forceinline__ void red_add_v4(float* addr, float4 v) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
