@@ -14,8 +14,6 @@
 //     instead of recomputing two 128^3-per-tile GEMMs on CUDA cores.
 // Backward: dZ2 = (dz3 . W3) * [H2>0]; dW2 += dZ2^T H1; dH1 = dZ2 W2; dZ1 = dH1 * [H1>0]; dW1k += dZ1^T X;
 // dX = dZ1 W1k; dvb[ray] += dZ1 (the host turns dvb into dW1[:,12:], db1 with the same tiny GEMM).
-#include <cstdlib>
-
 #include "common.cuh"
 
 namespace ubn {
@@ -440,14 +438,12 @@ struct SmallSmem {
   static constexpr int oDZ = 0;                               // dZ1s[s][k]  64 x 132
   static constexpr int oX = oDZ + kBwdTile * kRow;            // Xs[s][k']   64 x 12
   static constexpr int oW1 = oX + kBwdTile * kF;              // W1k[j][k']  128 x 12
-  static constexpr int kW1Row = kW + 4;                       // padded row of the transposed W1k (bank-conflict free)
-  static constexpr int oW3 = oW1 + kF * kW1Row;               // W3[c][j]
+  static constexpr int oW3 = oW1 + kW * kF;                   // W3[c][j]
   static constexpr int oDz3 = oW3 + 3 * kW;
   static constexpr int oRay = oDz3 + kBwdTile * 4;
   static constexpr int kFloats = oRay + kBwdTile;
 };
 
-template <bool kVec>
 __global__ void __launch_bounds__(kThreads, 2) k_shade_bwd_small(
     const float* __restrict__ feat, const int64_t* __restrict__ ray_id, const float* __restrict__ W1k,
     const float* __restrict__ W3, const float* __restrict__ rgb, const float* __restrict__ h2,
@@ -464,11 +460,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_shade_bwd_small(
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
   constexpr int R = SmallSmem::kRow;
-  if (kVec) {
-    for (int i = tid; i < kW * kF; i += kThreads) sW1[(i % kF) * SmallSmem::kW1Row + i / kF] = W1k[i];   // transposed sW1[k'][j], padded rows
-  } else {
-    for (int i = tid; i < kW * kF; i += kThreads) sW1[i] = W1k[i];
-  }
+  for (int i = tid; i < kW * kF; i += kThreads) sW1[i] = W1k[i];
   for (int i = tid; i < 3 * kW; i += kThreads) sW3[i] = W3[i];
   __syncthreads();
   float w3[3][8];
@@ -476,11 +468,11 @@ __global__ void __launch_bounds__(kThreads, 2) k_shade_bwd_small(
   for (int c = 0; c < 3; ++c)
 #pragma unroll
     for (int jj = 0; jj < 8; ++jj) w3[c][jj] = sW3[c * kW + jj * 16 + tx];
-  float aB2[8], aW3[3][8], aW1[kF], aB3[3] = {0.f, 0.f, 0.f};
+  float aB2[8], aW3[3][8], aW1[6], aB3[3] = {0.f, 0.f, 0.f};
 #pragma unroll
   for (int jj = 0; jj < 8; ++jj) { aB2[jj] = 0.f; aW3[0][jj] = aW3[1][jj] = aW3[2][jj] = 0.f; }
 #pragma unroll
-  for (int q = 0; q < kF; ++q) aW1[q] = 0.f;
+  for (int q = 0; q < 6; ++q) aW1[q] = 0.f;
   float run[8];
   int run_ray = -1;
 #pragma unroll
@@ -555,45 +547,6 @@ __global__ void __launch_bounds__(kThreads, 2) k_shade_bwd_small(
         run[4] += v1.x; run[5] += v1.y; run[6] += v1.z; run[7] += v1.w;
       }
     }
-    if (kVec) {
-    // dW1k[j][0..11] += dZ1[s][j] * X[s][0..11]: thread = (hidden unit j, sample parity); X rows are three broadcast
-    // LDS.128, so 12 FMAs cost 4 shared-memory wavefronts (the first version spent 7 wavefronts per 6 FMAs and the
-    // kernel was LDS-bound); the two parities are merged by the atomics at the end.
-    {
-      const int j = tid & 127;
-#pragma unroll 4
-      for (int s = tid >> 7; s < kBwdTile; s += 2) {
-        const float d = sDZ[s * R + j];
-        const float4 xa = *reinterpret_cast<const float4*>(sX + s * kF);
-        const float4 xb = *reinterpret_cast<const float4*>(sX + s * kF + 4);
-        const float4 xc = *reinterpret_cast<const float4*>(sX + s * kF + 8);
-        aW1[0] = fmaf(d, xa.x, aW1[0]); aW1[1] = fmaf(d, xa.y, aW1[1]); aW1[2] = fmaf(d, xa.z, aW1[2]);
-        aW1[3] = fmaf(d, xa.w, aW1[3]); aW1[4] = fmaf(d, xb.x, aW1[4]); aW1[5] = fmaf(d, xb.y, aW1[5]);
-        aW1[6] = fmaf(d, xb.z, aW1[6]); aW1[7] = fmaf(d, xb.w, aW1[7]); aW1[8] = fmaf(d, xc.x, aW1[8]);
-        aW1[9] = fmaf(d, xc.y, aW1[9]); aW1[10] = fmaf(d, xc.z, aW1[10]); aW1[11] = fmaf(d, xc.w, aW1[11]);
-      }
-    }
-    // dX[s][kk..kk+2] = sum_j dZ1[s][j] * W1k[j][kk..]: thread = (sample, channel triple); four hidden units per step
-    // with one LDS.128 of the dZ1 row and three LDS.128 of the transposed weights (4 wavefronts per 12 FMAs).
-    {
-      const int s = tid >> 2, kk = 3 * (tid & 3);
-      float x0 = 0.f, x1 = 0.f, x2 = 0.f;
-#pragma unroll 4
-      for (int jx = 0; jx < kW; jx += 4) {
-        const float4 d = *reinterpret_cast<const float4*>(sDZ + s * R + jx);
-        const float4 wa = *reinterpret_cast<const float4*>(sW1 + kk * SmallSmem::kW1Row + jx);
-        const float4 wb = *reinterpret_cast<const float4*>(sW1 + (kk + 1) * SmallSmem::kW1Row + jx);
-        const float4 wc = *reinterpret_cast<const float4*>(sW1 + (kk + 2) * SmallSmem::kW1Row + jx);
-        x0 = fmaf(d.x, wa.x, x0); x0 = fmaf(d.y, wa.y, x0); x0 = fmaf(d.z, wa.z, x0); x0 = fmaf(d.w, wa.w, x0);
-        x1 = fmaf(d.x, wb.x, x1); x1 = fmaf(d.y, wb.y, x1); x1 = fmaf(d.z, wb.z, x1); x1 = fmaf(d.w, wb.w, x1);
-        x2 = fmaf(d.x, wc.x, x2); x2 = fmaf(d.y, wc.y, x2); x2 = fmaf(d.z, wc.z, x2); x2 = fmaf(d.w, wc.w, x2);
-      }
-      if (s < n_here) {
-        float* o = g_feat + (base + s) * kF + kk;
-        o[0] = x0; o[1] = x1; o[2] = x2;
-      }
-    }
-    } else {
     // dW1k, dX
     {
       const int j = tid & 127, k0 = 6 * (tid >> 7);
@@ -617,7 +570,6 @@ __global__ void __launch_bounds__(kThreads, 2) k_shade_bwd_small(
         o[0] = x0; o[1] = x1; o[2] = x2;
       }
     }
-    }
     __syncthreads();
   }
   if (run_ray >= 0) {
@@ -633,9 +585,9 @@ __global__ void __launch_bounds__(kThreads, 2) k_shade_bwd_small(
     atomicAdd(gW3 + 2 * kW + j, aW3[2][jj]);
   }
   {
-    const int j = tid & 127;
+    const int j = tid & 127, k0 = 6 * (tid >> 7);
 #pragma unroll
-    for (int q = 0; q < (kVec ? kF : 6); ++q) atomicAdd(gW1k + j * kF + (kVec ? 0 : 6 * (tid >> 7)) + q, aW1[q]);
+    for (int q = 0; q < 6; ++q) atomicAdd(gW1k + j * kF + k0 + q, aW1[q]);
   }
   if (tid < kBwdTile) {
     atomicAdd(gb3, aB3[0]); atomicAdd(gb3 + 1, aB3[1]); atomicAdd(gb3 + 2, aB3[2]);
@@ -696,12 +648,11 @@ extern "C" int ubn_rgbnet_bwd_small(const float* feat, const int64_t* ray_id, co
                                     float* grad_W3, float* grad_b3, void* stream) {
   if (n_pts <= 0) return 0;
   const size_t smem = sizeof(float) * SmallSmem::kFloats;
-  static const bool vec = [] { const char* v = getenv("UBN_SMALL_IMPL"); return !(v && v[0] == '0'); }();
-  auto kern = vec ? k_shade_bwd_small<true> : k_shade_bwd_small<false>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(k_shade_bwd_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return finish(e);
-  kern<<<2 * kNumSMs, kThreads, smem, as_stream(stream)>>>(feat, ray_id, W1k, W3, rgb, h2_save, grad_rgb, dz1, n_pts, grad_feat,
-                                                           grad_view_bias, grad_W1k, grad_b2, grad_W3, grad_b3);
+  k_shade_bwd_small<<<2 * kNumSMs, kThreads, smem, as_stream(stream)>>>(feat, ray_id, W1k, W3, rgb, h2_save, grad_rgb, dz1, n_pts,
+                                                                        grad_feat, grad_view_bias, grad_W1k, grad_b2, grad_W3,
+                                                                        grad_b3);
   UBN_LAUNCH_CHECK();
   return 0;
 }
