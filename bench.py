@@ -472,7 +472,7 @@ def main():
                         'mode': os.environ.get('UBN_BENCH_TAIL', 'pipelined')},
             'fwd_only': {'value': samples_per_step / (ms_fwd / args.steps * 1e-3), 'unit': 'ray-samples/s',
                          'ms_per_step': ms_fwd / args.steps}}
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:              # rank 0 at N = 1 only
         try:
             v, sec = cpu_reference_step(flavor, kwargs, stepsize, args.cpu_rays, cores, 1, 1)
             line['cpu_baseline'] = {'value': v, 'unit': 'ray-samples/s', 'cores': cores, 'kind': 'port',
@@ -480,6 +480,17 @@ def main():
                                               f'{sec:.1f} s/step'}
         except Exception as e:                                           # never lose the GPU numbers to a CPU-side problem
             line['cpu_baseline'] = {'value': None, 'unit': 'ray-samples/s', 'cores': cores, 'kind': 'port', 'sample': f'failed: {e}'}
+        try:
+            # second half of BASELINE.json's metric: PSNR delta vs ref on the procedural teacher / student scene, the oracle as
+            # the checker (oracle/psnr_check.py; same protocol as tests/test_gpu_models.py::test_psnr_delta_vs_oracle)
+            from oracle.psnr_check import psnr_delta
+            torch.set_num_threads(cores)
+            pd = psnr_delta(flavor, 3 if flavor == 'fouriergrid' else 0, dev)
+            line['psnr_delta_vs_ref'] = {'delta_db': pd['delta_db'], 'psnr_ref_db': pd['psnr_oracle'], 'psnr_ours_db': pd['psnr_cuda'],
+                                         'ours_vs_ref_image_db': pd['psnr_cuda_vs_oracle'],
+                                         'scene': 'procedural teacher / noisy student, 2 views 24x24, 32^3 grids (no datasets offline)'}
+        except Exception as e:
+            line['psnr_delta_vs_ref'] = {'delta_db': None, 'failed': str(e)}
     emit(line)
     if world > 1:
         torch.distributed.destroy_process_group()

@@ -309,71 +309,15 @@ def test_reduce_tv_step_single_process_matches_tv_then_step():
         assert torch.equal(outs[0][k], outs[1][k]), k
 
 
-def _pinhole_rays(H, W, cam_pos, look_at=(0., 0., 0.), focal=None):
-    """A small pinhole view (rays_o, rays_d, viewdirs) -- test-side ray generation, dvgo.get_rays_of_a_view conventions."""
-    focal = focal or float(W)
-    cam_pos = torch.tensor(cam_pos)
-    fwd = torch.tensor(look_at) - cam_pos
-    fwd = fwd / fwd.norm()
-    right = torch.linalg.cross(fwd, torch.tensor([0., 0., 1.]))
-    right = right / right.norm()
-    up = torch.linalg.cross(right, fwd)
-    j, i = torch.meshgrid(torch.arange(H, dtype=torch.float32) + 0.5, torch.arange(W, dtype=torch.float32) + 0.5, indexing='ij')
-    d = ((i - W / 2) / focal)[..., None] * right + (-(j - H / 2) / focal)[..., None] * up + fwd
-    rd = d.reshape(-1, 3).contiguous()
-    ro = cam_pos.expand_as(rd).contiguous()
-    return ro, rd, (rd / rd.norm(dim=-1, keepdim=True)).contiguous()
-
-
-def _psnr(a, b):
-    return -10.0 * torch.log10(((a.double() - b.double()) ** 2).mean()).item()
-
-
 @pytest.mark.parametrize('flavor,F_', [('fouriergrid', 3), ('dcvgo', 0)])
-def test_psnr_delta_vs_oracle(oracle, flavor, F_):
-    """BASELINE.json metric, second half: "PSNR delta vs ref" (SURVEY.md 8d protocol, no datasets offline).
-    Teacher = seeded smooth scene rendered by the ORACLE to 2 views = ground truth.  Student = teacher + seeded noise,
-    rendered once by the oracle (the reference's arithmetic) and once by the fused CUDA path on identical rays / weights.
-    Gate: |PSNR(cuda, GT) - PSNR(oracle, GT)| <= 0.01 dB, and the two student images agree to > 90 dB."""
-    world, H, W = 32, 24, 24
-    m, kw = _fresh_model(flavor, world, F_, 1e-4, 4242, dens_mean=0.0, dens_std=1.0)
-    g = torch.Generator().manual_seed(99)
-    with torch.no_grad():
-        # smooth procedural scene: a dense ball in the middle, colours varying slowly -- low-pass filtered noise
-        def smooth(shape, amp):
-            low = torch.randn(shape[0], shape[1], 6, 6, 6, generator=g)
-            return torch.nn.functional.interpolate(low, size=shape[2:], mode='trilinear', align_corners=True) * amp
-        X = m.density.grid.shape[2]
-        ax = torch.linspace(-1.2, 1.2, X)
-        rr = (ax[:, None, None] ** 2 + ax[None, :, None] ** 2 + ax[None, None, :] ** 2).sqrt()
-        ball = ((0.55 - rr) * 40.0).clamp(-4.0, 8.0)                     # > 0 inside radius 0.55
-        # (FourierGrid averages 1+2F warped look-ups, so the scene is a lumpy fog around act_shift = -9.2 rather than a solid)
-        m.density.grid.copy_(smooth(m.density.grid.shape, 3.0) + ball[None, None] + 7.0)
-        m.k0.grid.copy_(smooth(m.k0.grid.shape, 1.5))
-        if flavor == 'dcvgo':
-            m.mask_cache.mask.fill_(True)
-    views = [_pinhole_rays(H, W, (2.2, 0.3, 0.4)), _pinhole_rays(H, W, (-0.5, -2.0, 1.0))]
-
-    def render_oracle(state):
-        p = oracle.params_from_state(flavor, kw, state)
-        with torch.no_grad():
-            return torch.cat([oracle.model_forward(flavor, p, *v, 0.5, bg=1, render_depth=False)['rgb_marched'] for v in views])
-
-    teacher = {k: v.detach().clone().contiguous() for k, v in m.state_dict().items()}
-    gt = render_oracle(teacher)
-    assert gt.std() > 0.02, 'degenerate teacher image'
-    with torch.no_grad():                                                 # student = teacher + noise
-        m.density.grid.add_(torch.randn(m.density.grid.shape, generator=g) * 0.5)
-        m.k0.grid.add_(torch.randn(m.k0.grid.shape, generator=g) * 0.3)
-    student = {k: v.detach().clone().contiguous() for k, v in m.state_dict().items()}
-    img_ref = render_oracle(student)
-    m = m.to(DEV)
-    with torch.no_grad():
-        img_new = torch.cat([m(*(t.to(DEV) for t in v), global_step=None, is_train=False, near=0., far=1e9, bg=1, rand_bkgd=False,
-                               stepsize=0.5, render_depth=False)['rgb_marched'].cpu() for v in views])
-    psnr_ref, psnr_new = _psnr(img_ref, gt), _psnr(img_new, gt)
-    print(f'[psnr] {flavor}: PSNR(oracle, GT) = {psnr_ref:.4f} dB, PSNR(cuda, GT) = {psnr_new:.4f} dB, '
-          f'delta = {psnr_new - psnr_ref:+.2e} dB, PSNR(cuda vs oracle) = {_psnr(img_new, img_ref):.1f} dB')
-    assert 5.0 < psnr_ref < 60.0, 'student should differ visibly from the teacher'
-    assert abs(psnr_new - psnr_ref) <= 0.01
-    assert _psnr(img_new, img_ref) > 90.0
+def test_psnr_delta_vs_oracle(flavor, F_):
+    """BASELINE.json metric, second half: "PSNR delta vs ref" (SURVEY.md 8d protocol, no datasets offline; see
+    oracle/psnr_check.py).  Gate: |PSNR(cuda, GT) - PSNR(oracle, GT)| <= 0.01 dB, student images agree to > 90 dB."""
+    from oracle.psnr_check import psnr_delta
+    r = psnr_delta(flavor, F_, DEV)
+    print(f"[psnr] {flavor}: PSNR(oracle, GT) = {r['psnr_oracle']:.4f} dB, PSNR(cuda, GT) = {r['psnr_cuda']:.4f} dB, "
+          f"delta = {r['delta_db']:+.2e} dB, PSNR(cuda vs oracle) = {r['psnr_cuda_vs_oracle']:.1f} dB")
+    assert r['gt_std'] > 0.02, 'degenerate teacher image'
+    assert 5.0 < r['psnr_oracle'] < 60.0, 'student should differ visibly from the teacher'
+    assert abs(r['delta_db']) <= 0.01
+    assert r['psnr_cuda_vs_oracle'] > 90.0
