@@ -141,6 +141,22 @@ int ubn_tv_adam_fused(float* param, float* grad, float* exp_avg, float* exp_avg_
 int ubn_cumdist_thres(const float* dist, float thres, int64_t n_rays, int64_t n_pts, uint8_t* mask,
                       void* stream);
 
+/* ---- rays and batches: the step either side of the march ---------------------
+ * dvgo.get_rays_of_a_view                      FourierGrid/dvgo.py:492-555 (get_rays + ndc_rays + viewdirs)
+ * One launch writes rays_o, rays_d, viewdirs [H*W,3] of one view.  K_host: 3x3 row-major intrinsics, c2w_host: camera-
+ * to-world rows of length c2w_row_stride (4 for a 3x4 / 4x4 pose) -- both HOST pointers (21 scalars).  mode: 0 'lefttop',
+ * 1 'center', 2 'random' with `jitter` = device [2,H,W] uniform(0,1) offsets (plane 0 for i, plane 1 for j; the caller
+ * draws them, torch.rand_like in the reference).  ndc uses near = 1, focal = K[0][0] like dvgo.py:553-554. */
+int ubn_get_rays_of_a_view(int H, int W, const float* K_host, const float* c2w_host, int c2w_row_stride, int ndc,
+                           int inverse_y, int flip_x, int flip_y, int mode, const float* jitter, float* rays_o,
+                           float* rays_d, float* viewdirs, void* stream);
+
+/* Per-step batch assembly, run_train.py:204-212 (target / rays_o / rays_d / viewdirs = *_tr[sel_i]): gathers rows idx[k]
+ * of up to four [n_src,3] fp32 arrays in ONE launch.  src / dst: HOST arrays of n_arrays device pointers.  Negative
+ * indices wrap like Python; an out-of-range index sets *oob_flag (device int, caller-zeroed) instead of faulting. */
+int ubn_gather_rays(const float* const* src, float* const* dst, int n_arrays, const int64_t* idx, int64_t n_sel,
+                    int64_t n_src, int* oob_flag, void* stream);
+
 /* ---- trilinear voxel-grid reads: DenseGrid.forward (grid.py:50-61) and FourierGrid.forward
  *      (FourierGrid_grid.py:60-78) == torch F.grid_sample(bilinear, align_corners=True, zero padding)
  *      + its adjoint (grid_sampler_3d_backward wrt the grid) -------------------------------------

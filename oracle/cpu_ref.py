@@ -358,6 +358,48 @@ def rgbnet_forward(feat, w):
 
 
 # --------------------------------------------------------------------------------------
+# rays of a view (dvgo.py:492-557), torch CPU restatement
+# --------------------------------------------------------------------------------------
+def get_rays_of_a_view(H, W, K, c2w, ndc, inverse_y, flip_x, flip_y, mode='center', jitter=None):
+    """dvgo.get_rays (dvgo.py:492-520) + viewdirs + ndc_rays(near=1, focal=K[0][0]) (dvgo.py:532-557).
+    mode 'random' takes the uniform offsets as ``jitter`` [2,H,W] (plane 0 added to i, plane 1 to j) so it is testable."""
+    K = torch.as_tensor(K, dtype=torch.float64)
+    c2w = torch.as_tensor(c2w, dtype=torch.float32)
+    i, j = torch.meshgrid(torch.linspace(0, W - 1, W), torch.linspace(0, H - 1, H), indexing='ij')
+    i, j = i.t().float(), j.t().float()
+    if mode == 'center':
+        i, j = i + 0.5, j + 0.5
+    elif mode == 'random':
+        i, j = i + jitter[0], j + jitter[1]
+    elif mode != 'lefttop':
+        raise NotImplementedError
+    if flip_x:
+        i = i.flip((1,))
+    if flip_y:
+        j = j.flip((0,))
+    fx, fy, cx, cy = float(K[0][0]), float(K[1][1]), float(K[0][2]), float(K[1][2])
+    if inverse_y:
+        dirs = torch.stack([(i - cx) / fx, (j - cy) / fy, torch.ones_like(i)], -1)
+    else:
+        dirs = torch.stack([(i - cx) / fx, -(j - cy) / fy, -torch.ones_like(i)], -1)
+    rays_d = torch.sum(dirs[..., None, :] * c2w[:3, :3], -1)
+    rays_o = c2w[:3, 3].expand(rays_d.shape)
+    viewdirs = rays_d / rays_d.norm(dim=-1, keepdim=True)
+    if ndc:
+        near, focal = 1., fx
+        t = -(near + rays_o[..., 2]) / rays_d[..., 2]
+        rays_o = rays_o + t[..., None] * rays_d
+        o0 = -1. / (W / (2. * focal)) * rays_o[..., 0] / rays_o[..., 2]
+        o1 = -1. / (H / (2. * focal)) * rays_o[..., 1] / rays_o[..., 2]
+        o2 = 1. + 2. * near / rays_o[..., 2]
+        d0 = -1. / (W / (2. * focal)) * (rays_d[..., 0] / rays_d[..., 2] - rays_o[..., 0] / rays_o[..., 2])
+        d1 = -1. / (H / (2. * focal)) * (rays_d[..., 1] / rays_d[..., 2] - rays_o[..., 1] / rays_o[..., 2])
+        d2 = -2. * near / rays_o[..., 2]
+        rays_o, rays_d = torch.stack([o0, o1, o2], -1), torch.stack([d0, d1, d2], -1)
+    return rays_o.contiguous(), rays_d.contiguous(), viewdirs.contiguous()
+
+
+# --------------------------------------------------------------------------------------
 # autograd wrappers over the C oracle (dvgo.py:430-488 semantics) and full model forwards
 # --------------------------------------------------------------------------------------
 def _autograd_fns(ext):

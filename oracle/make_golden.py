@@ -227,9 +227,40 @@ def golden_models():
     _save('l2_models.pt', out)
 
 
+def golden_rays():
+    """dvgo.get_rays_of_a_view / get_training_rays_flatten (dvgo.py:492-612) on small views, every flag combination."""
+    g = torch.Generator().manual_seed(SEED + 5)
+    rec = {'views': []}
+    H, W = 5, 7
+    K = np.array([[9.5, 0., 3.4], [0., 9.1, 2.6], [0., 0., 1.]])
+    ang = 0.7
+    R = torch.tensor([[np.cos(ang), -np.sin(ang), 0.], [np.sin(ang), np.cos(ang), 0.], [0., 0., 1.]], dtype=torch.float32)
+    R = R @ torch.tensor([[1., 0., 0.], [0., 0.8, -0.6], [0., 0.6, 0.8]])
+    c2w = torch.cat([R, torch.tensor([[0.3], [-0.2], [1.7]])], 1)
+    for ndc in (False, True):
+        for inverse_y in (False, True):
+            for flip_x, flip_y in ((False, False), (True, False), (False, True), (True, True)):
+                for mode in ('center', 'lefttop'):
+                    o, d, v = ref_dvgo.get_rays_of_a_view(H, W, K, c2w, ndc, inverse_y, flip_x, flip_y, mode=mode)
+                    rec['views'].append(dict(H=H, W=W, K=torch.tensor(K), c2w=c2w.clone(), ndc=ndc, inverse_y=inverse_y,
+                                             flip_x=flip_x, flip_y=flip_y, mode=mode, rays_o=_c(o), rays_d=_c(d), viewdirs=_c(v)))
+    # flattened training set of two views of different size
+    imgs = [torch.rand(4, 6, 3, generator=g), torch.rand(5, 3, 3, generator=g)]
+    poses = [c2w, torch.cat([R.t().contiguous(), torch.tensor([[-1.0], [0.4], [0.9]])], 1)]
+    HW = np.array([[4, 6], [5, 3]])
+    Ks = np.stack([K, K * np.array([[0.5], [0.5], [1.0]])])
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        out = ref_dvgo.get_training_rays_flatten(imgs, poses, HW, Ks, ndc=False, inverse_y=False, flip_x=False, flip_y=False)
+    rec['flatten'] = dict(imgs=imgs, poses=poses, HW=torch.tensor(HW), Ks=torch.tensor(Ks), rgb_tr=_c(out[0]), rays_o_tr=_c(out[1]),
+                          rays_d_tr=_c(out[2]), viewdirs_tr=_c(out[3]), imsz=list(out[4]))
+    _save('l1_rays.pt', rec)
+
+
 if __name__ == '__main__':
     torch.set_num_threads(4)
     golden_grids()
     golden_autograd_fns()
     golden_masked_adam()
     golden_models()
+    golden_rays()

@@ -379,3 +379,49 @@ def test_host_scalar_cache_is_per_tensor_object():
         t.add_(0.5)                                  # in-place update bumps the version
         assert host_scalar(t) == float(k) + 0.5
         del t
+
+
+def test_rays_of_a_view_golden():
+    """ubn_get_rays_of_a_view (one launch per view) vs the reference's dvgo.get_rays_of_a_view on every flag combination,
+    and get_training_rays_flatten vs dvgo.get_training_rays_flatten (dvgo.py:492-612)."""
+    from unboundednerfpytorch_b200 import rays as R
+    rec = load_golden('l1_rays.pt')
+    for v in rec['views']:
+        o, d, vd = R.get_rays_of_a_view(v['H'], v['W'], v['K'].numpy(), v['c2w'], v['ndc'], v['inverse_y'], v['flip_x'],
+                                        v['flip_y'], mode=v['mode'])
+        tag = f"ndc={v['ndc']} inv={v['inverse_y']} fx={v['flip_x']} fy={v['flip_y']} {v['mode']}"
+        assert o.is_cuda and o.shape == (v['H'], v['W'], 3)
+        assert_close(o, v['rays_o'], rtol=2e-6, what='rays_o ' + tag)
+        assert_close(d, v['rays_d'], rtol=2e-6, what='rays_d ' + tag)
+        assert_close(vd, v['viewdirs'], rtol=2e-6, what='viewdirs ' + tag)
+    o2, d2 = R.get_rays(5, 7, rec['views'][0]['K'].numpy(), rec['views'][0]['c2w'].to(DEV), False, False, False)
+    assert_close(o2, rec['views'][0]['rays_o']); assert_close(d2, rec['views'][0]['rays_d'])
+    f = rec['flatten']
+    out = R.get_training_rays_flatten([im.to(DEV) for im in f['imgs']], f['poses'], f['HW'].numpy(), f['Ks'].numpy(),
+                                      ndc=False, inverse_y=False, flip_x=False, flip_y=False)
+    for a, k in zip(out[:4], ('rgb_tr', 'rays_o_tr', 'rays_d_tr', 'viewdirs_tr')):
+        assert_close(a, f[k], rtol=2e-6, what=k)
+    assert list(out[4]) == list(f['imsz'])
+    # mode 'random': offsets in [0,1) of the pixel, statistically centred
+    o3, d3, _ = R.get_rays_of_a_view(64, 64, rec['views'][0]['K'].numpy(), rec['views'][0]['c2w'], False, False, False, False,
+                                     mode='random')
+    _, dl, _ = R.get_rays_of_a_view(64, 64, rec['views'][0]['K'].numpy(), rec['views'][0]['c2w'], False, False, False, False,
+                                    mode='lefttop')
+    _, dc, _ = R.get_rays_of_a_view(64, 64, rec['views'][0]['K'].numpy(), rec['views'][0]['c2w'], False, False, False, False,
+                                    mode='center')
+    assert ((d3 - dl).abs().max() <= (1 / 9.1) * 1.8) and ((d3 - dc).mean().abs() < 5e-3)
+
+
+def test_gather_ray_batch():
+    """One-launch batch assembly == four index ops (run_train.py:204-212); negative indices wrap, bad ones raise."""
+    from unboundednerfpytorch_b200 import rays as R
+    g = torch.Generator().manual_seed(3)
+    arrs = [torch.randn(1000, 3, generator=g).to(DEV) for _ in range(4)]
+    sel = torch.randint(0, 1000, (4096,), generator=g)
+    sel[:3] = torch.tensor([-1, -1000, 999])
+    outs = R.gather_ray_batch(sel, *arrs)
+    for o, a in zip(outs, arrs):
+        assert_equal(o, a[sel.to(DEV)], 'gather')
+    assert R.gather_ray_batch(sel[:0], arrs[0])[0].shape == (0, 3)
+    with pytest.raises(IndexError):
+        R.gather_ray_batch(torch.tensor([5, 1000]), arrs[0], arrs[1])

@@ -133,3 +133,17 @@ def test_sampling_oracle_matches_reference_dvgo(oracle):
     # each ray gets ceil(segment * |d| / stepdist) >= 1 samples and the sample positions advance by stepdist
     n_steps = out[4]
     assert (n_steps >= 1).all() and int(n_steps.sum()) == out[0].shape[0]
+
+
+def test_rays_oracle_matches_reference():
+    """oracle.get_rays_of_a_view == the reference's dvgo.get_rays_of_a_view (dvgo.py:492-557) on every flag combination."""
+    from oracle import cpu_ref
+    rec = load_golden('l1_rays.pt')
+    assert len(rec['views']) == 32
+    for v in rec['views']:
+        o, d, vd = cpu_ref.get_rays_of_a_view(v['H'], v['W'], v['K'], v['c2w'], v['ndc'], v['inverse_y'], v['flip_x'],
+                                              v['flip_y'], mode=v['mode'])
+        tag = f"ndc={v['ndc']} inv={v['inverse_y']} fx={v['flip_x']} fy={v['flip_y']} {v['mode']}"
+        assert_close(o, v['rays_o'], rtol=1e-6, what='rays_o ' + tag)
+        assert_close(d, v['rays_d'], rtol=1e-6, what='rays_d ' + tag)
+        assert_close(vd, v['viewdirs'], rtol=1e-6, what='viewdirs ' + tag)
