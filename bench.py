@@ -319,6 +319,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     from unboundednerfpytorch_b200 import _cabi, models
+    from unboundednerfpytorch_b200.functional import render_loss
     from unboundednerfpytorch_b200.masked_adam import create_optimizer_or_freeze_model
     _cabi.load()
     torch.manual_seed(SEED)
@@ -343,7 +344,10 @@ def main():
     def train_step(ro, rd, vd, target, it):
         ret = model(ro, rd, vd, global_step=it, is_train=True, **rk)
         opt.zero_grad(set_to_none=True)
-        loss = step_loss(ret, target, N_RAYS)
+        if os.environ.get('UBN_BENCH_LOSS', 'fused') == 'torch':     # A/B switch: the reference's torch composition
+            loss = step_loss(ret, target, N_RAYS)
+        else:                                                        # same three terms, value + gradients in two launches
+            loss, _ = render_loss(ret, target, 1.0, 1e-3, 1e-2)
         loss.backward()
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
         ev[0].record()

@@ -157,6 +157,18 @@ int ubn_get_rays_of_a_view(int H, int W, const float* K_host, const float* c2w_h
 int ubn_gather_rays(const float* const* src, float* const* dst, int n_arrays, const int64_t* idx, int64_t n_sel,
                     int64_t n_src, int* oob_flag, void* stream);
 
+/* ---- in-kernel training losses ------------------------------------------------
+ * FourierGrid/run_train.py:254-279: loss = w_main * F.mse_loss(rgb_marched, target)
+ *   + w_entropy * entropy_last(alphainv_last.clamp(1e-6, 1-1e-6)) + w_rgbper * sum_m weights_m |raw_rgb_m - target[ray_id_m]|^2 / n_rays
+ * and d loss / d {rgb_marched [n_rays,3], alphainv_last [n_rays], raw_rgb [n_pts,3]} (weights detached, :277) in two
+ * launches.  out4 = {loss, mse, entropy_last, rgbper} (device).  alphainv_last / raw_rgb may be NULL (term off; their
+ * gradient buffers are then not written).  scratch: >= 1776 doubles of device memory (per-block partials, summed in a
+ * fixed order: the loss value is deterministic). */
+int ubn_render_loss(const float* rgb_marched, const float* alphainv_last, const float* raw_rgb, const float* weights,
+                    const int64_t* ray_id, const float* target, int64_t n_rays, int64_t n_pts, float w_main,
+                    float w_entropy, float w_rgbper, float* out4, float* grad_rgb_marched, float* grad_alphainv_last,
+                    float* grad_raw_rgb, double* scratch, int64_t scratch_len, void* stream);
+
 /* ---- trilinear voxel-grid reads: DenseGrid.forward (grid.py:50-61) and FourierGrid.forward
  *      (FourierGrid_grid.py:60-78) == torch F.grid_sample(bilinear, align_corners=True, zero padding)
  *      + its adjoint (grid_sampler_3d_backward wrt the grid) -------------------------------------

@@ -425,3 +425,49 @@ def test_gather_ray_batch():
     assert R.gather_ray_batch(sel[:0], arrs[0])[0].shape == (0, 3)
     with pytest.raises(IndexError):
         R.gather_ray_batch(torch.tensor([5, 1000]), arrs[0], arrs[1])
+
+
+@pytest.mark.parametrize('n_rays,n_pts', [(1, 1), (37, 500), (8192, 300000), (64, 0)])
+def test_render_loss_vs_torch(n_rays, n_pts):
+    """ubn_render_loss (value + gradients in two launches) vs the reference's torch composition, run_train.py:254-279."""
+    from unboundednerfpytorch_b200.functional import render_loss
+    g = torch.Generator().manual_seed(n_rays + n_pts)
+    rgbm = torch.rand(n_rays, 3, generator=g)
+    last = torch.rand(n_rays, generator=g)
+    last[::5] = 0.0                     # below the clamp: no gradient
+    if n_rays > 3:
+        last[1], last[2] = 1.0, 2e-6    # above the clamp (no gradient) / just inside it
+    raw = torch.rand(n_pts, 3, generator=g)
+    w = torch.rand(n_pts, generator=g)
+    rid = torch.sort(torch.randint(0, n_rays, (n_pts,), generator=g)).values
+    tgt = torch.rand(n_rays, 3, generator=g)
+
+    def torch_loss(rgbm, last, raw, w, rid, tgt):
+        loss = 1.0 * torch.nn.functional.mse_loss(rgbm, tgt)
+        pout = last.clamp(1e-6, 1 - 1e-6)
+        ent = -(pout * torch.log(pout) + (1 - pout) * torch.log(1 - pout)).mean()
+        per = ((raw - tgt[rid]).pow(2).sum(-1) * w.detach()).sum() / len(rgbm)
+        return loss + 1e-3 * ent + 1e-2 * per, (loss, ent, per)
+
+    a = [t.clone().double().requires_grad_(t.dtype.is_floating_point and i < 3) for i, t in enumerate((rgbm, last, raw))]
+    ref, terms = torch_loss(a[0], a[1], a[2], w.double(), rid, tgt.double())          # fp64 torch as the yardstick
+    ref.backward()
+    b = [t.clone().to(DEV).requires_grad_(True) for t in (rgbm, last, raw)]
+    ret = dict(rgb_marched=b[0], alphainv_last=b[1], raw_rgb=b[2], weights=w.to(DEV), ray_id=rid.to(DEV))
+    loss, t3 = render_loss(ret, tgt.to(DEV), 1.0, 1e-3, 1e-2)
+    loss.backward()
+    assert_close(loss.detach().cpu().double(), ref.detach(), rtol=2e-6, what='loss')
+    for k, v in zip(('mse', 'entropy_last', 'rgbper'), terms):
+        assert_close(t3[k].cpu().double(), v.detach(), rtol=2e-6, what=k)
+    for mine, theirs, nm in zip(b, a, ('rgb_marched', 'alphainv_last', 'raw_rgb')):
+        if n_pts == 0 and nm == 'raw_rgb':
+            assert mine.grad is None or mine.grad.numel() == 0
+            continue
+        assert_close(mine.grad.cpu().double(), theirs.grad, rtol=2e-5, atol=1e-10, what='grad ' + nm)
+    # terms switched off: no gradient to alphainv_last / raw_rgb, value = mse
+    b2 = [t.clone().to(DEV).requires_grad_(True) for t in (rgbm, last, raw)]
+    l2, _ = render_loss(dict(rgb_marched=b2[0], alphainv_last=b2[1], raw_rgb=b2[2], weights=w.to(DEV), ray_id=rid.to(DEV)),
+                        tgt.to(DEV), 1.0, 0.0, 0.0)
+    l2.backward()
+    assert_close(l2.detach().cpu().double(), terms[0].detach(), rtol=2e-6, what='mse only')
+    assert b2[1].grad is None and b2[2].grad is None

@@ -127,3 +127,64 @@ def segment_coo(src, index, out, reduce='sum'):
     if reduce != 'sum':
         raise NotImplementedError(reduce)
     return out + segment_sum(src, index, out.shape[0]).reshape(out.shape)
+
+
+# --------------------------------------------------------------------------------------------------
+# in-kernel training losses (run_train.py:254-279): MSE + entropy_last + per-point rgb loss
+# --------------------------------------------------------------------------------------------------
+_loss_scratch = {}
+
+
+class RenderLoss(torch.autograd.Function):
+    """loss = w_main * mse(rgb_marched, target) + w_entropy * entropy_last(alphainv_last) + w_rgbper * rgbper, value and
+    gradients from two launches (ubn_render_loss).  Returns a [4] tensor {loss, mse, entropy_last, rgbper}; only element 0
+    carries gradient (the other three are the detached terms the training loop logs, e.g. psnr = mse2psnr(out[1]))."""
+
+    @staticmethod
+    def forward(ctx, rgb_marched, alphainv_last, raw_rgb, weights, ray_id, target, w_main, w_entropy, w_rgbper):
+        from ._cabi import c_f, c_i64, check, ptr, stream_of
+        dev = rgb_marched.device
+        for t, nm in ((rgb_marched, 'rgb_marched'), (target, 'target')):
+            if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+                raise RuntimeError(f'{nm} must be a contiguous CUDA fp32 tensor')
+        n_rays = rgb_marched.shape[0]
+        use_ent = alphainv_last is not None and w_entropy != 0
+        use_per = raw_rgb is not None and w_rgbper != 0 and raw_rgb.shape[0] > 0
+        if use_ent:
+            alphainv_last = alphainv_last.contiguous()
+        if use_per:
+            raw_rgb, weights, ray_id = raw_rgb.contiguous(), weights.detach().contiguous(), ray_id.contiguous()
+        n_pts = raw_rgb.shape[0] if use_per else 0
+        scratch = _loss_scratch.get(dev)
+        if scratch is None:
+            scratch = _loss_scratch[dev] = torch.empty(3 * 1024, dtype=torch.float64, device=dev)
+        out = torch.empty(4, device=dev)
+        g_rgb = torch.empty_like(rgb_marched)
+        g_last = torch.empty_like(alphainv_last) if use_ent else None
+        g_raw = torch.empty_like(raw_rgb) if use_per else None
+        with ops._Guard(rgb_marched) as lib:
+            check(lib.ubn_render_loss(ptr(rgb_marched), ptr(alphainv_last if use_ent else None), ptr(raw_rgb if use_per else None),
+                                      ptr(weights if use_per else None), ptr(ray_id if use_per else None), ptr(target),
+                                      c_i64(n_rays), c_i64(n_pts), c_f(float(w_main)), c_f(float(w_entropy)),
+                                      c_f(float(w_rgbper)), ptr(out), ptr(g_rgb), ptr(g_last), ptr(g_raw), ptr(scratch),
+                                      c_i64(scratch.numel()), stream_of(rgb_marched)))
+        ctx.save_for_backward(g_rgb, g_last, g_raw)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        g_rgb, g_last, g_raw = ctx.saved_tensors
+        s = grad_out[0]
+        return (g_rgb * s, None if g_last is None else g_last * s, None if g_raw is None else g_raw * s,
+                None, None, None, None, None, None)
+
+
+def render_loss(render_result, target, weight_main=1.0, weight_entropy_last=0.0, weight_rgbper=0.0):
+    """The always-on loss terms of the reference training loop (run_train.py:254-279) from a model ``ret_dict``.
+    Returns (loss, {'mse', 'entropy_last', 'rgbper'}) -- loss is differentiable, the terms are detached scalars."""
+    out = RenderLoss.apply(render_result['rgb_marched'], render_result.get('alphainv_last'), render_result.get('raw_rgb'),
+                           render_result.get('weights'), render_result.get('ray_id'), target.contiguous(),
+                           weight_main, weight_entropy_last, weight_rgbper)
+    d = out.detach()
+    return out[0], {'mse': d[1], 'entropy_last': d[2], 'rgbper': d[3]}
