@@ -113,6 +113,15 @@ int ubn_alpha2weight_backward(const float* alpha, const float* weight, const flo
 int ubn_segment_sum(const float* src, int64_t k, const int64_t* ray_id, int64_t n_pts, int64_t n_rays,
                     int64_t* i_start, int64_t* i_end, float* out, void* stream);
 
+/* The colour composite itself, rgb_marched = segment_coo(weights[:,None] * rgb, ray_id, zeros[n_rays,3], 'sum')
+ * (FourierGrid_model.py:640-644, dcvgo.py:345-349, dvgo.py:401-405), without materialising the [n_pts,3] product, and its
+ * adjoint in one pass: grad_rgb_i = w_i * g[ray_i], grad_weights_i = sum_c g[ray_i,c] * rgb_i[c] (either may be NULL).
+ * Same rounding as the two-op form (product rounded before the sum). */
+int ubn_composite_fwd(const float* weights, const float* rgb, const int64_t* ray_id, int64_t n_pts, int64_t n_rays,
+                      int64_t* i_start, int64_t* i_end, float* out, void* stream);
+int ubn_composite_bwd(const float* weights, const float* rgb, const int64_t* ray_id, const float* grad_out, int64_t n_pts,
+                      float* grad_weights, float* grad_rgb, void* stream);
+
 /* ---- total_variation_cuda (FourierGrid/cuda/total_variation.cpp:22-24) ----------------------- */
 /* total_variation_cuda.total_variation_add_grad   total_variation.cpp:13-20 / total_variation_kernel.cu:14-67.
  * param/grad: logical [lead, sz_i, sz_j, sz_k, inner] row-major in MEMORY.  Reference layout

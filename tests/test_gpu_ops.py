@@ -471,3 +471,30 @@ def test_render_loss_vs_torch(n_rays, n_pts):
     l2.backward()
     assert_close(l2.detach().cpu().double(), terms[0].detach(), rtol=2e-6, what='mse only')
     assert b2[1].grad is None and b2[2].grad is None
+
+
+@pytest.mark.parametrize('n_rays,n_pts', [(1, 1), (50, 777), (8192, 200000), (9, 0)])
+def test_composite_rgb_vs_torch(n_rays, n_pts):
+    """ubn_composite_fwd/bwd == segment_coo(weights[:,None] * rgb, ray_id, zeros, 'sum') and its autograd (bit-exact forward
+    against the two-op form through the same kernel family; gradients against torch index_add autograd)."""
+    from unboundednerfpytorch_b200.functional import composite_rgb, segment_sum
+    g = torch.Generator().manual_seed(n_rays * 7 + n_pts)
+    w = torch.rand(n_pts, generator=g)
+    rgb = torch.rand(n_pts, 3, generator=g)
+    rid = torch.sort(torch.randint(0, n_rays, (n_pts,), generator=g)).values
+    if n_pts > 10:
+        rid[rid == 3] = 4                                   # an empty ray in the middle
+    gout = torch.randn(n_rays, 3, generator=g)
+    a = [t.clone().to(DEV).requires_grad_(True) for t in (w, rgb)]
+    out = composite_rgb(a[0], a[1], rid.to(DEV), n_rays)
+    out.backward(gout.to(DEV))
+    b = [t.clone().to(DEV).requires_grad_(True) for t in (w, rgb)]
+    two_op = segment_sum(b[0].unsqueeze(-1) * b[1], rid.to(DEV), n_rays)
+    assert_equal(out, two_op, 'fused composite vs mul + segment_sum')
+    c = [t.clone().double().requires_grad_(True) for t in (w, rgb)]
+    ref = torch.zeros(n_rays, 3, dtype=torch.float64).index_add_(0, rid, c[0].unsqueeze(-1) * c[1])
+    ref.backward(gout.double())
+    assert_close(out.detach().cpu().double(), ref.detach(), rtol=1e-5, what='composite')
+    if n_pts:
+        assert_close(a[0].grad.cpu().double(), c[0].grad, rtol=1e-5, atol=1e-6, what='grad weights')
+        assert_close(a[1].grad.cpu().double(), c[1].grad, rtol=1e-6, what='grad rgb')

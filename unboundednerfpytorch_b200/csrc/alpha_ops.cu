@@ -336,3 +336,76 @@ extern "C" int ubn_segment_sum(const float* src, int64_t k, const int64_t* ray_i
   UBN_LAUNCH_CHECK();
   return 0;
 }
+
+
+// ---- composite: rgb_marched[r] = sum_{i in r} weights_i * rgb_i  (FourierGrid_model.py:640-644, dcvgo.py:345-349,
+// dvgo.py:401-405) without materialising weights[:,None] * rgb, and its adjoint in one pass -------------------------------
+namespace ubn {
+
+__global__ void __launch_bounds__(128) k_composite_fwd(const float* __restrict__ weights, const float* __restrict__ rgb,
+                                                       const int64_t* __restrict__ i_start, const int64_t* __restrict__ i_end,
+                                                       int64_t n_rays, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t ray = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (ray >= n_rays) return;
+  const int64_t s = i_start[ray], e = i_end[ray];
+  float acc[3] = {0.f, 0.f, 0.f};
+  for (int64_t i = s + lane; i < e; i += 32) {
+    const float w = weights[i];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) acc[k] += __fmul_rn(w, rgb[i * 3 + k]);   // product rounded first, like the torch mul
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) out[ray * 3 + k] = acc[k];
+  }
+}
+
+// grad_rgb_i = w_i * g[ray_i];  grad_w_i = sum_c g[ray_i, c] * rgb_i[c]
+__global__ void __launch_bounds__(256) k_composite_bwd(const float* __restrict__ weights, const float* __restrict__ rgb,
+                                                       const int64_t* __restrict__ ray_id, const float* __restrict__ g,
+                                                       int64_t n_pts, float* __restrict__ grad_w, float* __restrict__ grad_rgb) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pts) return;
+  const int64_t r = ray_id[i];
+  const float g0 = g[3 * r], g1 = g[3 * r + 1], g2 = g[3 * r + 2];
+  if (grad_rgb) {
+    const float w = weights[i];
+    grad_rgb[3 * i] = __fmul_rn(g0, w); grad_rgb[3 * i + 1] = __fmul_rn(g1, w); grad_rgb[3 * i + 2] = __fmul_rn(g2, w);
+  }
+  if (grad_w)
+    grad_w[i] = __fadd_rn(__fadd_rn(__fmul_rn(g0, rgb[3 * i]), __fmul_rn(g1, rgb[3 * i + 1])), __fmul_rn(g2, rgb[3 * i + 2]));
+}
+
+}  // namespace ubn
+
+extern "C" int ubn_composite_fwd(const float* weights, const float* rgb, const int64_t* ray_id, int64_t n_pts, int64_t n_rays,
+                                 int64_t* i_start, int64_t* i_end, float* out, void* stream) {
+  using namespace ubn;
+  cudaStream_t st = as_stream(stream);
+  if (n_rays <= 0) return 0;
+  k_init_rays<<<blocks_for(n_rays, 256), 256, 0, st>>>(n_rays, out, i_start, i_end);
+  UBN_LAUNCH_CHECK();
+  if (n_pts > 0) {
+    k_segment_bounds<<<blocks_for(n_pts, 256), 256, 0, st>>>(ray_id, n_pts, i_start, i_end);
+    UBN_LAUNCH_CHECK();
+  }
+  k_composite_fwd<<<blocks_for(n_rays, 4), 128, 0, st>>>(weights, rgb, i_start, i_end, n_rays, out);
+  UBN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ubn_composite_bwd(const float* weights, const float* rgb, const int64_t* ray_id, const float* grad_out,
+                                 int64_t n_pts, float* grad_weights, float* grad_rgb, void* stream) {
+  using namespace ubn;
+  if (n_pts <= 0) return 0;
+  k_composite_bwd<<<blocks_for(n_pts, 256), 256, 0, as_stream(stream)>>>(weights, rgb, ray_id, grad_out, n_pts, grad_weights,
+                                                                         grad_rgb);
+  UBN_LAUNCH_CHECK();
+  return 0;
+}

@@ -121,6 +121,44 @@ def segment_sum(src, ray_id, n_rays):
     return SegmentSum.apply(src, ray_id, n_rays)
 
 
+class CompositeRGB(torch.autograd.Function):
+    """rgb_marched[r] = sum_{i: ray_id[i]==r} weights[i] * rgb[i]  ==  segment_sum(weights[:,None] * rgb, ray_id, n_rays)
+    (FourierGrid_model.py:640-644) with the product never materialised; backward writes both gradients in one launch."""
+
+    @staticmethod
+    def forward(ctx, weights, rgb, ray_id, n_rays):
+        from ._cabi import c_i64, check, ptr, stream_of
+        if not (weights.is_cuda and rgb.is_cuda):
+            raise RuntimeError('weights / rgb must be CUDA tensors')
+        weights, rgb, ray_id = weights.contiguous().float(), rgb.contiguous().float(), ray_id.contiguous()
+        assert rgb.dim() == 2 and rgb.shape[1] == 3 and weights.shape[0] == rgb.shape[0]
+        out = torch.empty(n_rays, 3, dtype=torch.float32, device=rgb.device)
+        i_s = torch.empty(n_rays, dtype=torch.int64, device=rgb.device)
+        i_e = torch.empty(n_rays, dtype=torch.int64, device=rgb.device)
+        with ops._Guard(rgb) as lib:
+            check(lib.ubn_composite_fwd(ptr(weights), ptr(rgb), ptr(ray_id), c_i64(rgb.shape[0]), c_i64(n_rays), ptr(i_s), ptr(i_e),
+                                        ptr(out), stream_of(rgb)))
+        ctx.save_for_backward(weights, rgb, ray_id)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        from ._cabi import c_i64, check, ptr, stream_of
+        weights, rgb, ray_id = ctx.saved_tensors
+        g = g.contiguous()
+        gw = torch.empty_like(weights) if ctx.needs_input_grad[0] else None
+        grgb = torch.empty_like(rgb) if ctx.needs_input_grad[1] else None
+        with ops._Guard(rgb) as lib:
+            check(lib.ubn_composite_bwd(ptr(weights), ptr(rgb), ptr(ray_id), ptr(g), c_i64(rgb.shape[0]), ptr(gw), ptr(grgb),
+                                        stream_of(rgb)))
+        return gw, grgb, None, None
+
+
+def composite_rgb(weights, rgb, ray_id, n_rays):
+    return CompositeRGB.apply(weights, rgb, ray_id, n_rays)
+
+
 def segment_coo(src, index, out, reduce='sum'):
     """torch_scatter.segment_coo(reduce='sum') for sorted ``index`` (call sites dvgo.py:401,418;
     dcvgo.py:345,354,377; FourierGrid_model.py:640,666): out += per-segment sums of the rows of ``src``."""

@@ -19,7 +19,7 @@ import torch.nn.functional as F
 from . import grid as G
 from . import march
 from . import shade as shade_mod
-from .functional import Alphas2Weights, Raw2Alpha, host_scalar, segment_sum
+from .functional import Alphas2Weights, Raw2Alpha, composite_rgb, host_scalar, segment_sum
 
 
 def _cube_root_size(xyz_min, xyz_max, num_voxels):
@@ -359,7 +359,7 @@ class FourierGridModel(_ContractedBase):
         (weights, alphainv_last, alpha, density, k0, ray_id, step_id, t, inner), t_table = self._march(
             rays_o, rays_d, render_kwargs['stepsize'])
         rgb = self._shade(k0, viewdirs, ray_id)
-        rgb_marched = segment_sum(weights.unsqueeze(-1) * rgb, ray_id, N)
+        rgb_marched = composite_rgb(weights, rgb, ray_id, N)
         if render_kwargs.get('rand_bkgd', False):
             rgb_marched = rgb_marched + alphainv_last.unsqueeze(-1) * torch.rand_like(rgb_marched)
         s = 1 - 1 / (1 + t)
@@ -401,7 +401,7 @@ class FourierGridModel(_ContractedBase):
             t, density, alpha = t.reshape(-1), density.reshape(-1), alpha.reshape(-1)
         k0 = self.k0(ray_pts)
         rgb = self._shade(k0, viewdirs, ray_id)
-        rgb_marched = segment_sum(weights.unsqueeze(-1) * rgb, ray_id, N)
+        rgb_marched = composite_rgb(weights, rgb, ray_id, N)
         if render_kwargs.get('rand_bkgd', False):
             rgb_marched = rgb_marched + alphainv_last.unsqueeze(-1) * torch.rand_like(rgb_marched)
         s = 1 - 1 / (1 + t)
@@ -507,7 +507,7 @@ class DirectContractedVoxGO(_ContractedBase):
 
     def _finish(self, N, dev, weights, alphainv_last, density, alpha, rgb, ray_id, step_id, t, inner_mask, n_max,
                 is_train, render_kwargs):
-        rgb_marched = segment_sum(weights.unsqueeze(-1) * rgb, ray_id, N)
+        rgb_marched = composite_rgb(weights, rgb, ray_id, N)
         if render_kwargs.get('rand_bkgd', False) and is_train:
             rgb_marched = rgb_marched + alphainv_last.unsqueeze(-1) * torch.rand_like(rgb_marched)
         else:
@@ -699,7 +699,7 @@ class DirectVoxGO(nn.Module):
             emb = _view_embed(viewdirs, self.viewfreq).flatten(0, -2)[ray_id]
             logit = self.rgbnet(torch.cat([k0_view, emb], -1))
             rgb = torch.sigmoid(logit if self.rgbnet_direct else logit + k0[:, :3])
-        rgb_marched = segment_sum(weights.unsqueeze(-1) * rgb, ray_id, N)
+        rgb_marched = composite_rgb(weights, rgb, ray_id, N)
         rgb_marched = rgb_marched + alphainv_last.unsqueeze(-1) * render_kwargs['bg']
         ret = {'alphainv_last': alphainv_last, 'weights': weights, 'rgb_marched': rgb_marched, 'raw_alpha': alpha,
                'raw_rgb': rgb, 'ray_id': ray_id}
