@@ -124,6 +124,62 @@ def test_pipelined_reduce_tv_adam_tail_gloo_world2():
     assert sorted(res) == [(0, 'ok'), (1, 'ok')], res
 
 
+def _sparse_worker(rank, world, port, q):
+    """allreduce_grads_sparse == allreduce_grads exactly; sparse route taken only where it pays."""
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    from unboundednerfpytorch_b200 import dist as D, grid as G
+    D.init_from_env(backend='gloo')
+    try:
+        g = torch.Generator().manual_seed(40 + rank)
+        chunk = 64
+
+        def make(shape, touched_frac, cl):
+            # whole chunks of zeros IN MEMORY ORDER, different per rank; cl: logical [P,C,X,Y,Z] over a [P,X,Y,Z,C] buffer
+            mem_shape = (shape[0], shape[2], shape[3], shape[4], shape[1]) if cl else shape
+            full = torch.randn(mem_shape, generator=g)
+            n = full.numel()
+            keep = (torch.rand((n + chunk - 1) // chunk, generator=g) < touched_frac).repeat_interleave(chunk)[:n]
+            full = (full.view(-1) * keep).view(mem_shape)
+            return full.permute(0, 4, 1, 2, 3) if cl else full
+
+        specs = [((3, 4, 9, 10, 11), 0.1, True),      # channels-last grid, sparse  -> sparse route (ragged tail: 11880 % 64 != 0)
+                 ((1, 1, 20, 20, 20), 0.9, False),    # mostly touched             -> dense fallback
+                 ((2, 2, 16, 16, 8), 0.0, False),     # nothing touched anywhere   -> nothing exchanged but flags
+                 ((40,), 1.0, False)]                 # small                      -> dense
+        pa, pb = [], []
+        for shape, frac, cl in specs:
+            grad = make(shape, frac, cl)
+            for lst in (pa, pb):
+                p = torch.nn.Parameter(torch.zeros(shape) if not cl else G.zeros_grid(list(shape)))
+                p.grad = torch.empty_like(p, memory_format=torch.preserve_format).copy_(grad)
+                assert p.grad.stride() == p.stride()
+                lst.append(p)
+        stats = D.allreduce_grads_sparse(pa, chunk=chunk, dense_above=0.5)
+        D.allreduce_grads(pb)
+        for x, y in zip(pa, pb):
+            assert x.grad.stride() == y.grad.stride() and torch.equal(x.grad, y.grad)
+        assert 0.0 < stats[pa[0]] <= 0.25 and stats[pa[1]] == 1.0 and stats[pa[2]] == 0.0 and pa[3] not in stats
+        q.put((rank, 'ok'))
+    except Exception:
+        import traceback
+        q.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_chunk_sparse_grad_exchange_gloo_world2():
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sparse_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, 'ok'), (1, 'ok')], res
+
+
 def test_ray_sharding_and_grad_exchange_gloo_world2():
     ctx = mp.get_context('spawn')
     q = ctx.Queue()

@@ -60,6 +60,52 @@ def allreduce_grads(params, world=None):
         h.wait()
 
 
+def allreduce_grads_sparse(params, chunk=4096, dense_above=0.5):
+    """Chunk-sparse gradient exchange (SURVEY.md 8e "brick-sparse all-reduce", with 1-D bricks of the memory-order buffer so
+    that no re-layout or padding of the grid is needed): for every large gradient
+      1. per-chunk touch flags  (any element != 0 in a run of `chunk` consecutive floats)     -- one pass over the gradient
+      2. union of the flags over ranks                                                        -- all-reduce(MAX) of n/chunk bytes
+      3. gather the union's chunks, all-reduce only those, scatter them back                  -- |union| * chunk floats
+    falling back to the dense all-reduce when the union covers more than `dense_above` of the tensor (then the
+    compaction would cost more than it saves; the synthetic bench rays touch nearly every chunk) or the tensor is
+    small.  Elements outside the union are zero on every rank, so the result equals the dense sum exactly, and
+    MaskedAdam's "skip where the summed grad == 0" rule is unchanged.  One host read per large tensor (the union size).
+    Returns {param: fraction of chunks exchanged} for the tensors that took the sparse route (1.0 = dense fallback)."""
+    stats = {}
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return stats
+    dense = []
+    for p in sorted((p for p in params if p.grad is not None), key=lambda p: -p.numel()):
+        g = _memory_order(p.grad)
+        n = g.numel()
+        if n < 64 * chunk or not g.is_contiguous():
+            dense.append(g)
+            continue
+        flat = g.view(-1)
+        n_full = n // chunk
+        body = flat[:n_full * chunk].view(n_full, chunk)
+        touched = (body != 0).any(dim=1).to(torch.uint8)
+        dist.all_reduce(touched, op=dist.ReduceOp.MAX)
+        idx = touched.nonzero(as_tuple=False).squeeze(1)             # host sync: the size of the union
+        frac = idx.numel() / max(n_full, 1)
+        if frac > dense_above:
+            dense.append(g)
+            stats[p] = 1.0
+            continue
+        stats[p] = frac
+        if idx.numel():
+            buf = body.index_select(0, idx)
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+            body.index_copy_(0, idx, buf)
+        if n_full * chunk < n:                                       # ragged tail: always exchanged
+            tail = flat[n_full * chunk:]
+            dist.all_reduce(tail, op=dist.ReduceOp.SUM)
+    handles = [dist.all_reduce(g, op=dist.ReduceOp.SUM, async_op=True) for g in dense]
+    for h in handles:
+        h.wait()
+    return stats
+
+
 def _memory_order(t):
     """Contiguous view of a channels-last 5-D grid (or the tensor itself) for a collective."""
     if not t.is_contiguous() and t.dim() == 5:
