@@ -1,0 +1,1 @@
+"""GPU / CPU parity tests of unboundednerfpytorch_b200 (see tests/conftest.py for the `gpu` marker)."""
