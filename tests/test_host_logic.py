@@ -147,3 +147,24 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_cabi, 'LIB_PATH', str(tmp_path / 'nope.so'))
     with pytest.raises(RuntimeError, match='no CPU or eager-PyTorch fallback'):
         _cabi.load()
+
+
+def test_rays_host_side_pieces():
+    """rays.py parts that are plain torch / numpy (the kernels are covered by the -m gpu tests): ndc_rays == the oracle's
+    restatement of dvgo.py:532-550 on the golden view, batch_indices_generator covers every index once per epoch."""
+    import numpy as np
+    from oracle import cpu_ref
+    from tests.util import assert_close, load_golden
+    from unboundednerfpytorch_b200 import rays as R
+    v = [x for x in load_golden('l1_rays.pt')['views'] if x['ndc'] and not x['flip_x'] and not x['flip_y'] and x['mode'] == 'center'][0]
+    o, d, _ = cpu_ref.get_rays_of_a_view(v['H'], v['W'], v['K'], v['c2w'], False, v['inverse_y'], False, False)
+    o2, d2 = R.ndc_rays(v['H'], v['W'], float(v['K'][0][0]), 1., o, d)
+    assert_close(o2, v['rays_o'], rtol=1e-6, what='ndc rays_o'); assert_close(d2, v['rays_d'], rtol=1e-6, what='ndc rays_d')
+    np.random.seed(0)
+    gen = R.batch_indices_generator(10, 4)
+    first_epoch = torch.cat([next(gen) for _ in range(2)])
+    assert first_epoch.dtype == torch.int64 and len(set(first_epoch.tolist())) == 8
+    nxt = next(gen)                                   # 8 + 4 > 10 -> reshuffle, like dvgo.py:663-665
+    assert nxt.shape == (4,) and int(nxt.max()) < 10
+    with pytest.raises(NotImplementedError):
+        R._rays_of_a_view(2, 2, np.eye(3), np.eye(4)[:3], False, False, False, False, 'bogus')
