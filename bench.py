@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the FourierGrid / DVGO rendering hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload truck|bicycle]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference|reference-gpu] [--workload truck|bicycle]
 
 Metric (BASELINE.json): ray-samples/sec, 8192 rays x 512 samples, one training iteration per step
 (forward + loss + backward + total-variation + MaskedAdam, i.e. run_train.py:251-288 of the reference).
@@ -14,7 +14,13 @@ One JSON line on stdout (rank 0).  `value` = device-timed throughput with the ra
 step through the public model API with the batch in pinned HOST memory (H2D of rays + target, D2H of the loss, every
 step, inside the timed region).  `roofline` = the dominant hand-written kernel, timed live with CUDA events inside the
 timed region.  `cpu_baseline` / `--impl reference` = the reference's algorithm on the host cores (CPU oracle port of
-the same step: torch F.grid_sample CPU path + C restatement of the CUDA-only ops) on a bounded ray sample.
+the same step: torch F.grid_sample CPU path + C restatement of the CUDA-only ops) on a bounded ray sample, with the
+thread count that is fastest for it.  `psnr_delta_vs_ref` = second half of the metric (oracle/psnr_check.py).
+`--impl reference-gpu` (informative, not part of the driver contract) = the reference's GPU path on this B200: its
+algorithm op by op with its own CUDA extension from oracle/_ref + ATen / cuBLAS.
+A/B switches (env): UBN_BENCH_TAIL=pipelined|sequential (multi-GPU tail), UBN_BENCH_LOSS=fused|torch,
+UBN_TV_IMPL=1|0 (streaming / element-per-thread TV), UBN_DENSITY_RED_PAIRS=1|0, UBN_FEATURE_IMPL, UBN_RGBNET_MODE,
+UBN_RGBNET_BWD_MODE, UBN_NCCL_HIGH_PRIORITY=1|0.
 """
 import argparse
 import json
