@@ -170,9 +170,6 @@ def segment_coo(src, index, out, reduce='sum'):
 # --------------------------------------------------------------------------------------------------
 # in-kernel training losses (run_train.py:254-279): MSE + entropy_last + per-point rgb loss
 # --------------------------------------------------------------------------------------------------
-_loss_scratch = {}
-
-
 class RenderLoss(torch.autograd.Function):
     """loss = w_main * mse(rgb_marched, target) + w_entropy * entropy_last(alphainv_last) + w_rgbper * rgbper, value and
     gradients from two launches (ubn_render_loss).  Returns a [4] tensor {loss, mse, entropy_last, rgbper}; only element 0
@@ -193,9 +190,7 @@ class RenderLoss(torch.autograd.Function):
         if use_per:
             raw_rgb, weights, ray_id = raw_rgb.contiguous(), weights.detach().contiguous(), ray_id.contiguous()
         n_pts = raw_rgb.shape[0] if use_per else 0
-        scratch = _loss_scratch.get(dev)
-        if scratch is None:
-            scratch = _loss_scratch[dev] = torch.empty(3 * 1024, dtype=torch.float64, device=dev)
+        scratch = torch.empty(3 * 1024, dtype=torch.float64, device=dev)   # per call: safe under concurrent streams
         out = torch.empty(4, device=dev)
         g_rgb = torch.empty_like(rgb_marched)
         g_last = torch.empty_like(alphainv_last) if use_ent else None
