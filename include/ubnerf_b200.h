@@ -178,6 +178,14 @@ int ubn_render_loss(const float* rgb_marched, const float* alphainv_last, const 
                     float w_entropy, float w_rgbper, float* out4, float* grad_rgb_marched, float* grad_alphainv_last,
                     float* grad_raw_rgb, double* scratch, int64_t scratch_len, void* stream);
 
+/* Distortion loss, torch_efficient_distloss.flatten_eff_distloss(w, s, interval, ray_id) as called at run_train.py:268-274
+ * (maths in-tree at dcvgo.py:387-409): out1[0] = (1/R) sum_rays [ sum_i interval/3 w_i^2 + 2 sum_i w_i (s_i W_<i - WS_<i) ]
+ * with R = n_rays (the caller passes ray_id.max()+1 like the library) and grad_w = d out / d w (NULL = value only).
+ * ray_id sorted; i_start / i_end: int64[n_rays] scratch; scratch: >= n_rays doubles.  Deterministic. */
+int ubn_distortion_loss(const float* w, const float* s, const int64_t* ray_id, int64_t n_pts, int64_t n_rays,
+                        float interval, int64_t* i_start, int64_t* i_end, float* out1, float* grad_w, double* scratch,
+                        int64_t scratch_len, void* stream);
+
 /* ---- trilinear voxel-grid reads: DenseGrid.forward (grid.py:50-61) and FourierGrid.forward
  *      (FourierGrid_grid.py:60-78) == torch F.grid_sample(bilinear, align_corners=True, zero padding)
  *      + its adjoint (grid_sampler_3d_backward wrt the grid) -------------------------------------

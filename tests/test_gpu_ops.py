@@ -498,3 +498,22 @@ def test_composite_rgb_vs_torch(n_rays, n_pts):
     if n_pts:
         assert_close(a[0].grad.cpu().double(), c[0].grad, rtol=1e-5, atol=1e-6, what='grad weights')
         assert_close(a[1].grad.cpu().double(), c[1].grad, rtol=1e-6, what='grad rgb')
+
+
+@pytest.mark.parametrize('n_rays,n_pts', [(1, 1), (7, 40), (300, 20000), (8192, 400000)])
+def test_distortion_loss_vs_oracle(oracle, n_rays, n_pts):
+    """ubn_distortion_loss vs the oracle's restatement of flatten_eff_distloss (dcvgo.py:387-409 maths), value + grad."""
+    from unboundednerfpytorch_b200.functional import flatten_eff_distloss
+    g = torch.Generator().manual_seed(n_rays + 3 * n_pts)
+    w = torch.rand(n_pts, generator=g) * 0.1
+    s = torch.sort(torch.rand(n_pts, generator=g)).values
+    rid = torch.sort(torch.randint(0, n_rays, (n_pts,), generator=g)).values
+    rid[-1] = n_rays - 1
+    wd = w.clone().double().requires_grad_(True)
+    ref = oracle.flatten_eff_distloss(wd, s.double(), 1 / 64, rid)
+    ref.backward()
+    wg = w.clone().to(DEV).requires_grad_(True)
+    out = flatten_eff_distloss(wg, s.to(DEV), 1 / 64, rid.to(DEV))
+    out.backward()
+    assert_close(out.detach().cpu().double(), ref.detach(), rtol=2e-5, what='distortion loss')
+    assert_close(wg.grad.cpu().double(), wd.grad, rtol=1e-4, atol=1e-7 * float(wd.grad.abs().max()) + 1e-12, what='grad w')

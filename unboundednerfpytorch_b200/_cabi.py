@@ -69,6 +69,7 @@ _SIGNATURES = {
     'ubn_gather_rays': [c_p, c_p, c_int, c_p, c_i64, c_i64, c_p, c_p],
     'ubn_composite_fwd': [c_p, c_p, c_p, c_i64, c_i64, c_p, c_p, c_p, c_p],
     'ubn_composite_bwd': [c_p, c_p, c_p, c_p, c_i64, c_p, c_p, c_p],
+    'ubn_distortion_loss': [c_p, c_p, c_p, c_i64, c_i64, c_f, c_p, c_p, c_p, c_p, c_p, c_i64, c_p],
     'ubn_render_loss': [c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_i64, c_f, c_f, c_f, c_p, c_p, c_p, c_p, c_p, c_i64, c_p],
     'ubn_grid_sample_fwd': [c_p, ctypes.POINTER(UbnGridDesc), c_p, c_i64, c_p, c_p],
     'ubn_grid_sample_bwd': [c_p, ctypes.POINTER(UbnGridDesc), c_p, c_i64, c_p, c_p],

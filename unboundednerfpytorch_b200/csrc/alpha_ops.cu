@@ -409,3 +409,100 @@ extern "C" int ubn_composite_bwd(const float* weights, const float* rgb, const i
   UBN_LAUNCH_CHECK();
   return 0;
 }
+
+
+// ---- distortion loss (torch_efficient_distloss.flatten_eff_distloss as used at run_train.py:268-274; maths kept in-tree at
+// dcvgo.py:387-409):  L = (1/R) sum_rays [ sum_i interval/3 * w_i^2 + 2 sum_i w_i (s_i W_<i - WS_<i) ],  R = max(ray_id)+1,
+// W_<i / WS_<i = exclusive prefix sums of w / w*s inside the ray.  One warp per ray: a forward sweep in 32-sample chunks
+// (warp scan + carried totals) yields the ray's loss and totals, a second sweep writes
+//   dL/dw_i = (1/R) [ 2/3 interval w_i + 2 (s_i W_<i - WS_<i) + 2 ((WS_tot - WS_<=i) - s_i (W_tot - W_<=i)) ].
+namespace ubn {
+
+__device__ __forceinline__ float warp_incl_scan(float v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const float t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += t;
+  }
+  return v;
+}
+
+__global__ void __launch_bounds__(128) k_distortion_loss(const float* __restrict__ w, const float* __restrict__ s,
+                                                         const int64_t* __restrict__ i_start, const int64_t* __restrict__ i_end,
+                                                         int64_t n_rays, float interval, float inv_r,
+                                                         float* __restrict__ grad_w, double* __restrict__ ray_loss) {
+  const int lane = threadIdx.x & 31;
+  const int64_t ray = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (ray >= n_rays) return;
+  const int64_t b = i_start[ray], e = i_end[ray];
+  float cw = 0.f, cws = 0.f;        // carried exclusive totals of the chunks done so far
+  double loss = 0.0;
+  for (int64_t c = b; c < e; c += 32) {
+    const int64_t i = c + lane;
+    const bool ok = i < e;
+    const float wi = ok ? w[i] : 0.f, si = ok ? s[i] : 0.f;
+    const float ws = wi * si;
+    const float iw = warp_incl_scan(wi, lane), iws = warp_incl_scan(ws, lane);
+    const float pw = cw + (iw - wi), pws = cws + (iws - ws);          // exclusive prefixes inside the ray
+    if (ok) loss += (double)(interval * (1.f / 3.f) * wi * wi + 2.f * wi * (si * pw - pws));
+    cw += __shfl_sync(0xffffffffu, iw, 31);
+    cws += __shfl_sync(0xffffffffu, iws, 31);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) loss += __shfl_xor_sync(0xffffffffu, loss, o);
+  if (lane == 0) ray_loss[ray] = loss;
+  if (!grad_w) return;
+  const float wt = cw, wst = cws;   // ray totals
+  cw = 0.f; cws = 0.f;
+  for (int64_t c = b; c < e; c += 32) {
+    const int64_t i = c + lane;
+    const bool ok = i < e;
+    const float wi = ok ? w[i] : 0.f, si = ok ? s[i] : 0.f;
+    const float ws = wi * si;
+    const float iw = warp_incl_scan(wi, lane), iws = warp_incl_scan(ws, lane);
+    const float pw = cw + (iw - wi), pws = cws + (iws - ws);
+    const float aw = wt - (cw + iw), aws = wst - (cws + iws);         // strictly-after sums
+    if (ok) grad_w[i] = inv_r * (interval * (2.f / 3.f) * wi + 2.f * (si * pw - pws) + 2.f * (aws - si * aw));
+    cw += __shfl_sync(0xffffffffu, iw, 31);
+    cws += __shfl_sync(0xffffffffu, iws, 31);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_distortion_finish(const double* __restrict__ ray_loss, int64_t n_rays, float inv_r,
+                                                           float* __restrict__ out) {
+  __shared__ double sh[256];
+  double a = 0;
+  for (int64_t r = threadIdx.x; r < n_rays; r += 256) a += ray_loss[r];   // fixed assignment -> deterministic
+  sh[threadIdx.x] = a;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = (float)(sh[0] * (double)inv_r);
+}
+
+}  // namespace ubn
+
+extern "C" int ubn_distortion_loss(const float* w, const float* s, const int64_t* ray_id, int64_t n_pts, int64_t n_rays,
+                                   float interval, int64_t* i_start, int64_t* i_end, float* out1, float* grad_w,
+                                   double* scratch, int64_t scratch_len, void* stream) {
+  using namespace ubn;
+  cudaStream_t st = as_stream(stream);
+  if (n_rays <= 0) return finish(cudaErrorInvalidValue);
+  if (scratch_len < n_rays) return finish(cudaErrorInvalidValue);
+  // segment bounds of the sorted ray_id (empty rays keep [0,0)); out1 doubles as k_init_rays' float slot when n_rays == 1
+  float* dummy = reinterpret_cast<float*>(scratch);   // n_rays floats fit in n_rays doubles; overwritten below
+  k_init_rays<<<blocks_for(n_rays, 256), 256, 0, st>>>(n_rays, dummy, i_start, i_end);
+  UBN_LAUNCH_CHECK();
+  if (n_pts > 0) {
+    k_segment_bounds<<<blocks_for(n_pts, 256), 256, 0, st>>>(ray_id, n_pts, i_start, i_end);
+    UBN_LAUNCH_CHECK();
+  }
+  const float inv_r = 1.f / (float)n_rays;
+  k_distortion_loss<<<blocks_for(n_rays, 4), 128, 0, st>>>(w, s, i_start, i_end, n_rays, interval, inv_r, grad_w, scratch);
+  UBN_LAUNCH_CHECK();
+  k_distortion_finish<<<1, 256, 0, st>>>(scratch, n_rays, inv_r, out1);
+  UBN_LAUNCH_CHECK();
+  return 0;
+}

@@ -115,3 +115,4 @@ extern "C" int ubn_render_loss(const float* rgb_marched, const float* alphainv_l
   UBN_LAUNCH_CHECK();
   return 0;
 }
+

@@ -221,3 +221,42 @@ def render_loss(render_result, target, weight_main=1.0, weight_entropy_last=0.0,
                            weight_main, weight_entropy_last, weight_rgbper)
     d = out.detach()
     return out[0], {'mse': d[1], 'entropy_last': d[2], 'rgbper': d[3]}
+
+
+# --------------------------------------------------------------------------------------------------
+# distortion loss (torch_efficient_distloss.flatten_eff_distloss, run_train.py:268-274)
+# --------------------------------------------------------------------------------------------------
+class DistortionLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, w, s, interval, ray_id, n_rays):
+        from ._cabi import c_f, c_i64, check, ptr, stream_of
+        if not (w.is_cuda and s.is_cuda and ray_id.is_cuda):
+            raise RuntimeError('w / s / ray_id must be CUDA tensors')
+        w, s, ray_id = w.contiguous().float(), s.contiguous().float(), ray_id.contiguous()
+        dev = w.device
+        out = torch.empty(1, device=dev)
+        gw = torch.empty_like(w)
+        i_s = torch.empty(n_rays, dtype=torch.int64, device=dev)
+        i_e = torch.empty(n_rays, dtype=torch.int64, device=dev)
+        scratch = torch.empty(max(n_rays, 1), dtype=torch.float64, device=dev)
+        with ops._Guard(w) as lib:
+            check(lib.ubn_distortion_loss(ptr(w), ptr(s), ptr(ray_id), c_i64(w.shape[0]), c_i64(n_rays), c_f(float(interval)),
+                                          ptr(i_s), ptr(i_e), ptr(out), ptr(gw), ptr(scratch), c_i64(scratch.numel()),
+                                          stream_of(w)))
+        ctx.save_for_backward(gw)
+        return out[0]
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        (gw,) = ctx.saved_tensors
+        return gw * g, None, None, None, None
+
+
+def flatten_eff_distloss(w, s, interval, ray_id):
+    """Same call as torch_efficient_distloss.flatten_eff_distloss (run_train.py:273): mean over max(ray_id)+1 rays.
+    One host read (the ray count) unless ``ray_id`` is empty."""
+    if w.numel() == 0:
+        return w.sum() * 0
+    n_rays = int(ray_id[-1]) + 1                      # sorted ids: the last one is the maximum
+    return DistortionLoss.apply(w, s, interval, ray_id, n_rays)
