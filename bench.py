@@ -379,7 +379,9 @@ def main():
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
         ev[0].record()
         # all-reduce (N > 1) -> dense TV -> MaskedAdam; per slab, so the sweeps of slab p overlap the transfer of slab p+1
-        if os.environ.get('UBN_BENCH_TAIL', 'pipelined') == 'sequential':     # A/B switch: whole-tensor all-reduce first
+        if os.environ.get('UBN_BENCH_TAIL', 'pipelined') == 'pingpong' and world == 1:   # single-sweep TV + Adam (WIP)
+            opt.step_fused_tv(tv_terms, write_grad=False)
+        elif os.environ.get('UBN_BENCH_TAIL', 'pipelined') == 'sequential':     # A/B switch: whole-tensor all-reduce first
             if world > 1:
                 ubdist.allreduce_grads(params)
             model.density_total_variation_add_grad(1e-6 / N_RAYS, True)

@@ -145,6 +145,16 @@ int ubn_tv_adam_fused(float* param, float* grad, float* exp_avg, float* exp_avg_
                       int64_t inner, int tv_mode, int step, float beta1, float beta2, float lr, float eps,
                       int adam_mode, int zero_grad, void* stream);
 
+/* Single-pass tail with ping-pong parameters: total_variation_add_grad + (masked) adam_upd in ONE walk that reads param,
+ * grad, exp_avg, exp_avg_sq once and writes the updated parameters to `param_out` (a second buffer of the same layout; the
+ * caller swaps the two afterwards), so the TV stencil never sees a half-updated neighbourhood.  Channels-last grids only
+ * (inner % 4 == 0, sz_k * inner / 4 <= 512).  Bit-identical to ubn_total_variation_add_grad followed by ubn_adam_upd
+ * (adam_mode 0 / 1).  write_grad = 0 skips storing the TV-augmented gradient. */
+int ubn_tv_adam_pingpong(const float* param, float* param_out, float* grad, float* exp_avg, float* exp_avg_sq, float wx,
+                         float wy, float wz, int64_t lead, int64_t sz_i, int64_t sz_j, int64_t sz_k, int64_t inner,
+                         int dense_mode, int step, float beta1, float beta2, float lr, float eps, int adam_mode,
+                         int write_grad, void* stream);
+
 /* ---- ub360_utils_cuda (FourierGrid/cuda/ub360_utils.cpp:20-22) -------------------------------- */
 /* ub360_utils_cuda.cumdist_thres              ub360_utils.cpp:13-18 / ub360_utils_kernel.cu:13-47 */
 int ubn_cumdist_thres(const float* dist, float thres, int64_t n_rays, int64_t n_pts, uint8_t* mask,

@@ -517,3 +517,30 @@ def test_distortion_loss_vs_oracle(oracle, n_rays, n_pts):
     out.backward()
     assert_close(out.detach().cpu().double(), ref.detach(), rtol=2e-5, what='distortion loss')
     assert_close(wg.grad.cpu().double(), wd.grad, rtol=1e-4, atol=1e-7 * float(wd.grad.abs().max()) + 1e-12, what='grad w')
+
+@pytest.mark.parametrize('shape', [(2, 12, 20, 9, 11), (1, 12, 40, 70, 11), (3, 4, 17, 33, 40)])
+def test_tv_adam_pingpong_matches_two_sweeps(shape):
+    """MaskedAdam.step_fused_tv (one ping-pong sweep) == total_variation_add_grad + step(), bit for bit, over 3 steps,
+    dense and sparse TV, masked and plain Adam."""
+    from unboundednerfpytorch_b200 import grid as G, ops
+    from unboundednerfpytorch_b200.masked_adam import MaskedAdam
+    for skip in (True, False):
+        g = torch.Generator().manual_seed(sum(shape) + skip)
+        init = torch.randn(shape, generator=g)
+        pa = torch.nn.Parameter(G._as_cl3d(init.clone().to(DEV)))
+        pb = torch.nn.Parameter(G._as_cl3d(init.clone().to(DEV)))
+        oa = MaskedAdam([dict(params=[pa], lr=0.1, skip_zero_grad=skip)])
+        ob = MaskedAdam([dict(params=[pb], lr=0.1, skip_zero_grad=skip)])
+        for it in range(3):
+            grad = (torch.randn(shape, generator=g) * (torch.rand(shape, generator=g) > 0.6)).to(DEV)
+            pa.grad = torch.empty_like(pa, memory_format=torch.preserve_format).copy_(grad)
+            pb.grad = torch.empty_like(pb, memory_format=torch.preserve_format).copy_(grad)
+            dense = it != 1
+            oa.step_fused_tv({pa: (0.3, 0.2, 0.1, dense)})
+            ops.total_variation_add_grad(pb, pb.grad, 0.3, 0.2, 0.1, dense)
+            ob.step()
+            assert pa.stride() == pb.stride()
+            assert_equal(pa.data, pb.data, f'param step {it} skip={skip}')
+            assert_equal(pa.grad, pb.grad, 'grad after TV')
+            assert_equal(oa.state[pa]['exp_avg'], ob.state[pb]['exp_avg'], 'exp_avg')
+            assert_equal(oa.state[pa]['exp_avg_sq'], ob.state[pb]['exp_avg_sq'], 'exp_avg_sq')

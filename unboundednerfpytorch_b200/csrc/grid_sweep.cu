@@ -225,6 +225,64 @@ __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, 
   else            p = __fsub_rn(p, __fdiv_rn(__fmul_rn(h.step_size, m), den));
 }
 
+// ---- single-pass tail: streaming TV + (masked) Adam with ping-pong parameters ------------------------------------------
+// The two sweeps above cost 12 + 28 B per element because Adam must not overwrite parameters the TV stencil of a
+// neighbouring CTA still has to read.  Writing the updated parameters into a SECOND buffer removes the hazard:
+// one walk reads p, g, m, v once and writes p_out, m, v (+ g when the caller wants the TV-augmented gradient kept):
+// 28-32 B per element.  Arithmetic = k_total_variation_stream followed by adam_one on the rounded sum, i.e. bit-identical
+// to the two-sweep result.  Masked mode (kMode 1): where the summed gradient is 0, p_out = p and m, v are left alone.
+constexpr int kTaThreads = 512;
+
+template <bool kDense, int kMode, bool kWriteGrad>
+__global__ void __launch_bounds__(kTaThreads, 2) k_tv_adam_stream(const float4* __restrict__ param, float4* __restrict__ param_out,
+                                                                  float4* __restrict__ grad, float4* __restrict__ exp_avg,
+                                                                  float4* __restrict__ exp_avg_sq, float wy, float wz,
+                                                                  TvStreamShape s, AdamHyper h) {
+  int b = blockIdx.x;
+  const int seg = b % s.n_seg; b /= s.n_seg;
+  const int jt = b % s.n_jt;
+  const int lead = b / s.n_jt;
+  const int j0 = jt * s.tj;
+  const int rows = min(s.tj, s.sz_j - j0);
+  const int i0 = seg * s.seg_len;
+  const int i1 = min(i0 + s.seg_len, s.sz_i);
+  const int64_t plane4 = (int64_t)s.sz_j * s.row4;
+  const int col = threadIdx.x;
+  if (col >= rows * s.row4) return;
+  const int jj = col / s.row4, r = col - jj * s.row4;
+  int64_t off = ((int64_t)lead * s.sz_i + i0) * plane4 + (int64_t)(j0 + jj) * s.row4 + r;
+  const bool hkm = r >= s.inner4, hkp = r < s.row4 - s.inner4, hjm = j0 + jj > 0, hjp = j0 + jj < s.sz_j - 1;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 prev = i0 > 0 ? param[off - plane4] : zero4;
+  float4 cur = param[off];
+  for (int i = i0; i < i1; ++i, off += plane4) {
+    const bool him = i > 0, hip = i < s.sz_i - 1;
+    const float4 next = hip ? param[off + plane4] : zero4;
+    float4 g = grad[off];
+    float4 m = exp_avg[off], v = exp_avg_sq[off];
+    const float4 p = cur;
+    const float4 km = hkm ? param[off - s.inner4] : zero4;
+    const float4 kp = hkp ? param[off + s.inner4] : zero4;
+    const float4 jm = hjm ? param[off - s.row4] : zero4;
+    const float4 jp = hjp ? param[off + s.row4] : zero4;
+    if (kDense || g.x != 0) g.x = g.x + tv_term_vals(p.x, km.x, kp.x, jm.x, jp.x, prev.x, next.x, hkm, hkp, hjm, hjp, him, hip, wy, wz);
+    if (kDense || g.y != 0) g.y = g.y + tv_term_vals(p.y, km.y, kp.y, jm.y, jp.y, prev.y, next.y, hkm, hkp, hjm, hjp, him, hip, wy, wz);
+    if (kDense || g.z != 0) g.z = g.z + tv_term_vals(p.z, km.z, kp.z, jm.z, jp.z, prev.z, next.z, hkm, hkp, hjm, hjp, him, hip, wy, wz);
+    if (kDense || g.w != 0) g.w = g.w + tv_term_vals(p.w, km.w, kp.w, jm.w, jp.w, prev.w, next.w, hkm, hkp, hjm, hjp, him, hip, wy, wz);
+    float4 q = p;
+    bool any = false;
+    if (kMode == 0 || g.x != 0) { adam_one<kMode>(q.x, g.x, m.x, v.x, 0.f, h); any = true; }
+    if (kMode == 0 || g.y != 0) { adam_one<kMode>(q.y, g.y, m.y, v.y, 0.f, h); any = true; }
+    if (kMode == 0 || g.z != 0) { adam_one<kMode>(q.z, g.z, m.z, v.z, 0.f, h); any = true; }
+    if (kMode == 0 || g.w != 0) { adam_one<kMode>(q.w, g.w, m.w, v.w, 0.f, h); any = true; }
+    param_out[off] = q;
+    if (any) { exp_avg[off] = m; exp_avg_sq[off] = v; }
+    if (kWriteGrad) grad[off] = g;
+    prev = p;
+    cur = next;
+  }
+}
+
 // vectorised (float4) main body + scalar tail
 template <int kMode>
 __global__ void __launch_bounds__(256) k_adam_vec4(float4* __restrict__ param, const float4* __restrict__ grad,
@@ -444,6 +502,51 @@ int ubn_tv_adam_fused(float* param, float* grad, float* exp_avg, float* exp_avg_
     return zero_grad ? launch_adam_zero<0, true>(param, grad, exp_avg, exp_avg_sq, g.n, h, st)
                      : launch_adam_zero<0, false>(param, grad, exp_avg, exp_avg_sq, g.n, h, st);
   return finish(cudaErrorInvalidValue);
+}
+
+
+int ubn_tv_adam_pingpong(const float* param, float* param_out, float* grad, float* exp_avg, float* exp_avg_sq, float wx,
+                         float wy, float wz, int64_t lead, int64_t sz_i, int64_t sz_j, int64_t sz_k, int64_t inner,
+                         int dense_mode, int step, float beta1, float beta2, float lr, float eps, int adam_mode,
+                         int write_grad, void* stream) {
+  (void)wx;
+  if (lead * sz_i * sz_j * sz_k * inner <= 0) return 0;
+  if (param == param_out || inner % 4 != 0 || sz_i < 8 || (adam_mode != 0 && adam_mode != 1)) return finish(cudaErrorInvalidValue);
+  if ((((uintptr_t)param) | ((uintptr_t)param_out) | ((uintptr_t)grad) | ((uintptr_t)exp_avg) | ((uintptr_t)exp_avg_sq)) & 15)
+    return finish(cudaErrorInvalidValue);
+  const int64_t row4 = sz_k * inner / 4;
+  if (row4 > kTaThreads || row4 < 32) return finish(cudaErrorInvalidValue);
+  TvStreamShape s;
+  s.sz_i = (int)sz_i; s.sz_j = (int)sz_j; s.row4 = (int)row4; s.inner4 = (int)(inner / 4);
+  s.tj = (int)std::max<int64_t>(1, kTaThreads / row4);
+  s.n_jt = (int)((sz_j + s.tj - 1) / s.tj);
+  const int64_t tiles = lead * s.n_jt;
+  int64_t n_seg = (8 * 2 * 148 + tiles - 1) / tiles;
+  n_seg = std::max<int64_t>(1, std::min<int64_t>(n_seg, sz_i / 16));
+  s.seg_len = (int)((sz_i + n_seg - 1) / n_seg);
+  s.n_seg = (int)((sz_i + s.seg_len - 1) / s.seg_len);
+  const int64_t nb = tiles * s.n_seg;
+  if (nb > 0x7fffffffll) return finish(cudaErrorInvalidValue);
+  const AdamHyper h = make_hyper(step, beta1, beta2, lr, eps);
+  wy /= 6; wz /= 6;
+  cudaStream_t st = as_stream(stream);
+  const float4* p = (const float4*)param;
+  float4 *po = (float4*)param_out, *g = (float4*)grad, *m = (float4*)exp_avg, *v = (float4*)exp_avg_sq;
+#define UBN_TA(D, M, W) k_tv_adam_stream<D, M, W><<<(unsigned)nb, kTaThreads, 0, st>>>(p, po, g, m, v, wy, wz, s, h)
+  const int key = (dense_mode ? 4 : 0) | (adam_mode ? 2 : 0) | (write_grad ? 1 : 0);
+  switch (key) {
+    case 0: UBN_TA(false, 0, false); break;
+    case 1: UBN_TA(false, 0, true); break;
+    case 2: UBN_TA(false, 1, false); break;
+    case 3: UBN_TA(false, 1, true); break;
+    case 4: UBN_TA(true, 0, false); break;
+    case 5: UBN_TA(true, 0, true); break;
+    case 6: UBN_TA(true, 1, false); break;
+    default: UBN_TA(true, 1, true); break;
+  }
+#undef UBN_TA
+  UBN_LAUNCH_CHECK();
+  return 0;
 }
 
 }  // extern "C"

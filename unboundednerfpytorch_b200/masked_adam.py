@@ -60,6 +60,37 @@ class MaskedAdam(torch.optim.Optimizer):
             ops.adam_upd(p, g, m, v, state['step'], beta1, beta2, lr, eps)
 
     @torch.no_grad()
+    def step_fused_tv(self, tv=None, write_grad=True):
+        """``total_variation_add_grad`` on the grids listed in ``tv`` ({param: (wx, wy, wz, dense_mode)}) + ``step()`` with the
+        two full-grid sweeps merged into one for channels-last grids (ops.tv_adam_pingpong): the updated parameters are
+        written into a second buffer and the parameter's storage is swapped with it (state key 'pingpong', allocated on
+        first use: +1 grid of memory).  Same result as the two calls, bit for bit."""
+        tv = tv or {}
+        for group in self.param_groups:
+            group['skip_zero_grad']
+            for param in group['params']:
+                if param.grad is None:
+                    continue
+                state = self._begin(param)
+                fused = (param in tv and self.per_lr is None and ops.tv_adam_pingpong_supported(param)
+                         and param.grad.stride() == param.stride())
+                if not fused:
+                    if param in tv:
+                        ops.total_variation_add_grad(param, param.grad, *tv[param])
+                    self._apply(group, param, state)
+                    continue
+                if 'pingpong' not in state:
+                    state['pingpong'] = torch.empty_like(param, memory_format=torch.preserve_format)
+                wx, wy, wz, dense = tv[param]
+                (beta1, beta2) = group['betas']
+                ops.tv_adam_pingpong(param.data, state['pingpong'], param.grad, state['exp_avg'], state['exp_avg_sq'], wx, wy, wz,
+                                     dense, state['step'], beta1, beta2, group['lr'], group['eps'],
+                                     skip_zero_grad=group['skip_zero_grad'], write_grad=write_grad)
+                old = param.data
+                param.data = state['pingpong']
+                state['pingpong'] = old
+
+    @torch.no_grad()
     def step(self):
         for group in self.param_groups:
             group['skip_zero_grad']                       # KeyError when absent, like masked_adam.py:49

@@ -288,6 +288,32 @@ def tv_adam_fused(param, grad, exp_avg, exp_avg_sq, wx, wy, wz, tv_mode, step, b
                                     c_int(1 if zero_grad else 0), stream_of(param)))
 
 
+def tv_adam_pingpong_supported(param):
+    """Channels-last 5-D grid whose (Z, C) row fits one CTA of the streaming kernel."""
+    if param.dim() != 5 or param.is_contiguous() or not param.permute(0, 2, 3, 4, 1).is_contiguous():
+        return False
+    C, X, Z = param.shape[1], param.shape[2], param.shape[4]
+    return C % 4 == 0 and X >= 8 and 32 <= Z * C // 4 <= 512
+
+
+def tv_adam_pingpong(param, param_out, grad, exp_avg, exp_avg_sq, wx, wy, wz, dense_mode, step, beta1, beta2, lr, eps,
+                     skip_zero_grad=True, write_grad=True):
+    """TV + (masked) Adam in one sweep, updated parameters written to ``param_out`` (same layout; caller swaps)."""
+    if not tv_adam_pingpong_supported(param):
+        raise RuntimeError('tv_adam_pingpong needs a channels-last [P,C,X,Y,Z] grid with C % 4 == 0')
+    lead, inner = _sweep_layout(param)
+    for t, nm in ((param_out, 'param_out'), (grad, 'grad'), (exp_avg, 'exp_avg'), (exp_avg_sq, 'exp_avg_sq')):
+        _dense_like(param, t, nm)
+    if param_out.data_ptr() == param.data_ptr():
+        raise RuntimeError('param_out must be a different buffer')
+    with _Guard(param) as lib:
+        check(lib.ubn_tv_adam_pingpong(ptr(param), ptr(param_out), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), c_f(float(wx)),
+                                       c_f(float(wy)), c_f(float(wz)), c_i64(lead), c_i64(param.shape[2]), c_i64(param.shape[3]),
+                                       c_i64(param.shape[4]), c_i64(inner), c_int(int(bool(dense_mode))), c_int(int(step)),
+                                       c_f(beta1), c_f(beta2), c_f(lr), c_f(eps), c_int(1 if skip_zero_grad else 0),
+                                       c_int(1 if write_grad else 0), stream_of(param)))
+
+
 def cumdist_thres(dist, thres):
     _chk(dist, 'dist')
     mask = torch.empty(dist.shape, dtype=torch.bool, device=dist.device)
