@@ -35,7 +35,7 @@ def _worker(rank, world, port, q):
         # 2) frame gather: every rank renders its shard, all ranks get the assembled frame
         frame = D.gather_frame(mine * 2, n, rank, world)
         assert torch.equal(frame, rays * 2)
-        # 3) gradient exchange: sum over ranks == single-process gradient of the concatenated batch, incl. a
+        # 3) gradient exchange: mean over ranks == single-process gradient of the mean loss on the concatenated batch, incl. a
         #    channels-last grid gradient (reduced in memory order without a copy) and a small rgbnet parameter
         torch.manual_seed(0)
         full = torch.randn(world, 2, 4, 3, 3, 3)
@@ -46,8 +46,8 @@ def _worker(rank, world, port, q):
         p_none = torch.nn.Parameter(torch.zeros(2))           # no grad on this rank: skipped
         D.allreduce_grads([p_grid, p_lin, p_none])
         assert p_grid.grad.stride() == p_grid.stride()
-        assert torch.allclose(p_grid.grad, full.sum(0))
-        assert torch.equal(p_lin.grad, torch.full((5,), float(sum(range(1, world + 1)))))
+        assert torch.allclose(p_grid.grad, full.mean(0))           # MEAN over ranks: per-rank losses are per-rank means
+        assert torch.allclose(p_lin.grad, torch.full((5,), float(sum(range(1, world + 1))) / world))
         # 4) Block-NeRF style inverse-distance compositing of per-rank renders
         o = torch.zeros(7, 3)
         cent = torch.tensor([1.0 + rank, 0., 0.])

@@ -51,12 +51,11 @@ def test_ray_aabb_and_counts(ops, oracle, n):
     st_g, dr_g = ops.infer_ray_start_dir(args_g[0], args_g[1], tmin_g)
     assert_close(st_g, st_c, what='start'); assert_close(dr_g, dr_c, what='dir')
     ref = ref_cuda('render_utils_cuda')
-    if ref is not None:             # bit-exact against the reference's own CUDA build
-        a, b = ref.infer_t_minmax(*args_g, 0.2, 1e9)
-        assert_equal(tmin_g, a, 't_min vs ref-cuda'); assert_equal(tmax_g, b, 't_max vs ref-cuda')
-        assert_equal(ns_g, ref.infer_n_samples(args_g[1], a, b, 0.03), 'N_steps vs ref-cuda')
-        a, b = ref.infer_ray_start_dir(args_g[0], args_g[1], tmin_g)
-        assert_equal(st_g, a, 'start vs ref-cuda'); assert_equal(dr_g, b, 'dir vs ref-cuda')
+    a, b = ref.infer_t_minmax(*args_g, 0.2, 1e9)
+    assert_equal(tmin_g, a, 't_min vs ref-cuda'); assert_equal(tmax_g, b, 't_max vs ref-cuda')
+    assert_equal(ns_g, ref.infer_n_samples(args_g[1], a, b, 0.03), 'N_steps vs ref-cuda')
+    a, b = ref.infer_ray_start_dir(args_g[0], args_g[1], tmin_g)
+    assert_equal(st_g, a, 'start vs ref-cuda'); assert_equal(dr_g, b, 'dir vs ref-cuda')
 
 
 @pytest.mark.parametrize('n', [1, 33, 1024, 8192])
@@ -66,10 +65,9 @@ def test_sample_pts_on_rays(ops, oracle, n):
     stepdist = 0.5 * 2 / 64
     out_g = ops.sample_pts_on_rays(ro.to(DEV), rd.to(DEV), mn.to(DEV), mx.to(DEV), 0.2, 1e9, stepdist)
     ref = ref_cuda('render_utils_cuda')
-    if ref is not None:
-        out_r = ref.sample_pts_on_rays(ro.to(DEV), rd.to(DEV), mn.to(DEV), mx.to(DEV), 0.2, 1e9, stepdist)
-        for a, b, nm in zip(out_g, out_r, ('pts', 'mask_outbbox', 'ray_id', 'step_id', 'N_steps', 't_min', 't_max')):
-            assert_equal(a, b, nm + ' vs ref-cuda')         # floats too: same arithmetic, same compiler
+    out_r = ref.sample_pts_on_rays(ro.to(DEV), rd.to(DEV), mn.to(DEV), mx.to(DEV), 0.2, 1e9, stepdist)
+    for a, b, nm in zip(out_g, out_r, ('pts', 'mask_outbbox', 'ray_id', 'step_id', 'N_steps', 't_min', 't_max')):
+        assert_equal(a, b, nm + ' vs ref-cuda')         # floats too: same arithmetic, same compiler
     out_c = oracle.sample_pts_on_rays(ro, rd, mn, mx, 0.2, 1e9, stepdist)
     if torch.equal(out_g[4].cpu(), out_c[4]):
         for a, b, nm in zip(out_g, out_c, ('pts', 'mask_outbbox', 'ray_id', 'step_id', 'N_steps', 't_min', 't_max')):
@@ -99,10 +97,9 @@ def test_sample_ndc_and_bg(ops, oracle):
     bc = oracle.sample_bg_pts_on_rays(ro, rd, tmax, 0.5, 32)
     assert_close(bg, bc, rtol=2e-5, what='bg pts')
     ref = ref_cuda('render_utils_cuda')
-    if ref is not None:
-        pr, mr = ref.sample_ndc_pts_on_rays(ro.to(DEV), rd.to(DEV), mn.to(DEV), mx.to(DEV), 65)
-        assert_equal(pg, pr, 'ndc pts vs ref-cuda'); assert_equal(mg, mr, 'ndc mask vs ref-cuda')
-        assert_equal(bg, ref.sample_bg_pts_on_rays(ro.to(DEV), rd.to(DEV), tmax.to(DEV), 0.5, 32), 'bg vs ref-cuda')
+    pr, mr = ref.sample_ndc_pts_on_rays(ro.to(DEV), rd.to(DEV), mn.to(DEV), mx.to(DEV), 65)
+    assert_equal(pg, pr, 'ndc pts vs ref-cuda'); assert_equal(mg, mr, 'ndc mask vs ref-cuda')
+    assert_equal(bg, ref.sample_bg_pts_on_rays(ro.to(DEV), rd.to(DEV), tmax.to(DEV), 0.5, 32), 'bg vs ref-cuda')
 
 
 @pytest.mark.parametrize('n', [0, 1, 999, 300000])
@@ -118,7 +115,7 @@ def test_maskcache_lookup(ops, oracle, n):
     assert out_g.dtype == torch.bool and out_g.shape == (n,)
     assert_equal(out_g, out_c, 'maskcache vs oracle')           # same fma + round-half-away => bit exact
     ref = ref_cuda('render_utils_cuda')
-    if ref is not None and n > 0:
+    if n > 0:
         assert_equal(out_g, ref.maskcache_lookup(mask.to(DEV), xyz.to(DEV), scale.to(DEV), shift.to(DEV)), 'vs ref-cuda')
 
 
@@ -153,7 +150,7 @@ def test_raw2alpha(ops, oracle, n):
     assert_close(ops.raw2alpha_nonuni_backward(e2, gb.to(DEV), itv.to(DEV))[fin.to(DEV)],
                  oracle.raw2alpha_nonuni_backward(e2c, gb, itv)[fin], what='nonuni grad')
     ref = ref_cuda('render_utils_cuda')
-    if ref is not None and n > 0:
+    if n > 0:
         er, ar = ref.raw2alpha(d.to(DEV), -2.0, 0.5)
         assert_equal(a_g, ar, 'alpha vs ref-cuda'); assert_equal(e_g, er, 'exp vs ref-cuda')
         assert_equal(g_g, ref.raw2alpha_backward(er, gb.to(DEV), 0.5), 'grad vs ref-cuda')
@@ -184,7 +181,7 @@ def test_alpha2weight_ragged(ops, oracle, n_rays, max_len):
     gc = oracle.alpha2weight_backward(alpha, *out_c, n_rays, gw, gl)
     assert_close(gg, gc, rtol=2e-5, atol=1e-6, what='alpha2weight grad')
     ref = ref_cuda('render_utils_cuda')
-    if ref is not None and len(alpha) > 0:
+    if len(alpha) > 0:
         out_r = ref.alpha2weight(alpha.to(DEV), ray_id.to(DEV), n_rays)
         for a, b, nm in zip(out_g, out_r, names):
             assert_equal(a, b, nm + ' vs ref-cuda')
@@ -242,8 +239,7 @@ def test_cumdist_thres(ops, oracle, n_rays, n_pts):
     out_g = ops.cumdist_thres(dist.to(DEV), 0.0149)
     assert_equal(out_g, oracle.cumdist_thres(dist, 0.0149), 'cumdist vs oracle')     # same sequential float adds
     ref = ref_cuda('ub360_utils_cuda')
-    if ref is not None:
-        assert_equal(out_g, ref.cumdist_thres(dist.to(DEV), 0.0149), 'cumdist vs ref-cuda')
+    assert_equal(out_g, ref.cumdist_thres(dist.to(DEV), 0.0149), 'cumdist vs ref-cuda')
 
 
 @pytest.mark.parametrize('shape,layout', [((1, 1, 5, 6, 7), 'ref'), ((1, 12, 9, 8, 10), 'ref'), ((9, 12, 6, 5, 7), 'cl'),
@@ -265,10 +261,9 @@ def test_total_variation(ops, oracle, shape, layout):
         if not dense:
             assert torch.equal(g_g.cpu()[grad == 0], grad[grad == 0])        # untouched where grad was 0
         ref = ref_cuda('total_variation_cuda')
-        if ref is not None:
-            g_r = grad.to(DEV)
-            ref.total_variation_add_grad(param.to(DEV), g_r, 0.3, 0.2, 0.1, dense)
-            assert_equal(g_g.contiguous(), g_r, 'tv vs ref-cuda')
+        g_r = grad.to(DEV)
+        ref.total_variation_add_grad(param.to(DEV), g_r, 0.3, 0.2, 0.1, dense)
+        assert_equal(g_g.contiguous(), g_r, 'tv vs ref-cuda')
     tv = load_golden('l1_grids.pt')['tv']
     for k in ('dense1', 'dense0'):
         gg = tv[k]['grad_in'].to(DEV)
@@ -284,23 +279,22 @@ def test_adam_variants(ops, oracle, n):
         perlr = torch.rand(n, generator=g)
         pg, mg, vg, lg = p.to(DEV), m.to(DEV), v.to(DEV), perlr.to(DEV)
         refm = ref_cuda('adam_upd_cuda')
-        pr, mr, vr = (pg.clone(), mg.clone(), vg.clone()) if refm is not None else (None, None, None)
+        pr, mr, vr = pg.clone(), mg.clone(), vg.clone()
         for step in (1, 2, 3):
             grad = torch.randn(n, generator=g) * (torch.rand(n, generator=g) > 0.5)
             gg = grad.to(DEV)
             if mode == 0:
                 oracle.adam_upd(p, grad, m, v, step, 0.9, 0.99, 0.1, 1e-8); ops.adam_upd(pg, gg, mg, vg, step, 0.9, 0.99, 0.1, 1e-8)
-                if refm: refm.adam_upd(pr, gg, mr, vr, step, 0.9, 0.99, 0.1, 1e-8)
+                refm.adam_upd(pr, gg, mr, vr, step, 0.9, 0.99, 0.1, 1e-8)
             elif mode == 1:
                 oracle.masked_adam_upd(p, grad, m, v, step, 0.9, 0.99, 0.1, 1e-8); ops.masked_adam_upd(pg, gg, mg, vg, step, 0.9, 0.99, 0.1, 1e-8)
-                if refm: refm.masked_adam_upd(pr, gg, mr, vr, step, 0.9, 0.99, 0.1, 1e-8)
+                refm.masked_adam_upd(pr, gg, mr, vr, step, 0.9, 0.99, 0.1, 1e-8)
             else:
                 oracle.adam_upd_with_perlr(p, grad, m, v, perlr, step, 0.9, 0.99, 0.1, 1e-8)
                 ops.adam_upd_with_perlr(pg, gg, mg, vg, lg, step, 0.9, 0.99, 0.1, 1e-8)
-                if refm: refm.adam_upd_with_perlr(pr, gg, mr, vr, lg, step, 0.9, 0.99, 0.1, 1e-8)
+                refm.adam_upd_with_perlr(pr, gg, mr, vr, lg, step, 0.9, 0.99, 0.1, 1e-8)
             assert_close(pg, p, what=f'adam mode {mode} p'); assert_close(mg, m, what='m'); assert_close(vg, v, what='v')
-            if refm:
-                assert_equal(pg, pr, f'adam mode {mode} p vs ref-cuda'); assert_equal(mg, mr, 'm vs ref-cuda'); assert_equal(vg, vr, 'v vs ref-cuda')
+            assert_equal(pg, pr, f'adam mode {mode} p vs ref-cuda'); assert_equal(mg, mr, 'm vs ref-cuda'); assert_equal(vg, vr, 'v vs ref-cuda')
 
 
 def test_masked_adam_golden_and_fused_tail(ops):

@@ -44,18 +44,49 @@ def shard_rays(rank, world, *tensors):
     return tuple(t[lo:hi] for t in tensors)
 
 
+class _MeanReduce:
+    """All-reduce that leaves the MEAN over ranks in the tensor.
+
+    Every loss term of the training step is a per-rank mean over that rank's rays (F.mse_loss, entropy_last .mean(), rgbper
+    / len(rays_o), TV weight / len(rays_o): run_train.py:254-287), so the gradient of the same loss on the concatenated
+    global batch of world x n rays is the mean -- not the sum -- of the per-rank gradients.  NCCL reduces with
+    ReduceOp.AVG (free); gloo has no AVG, so the sum is scaled after the wait."""
+
+    def __init__(self, tensor, async_op=True):
+        self.t = tensor
+        self.world = dist.get_world_size()
+        self.native = dist.get_backend() == 'nccl'
+        self.h = dist.all_reduce(tensor, op=dist.ReduceOp.AVG if self.native else dist.ReduceOp.SUM, async_op=async_op)
+
+    def wait(self):
+        if self.h is not None:
+            self.h.wait()
+            self.h = None
+        if not self.native:
+            self.t.mul_(1.0 / self.world)
+            self.native = True
+
+
+def _normalise_grad_layout(param):
+    """Make ``param.grad`` share the parameter's strides (channels-last grids keep channels-last gradients) so that TV, the
+    collectives and MaskedAdam all see one layout; autograd normally guarantees this, a torch-produced or accumulated
+    gradient may not."""
+    g = param.grad
+    if g is not None and g.stride() != param.stride():
+        param.grad = torch.empty_like(param, memory_format=torch.preserve_format).copy_(g)
+    return param.grad
+
+
 def allreduce_grads(params, world=None):
-    """Sum gradients across ranks in place (one collective per tensor, large grids first).  With identical replicas and
-    ray-sharded batches this reproduces the single-process gradient of the concatenated batch up to fp32 reassociation."""
+    """Average gradients across ranks in place (one collective per tensor, large grids first).  With identical replicas,
+    ray-sharded batches of equal size and per-rank mean losses this reproduces the single-process gradient of the same
+    loss on the concatenated batch up to fp32 reassociation (see _MeanReduce)."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return
     handles = []
     for p in sorted((p for p in params if p.grad is not None), key=lambda p: -p.numel()):
-        g = p.grad
-        if not g.is_contiguous() and g.dim() == 5:
-            # channels-last grids: reduce the dense storage in memory order (no copy)
-            g = g.permute(0, 2, 3, 4, 1)
-        handles.append(dist.all_reduce(g, op=dist.ReduceOp.SUM, async_op=True))
+        # channels-last grids: reduce the dense storage in memory order (no copy)
+        handles.append(_MeanReduce(_memory_order(_normalise_grad_layout(p))))
     for h in handles:
         h.wait()
 
@@ -68,15 +99,16 @@ def allreduce_grads_sparse(params, chunk=4096, dense_above=0.5):
       3. gather the union's chunks, all-reduce only those, scatter them back                  -- |union| * chunk floats
     falling back to the dense all-reduce when the union covers more than `dense_above` of the tensor (then the
     compaction would cost more than it saves; the synthetic bench rays touch nearly every chunk) or the tensor is
-    small.  Elements outside the union are zero on every rank, so the result equals the dense sum exactly, and
+    small.  Elements outside the union are zero on every rank, so the result equals the dense mean exactly, and
     MaskedAdam's "skip where the summed grad == 0" rule is unchanged.  One host read per large tensor (the union size).
     Returns {param: fraction of chunks exchanged} for the tensors that took the sparse route (1.0 = dense fallback)."""
     stats = {}
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return stats
     dense = []
+    world = dist.get_world_size()
     for p in sorted((p for p in params if p.grad is not None), key=lambda p: -p.numel()):
-        g = _memory_order(p.grad)
+        g = _memory_order(_normalise_grad_layout(p))
         n = g.numel()
         if n < 64 * chunk or not g.is_contiguous():
             dense.append(g)
@@ -95,12 +127,11 @@ def allreduce_grads_sparse(params, chunk=4096, dense_above=0.5):
         stats[p] = frac
         if idx.numel():
             buf = body.index_select(0, idx)
-            dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+            _MeanReduce(buf, async_op=False).wait()
             body.index_copy_(0, idx, buf)
         if n_full * chunk < n:                                       # ragged tail: always exchanged
-            tail = flat[n_full * chunk:]
-            dist.all_reduce(tail, op=dist.ReduceOp.SUM)
-    handles = [dist.all_reduce(g, op=dist.ReduceOp.SUM, async_op=True) for g in dense]
+            _MeanReduce(flat[n_full * chunk:], async_op=False).wait()
+    handles = [_MeanReduce(g) for g in dense]
     for h in handles:
         h.wait()
     return stats
@@ -115,7 +146,9 @@ def _memory_order(t):
 
 @torch.no_grad()
 def reduce_tv_step(opt, tv=None):
-    """Tail of a ray-sharded training step: gradient all-reduce -> total variation -> MaskedAdam, pipelined per slab.
+    """Tail of a ray-sharded training step: gradient all-reduce (mean over ranks) -> total variation -> MaskedAdam, pipelined
+    per slab.  The result equals the single-process step on the concatenated batch when the caller's TV weights use the GLOBAL
+    ray count (weight / (world * rays_per_rank), as run_train.py:283-287 would with the whole batch on one GPU).
 
     ``tv`` maps a grid parameter to ``(wx, wy, wz, dense_mode)`` (the arguments of ``total_variation_add_grad``).
     Single process: exactly ``total_variation_add_grad`` on every listed grid followed by ``opt.step()``.
@@ -134,7 +167,8 @@ def reduce_tv_step(opt, tv=None):
         for param in group['params']:
             if param.grad is None:
                 continue
-            if world > 1 and param.dim() == 5 and param.shape[0] > 1 and param.grad.stride() == param.stride():
+            _normalise_grad_layout(param)
+            if world > 1 and param.dim() == 5 and param.shape[0] > 1:
                 work.extend((group, param, slice(p, p + 1)) for p in range(param.shape[0]))
             else:
                 work.append((group, param, None))
@@ -143,7 +177,7 @@ def reduce_tv_step(opt, tv=None):
     if world > 1:
         for _, param, sl in work:
             g = param.grad if sl is None else param.grad[sl]
-            handles.append(dist.all_reduce(_memory_order(g), op=dist.ReduceOp.SUM, async_op=True))
+            handles.append(_MeanReduce(_memory_order(g)))
     states = {}
     for i, (group, param, sl) in enumerate(work):
         if handles:

@@ -150,7 +150,7 @@ def batch_indices_generator(N, BS):
         top += BS
 
 
-def gather_ray_batch(sel_i, *arrays):
+def gather_ray_batch(sel_i, *arrays, validate_device_indices=True):
     """run_train.py:204-212 in one launch: ``[a[sel_i] for a in arrays]`` for up to four [N,3] fp32 CUDA arrays."""
     if not 1 <= len(arrays) <= 4:
         raise ValueError('gather_ray_batch takes 1..4 arrays')
@@ -159,6 +159,13 @@ def gather_ray_batch(sel_i, *arrays):
         if not (a.is_cuda and a.dtype == torch.float32 and a.dim() == 2 and a.shape[1] == 3 and a.is_contiguous()
                 and a.shape[0] == a0.shape[0]):
             raise RuntimeError('arrays must be contiguous CUDA fp32 [N,3] tensors of the same length')
+    if not sel_i.is_cuda:
+        # validate where the indices already live (batch_indices_generator yields CPU LongTensors): no device round trip
+        if sel_i.numel() and (int(sel_i.min()) < 0 or int(sel_i.max()) >= a0.shape[0]):
+            raise IndexError('index out of range in gather_ray_batch')
+        check_device = False
+    else:
+        check_device = validate_device_indices
     sel = sel_i.to(device=a0.device, dtype=torch.int64, non_blocking=True).contiguous()
     n = sel.numel()
     outs = [torch.empty(n, 3, device=a0.device) for _ in arrays]
@@ -169,6 +176,8 @@ def gather_ray_batch(sel_i, *arrays):
     dst = (ctypes.c_void_p * len(arrays))(*[o.data_ptr() for o in outs])
     with _Guard(a0) as lib:
         check(lib.ubn_gather_rays(src, dst, len(arrays), ptr(sel), n, a0.shape[0], ptr(oob), stream_of(a0)))
-    if int(oob.item()):
+    # the kernel never reads out of range (an invalid index is skipped and raises the flag); reading the flag is a blocking
+    # host sync, so it is only done for device-resident indices and only when asked for
+    if check_device and int(oob.item()):
         raise IndexError('index out of range in gather_ray_batch')
     return outs

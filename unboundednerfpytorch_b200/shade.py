@@ -27,7 +27,9 @@ class _ShadeFn(torch.autograd.Function):
         M = feat.shape[0]
         dev = feat.device
         rgb = torch.empty(M, 3, dtype=torch.float32, device=dev)
-        need_grad = any(ctx.needs_input_grad)
+        # needs_input_grad mirrors requires_grad of the inputs even under torch.no_grad(): render / eval forwards must not
+        # allocate and stream the two [M,128] activation saves
+        need_grad = torch.is_grad_enabled() and any(ctx.needs_input_grad)
         h1 = torch.empty(M, 128, dtype=torch.float32, device=dev) if need_grad else None
         h2 = torch.empty(M, 128, dtype=torch.float32, device=dev) if need_grad else None
         with ops._Guard(feat) as lib:
