@@ -32,7 +32,7 @@ extern "C" {
 #pragma GCC visibility push(default)
 #endif
 
-#define UBN_ABI_VERSION 1
+#define UBN_ABI_VERSION 2
 
 /* ---- library introspection ------------------------------------------------------------------ */
 int ubn_abi_version(void);
@@ -177,21 +177,26 @@ int ubn_gather_rays(const float* const* src, float* const* dst, int n_arrays, co
                     int64_t n_src, int* oob_flag, void* stream);
 
 /* ---- in-kernel training losses ------------------------------------------------
- * FourierGrid/run_train.py:254-279: loss = w_main * F.mse_loss(rgb_marched, target)
- *   + w_entropy * entropy_last(alphainv_last.clamp(1e-6, 1-1e-6)) + w_rgbper * sum_m weights_m |raw_rgb_m - target[ray_id_m]|^2 / n_rays
- * and d loss / d {rgb_marched [n_rays,3], alphainv_last [n_rays], raw_rgb [n_pts,3]} (weights detached, :277) in two
- * launches.  out4 = {loss, mse, entropy_last, rgbper} (device).  alphainv_last / raw_rgb may be NULL (term off; their
- * gradient buffers are then not written).  scratch: >= 1776 doubles of device memory (per-block partials, summed in a
- * fixed order: the loss value is deterministic). */
+ * FourierGrid/run_train.py:253-279: loss = w_main * F.mse_loss(rgb_marched, target)
+ *   + w_freq * FourierMSELoss(rgb_marched, target)            (FourierGrid_model.py:114-130; real part of the colour-axis FFT, :255-257)
+ *   + w_entropy * entropy_last(alphainv_last.clamp(1e-6, 1-1e-6))                                                        (:258-261)
+ *   + w_nearclip * sum_{t_m < near_thres} (density_m - density_m.detach())   (value 0, gradient w_nearclip on raw_density,  :262-268)
+ *   + w_rgbper * sum_m weights_m |raw_rgb_m - target[ray_id_m]|^2 / n_rays                               (weights detached, :275-278)
+ * and d loss / d {rgb_marched [n_rays,3], alphainv_last [n_rays], raw_rgb [n_pts,3], raw_density [n_pts]} in two launches.
+ * out5 = {loss, mse, entropy_last, rgbper, freq} (device).  alphainv_last / raw_rgb / t_pts may be NULL (term off; their gradient
+ * buffers are then not written).  t_pts: the per-sample ray parameter ret_dict['t'] [n_pts].  scratch: >= 2368 doubles of device
+ * memory (per-block partials, summed in a fixed order: the loss value is deterministic). */
 int ubn_render_loss(const float* rgb_marched, const float* alphainv_last, const float* raw_rgb, const float* weights,
-                    const int64_t* ray_id, const float* target, int64_t n_rays, int64_t n_pts, float w_main,
-                    float w_entropy, float w_rgbper, float* out4, float* grad_rgb_marched, float* grad_alphainv_last,
-                    float* grad_raw_rgb, double* scratch, int64_t scratch_len, void* stream);
+                    const int64_t* ray_id, const float* target, const float* t_pts, int64_t n_rays, int64_t n_pts,
+                    float w_main, float w_entropy, float w_rgbper, float w_freq, float w_nearclip, float near_thres,
+                    float* out5, float* grad_rgb_marched, float* grad_alphainv_last, float* grad_raw_rgb,
+                    float* grad_raw_density, double* scratch, int64_t scratch_len, void* stream);
 
 /* Distortion loss, torch_efficient_distloss.flatten_eff_distloss(w, s, interval, ray_id) as called at run_train.py:268-274
  * (maths in-tree at dcvgo.py:387-409): out1[0] = (1/R) sum_rays [ sum_i interval/3 w_i^2 + 2 sum_i w_i (s_i W_<i - WS_<i) ]
- * with R = n_rays (the caller passes ray_id.max()+1 like the library) and grad_w = d out / d w (NULL = value only).
- * ray_id sorted; i_start / i_end: int64[n_rays] scratch; scratch: >= n_rays doubles.  Deterministic. */
+ * with R = ray_id.max() + 1 like the library (read on the device from the last element of the sorted ray_id: no host sync) and
+ * grad_w = d out / d w (NULL = value only).  n_rays: any upper bound of R (the batch size) -- it only sizes the per-ray arrays;
+ * ray_id sorted, n_pts >= 1; i_start / i_end: int64[n_rays] scratch; scratch: >= n_rays doubles.  Deterministic. */
 int ubn_distortion_loss(const float* w, const float* s, const int64_t* ray_id, int64_t n_pts, int64_t n_rays,
                         float interval, int64_t* i_start, int64_t* i_end, float* out1, float* grad_w, double* scratch,
                         int64_t scratch_len, void* stream);

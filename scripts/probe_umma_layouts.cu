@@ -7,6 +7,9 @@
 //                2 = MN-major, no swizzle, LBO / SBO fields swapped
 //                3 = MN-major, 128-byte swizzle, CUTLASS form                (LBO field = 32-element MN-group stride, SBO field = 8-K-group stride)
 //                4 = MN-major, 128-byte swizzle, LBO / SBO fields swapped
+//                5 = MN-major, SWIZZLE_128B_BASE32B (layout type 1: the only MN-major form CUTLASS builds for 32-bit operands), CUTLASS form
+//                6 = same, LBO / SBO fields swapped
+//                7 = K-major, no swizzle, K-panel stride (LBO) padded by 16 bytes (bank-conflict-free transposing 4-byte stores)
 // A source: 0 = shared memory (SS form), 1 = tensor memory (TS form; A is then always "row = lane", layout code ignored).
 //
 //   nvcc -std=c++17 -O2 -gencode arch=compute_100a,code=sm_100a scripts/probe_umma_layouts.cu -o scripts/bin/probe_umma_layouts
@@ -17,13 +20,20 @@
 #include <cuda_runtime.h>
 
 constexpr int kM = 128, kN = 128, kK = 32;
-constexpr uint32_t kOpBytes = kM * kK * 4;      // 16 KB per operand
+constexpr uint32_t kOpBytes = 20 * 1024;        // >= 16 KB per operand (+ room for the padded-LBO variant), keeps 1024-byte alignment
 
 __host__ __device__ inline uint32_t elem_offset(int layout, int r, int k) {
   if (layout == 0) return (uint32_t)(k >> 2) * 2048u + (uint32_t)r * 16u + (uint32_t)(k & 3) * 4u;
   if (layout == 1 || layout == 2) return (uint32_t)(r >> 2) * 128u + (uint32_t)(r & 3) * 4u + (uint32_t)(k & 7) * 16u + (uint32_t)(k >> 3) * 4096u;
-  uint32_t off = (uint32_t)(r >> 5) * 4096u + (uint32_t)(k >> 3) * 1024u + (uint32_t)(k & 7) * 128u + (uint32_t)(r & 31) * 4u;
-  return off ^ (((off >> 7) & 7u) << 4);
+  if (layout == 3 || layout == 4) {
+    uint32_t off = (uint32_t)(r >> 5) * 4096u + (uint32_t)(k >> 3) * 1024u + (uint32_t)(k & 7) * 128u + (uint32_t)(r & 31) * 4u;
+    return off ^ (((off >> 7) & 7u) << 4);
+  }
+  if (layout == 5 || layout == 6) {   // MN-major SWIZZLE_128B_BASE32B: 32 MN x 4 K atoms (512 B), byte bits [2,4) ^= bits [4,6)
+    uint32_t off = (uint32_t)(r >> 5) * 4096u + (uint32_t)(k >> 2) * 512u + (uint32_t)(k & 3) * 128u + (uint32_t)(r & 31) * 4u;
+    return off ^ (((off >> 4) & 3u) << 2);
+  }
+  return (uint32_t)(k >> 2) * 2064u + (uint32_t)r * 16u + (uint32_t)(k & 3) * 4u;    // 7: K-major, K-panel stride padded by 16 B
 }
 
 __device__ inline uint64_t make_desc(int layout, uint32_t smem_addr) {
@@ -34,7 +44,10 @@ __device__ inline uint64_t make_desc(int layout, uint32_t smem_addr) {
     case 1: lbo = 4096; sbo = 128; break;
     case 2: lbo = 128; sbo = 4096; break;
     case 3: lbo = 4096; sbo = 1024; type = 2; break;
-    default: lbo = 1024; sbo = 4096; type = 2; break;
+    case 4: lbo = 1024; sbo = 4096; type = 2; break;
+    case 5: lbo = 4096; sbo = 512; type = 1; break;
+    case 6: lbo = 512; sbo = 4096; type = 1; break;
+    default: lbo = 2064; sbo = 128; break;
   }
   return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46) | (type << 61);
 }
@@ -42,7 +55,9 @@ __device__ inline uint64_t make_desc(int layout, uint32_t smem_addr) {
 __device__ inline uint32_t k_step_bytes(int layout) {       // start-address advance per K = 8 step
   if (layout == 0) return 4096;
   if (layout == 1 || layout == 2) return 4096;
-  return 1024;
+  if (layout == 3 || layout == 4) return 1024;
+  if (layout == 5 || layout == 6) return 1024;     // two 4-K atoms
+  return 2 * 2064;
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -93,7 +108,7 @@ __global__ void __launch_bounds__(128, 1) k_probe(const float* __restrict__ A, c
   }
   if (tid == 0) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((la != 0 && !a_tmem) ? (1u << 15) : 0u) | ((lb != 0) ? (1u << 16) : 0u) |
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((la != 0 && la != 7 && !a_tmem) ? (1u << 15) : 0u) | ((lb != 0 && lb != 7) ? (1u << 16) : 0u) |
                            ((uint32_t)(kN >> 3) << 17) | ((uint32_t)(kM >> 4) << 24);
     for (int ks = 0; ks < kK / 8; ++ks) {
       const uint64_t db = make_desc(lb, smem_u32(sB) + ks * k_step_bytes(lb));
@@ -156,10 +171,11 @@ int main(int argc, char** argv) {
   cudaMemcpy(dB, hB, sizeof(hB), cudaMemcpyHostToDevice);
   const int smem = 2 * kOpBytes + 64;
   cudaFuncSetAttribute(k_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  const char* names[5] = {"K-major/none", "MN/none/cutlass", "MN/none/swapped", "MN/sw128/cutlass", "MN/sw128/swapped"};
+  const char* names[8] = {"K-major/none", "MN/none/cutlass", "MN/none/swapped", "MN/sw128/cutlass", "MN/sw128/swapped",
+                          "MN/sw128_base32b/cutlass", "MN/sw128_base32b/swapped", "K-major/none/padded-LBO"};
   for (int a_tmem = 0; a_tmem < 2; ++a_tmem)
-    for (int la = 0; la < (a_tmem ? 1 : 5); ++la)
-      for (int lb = 0; lb < 5; ++lb) {
+    for (int la = 0; la < (a_tmem ? 1 : 8); ++la)
+      for (int lb = 0; lb < 8; ++lb) {
         if (only && (a_tmem != o_t || la != o_a || lb != o_b)) continue;
         cudaMemset(dD, 0xff, sizeof(hD));
         k_probe<<<1, 128, smem>>>(dA, dB, la, lb, a_tmem, dD);

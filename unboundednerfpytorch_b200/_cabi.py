@@ -34,6 +34,7 @@ class UbnMarchCfg(ctypes.Structure):
                 ('use_maskcache', c_i32), ('mask_sz', c_i32 * 3), ('mask_scale', c_f * 3), ('mask_shift', c_f * 3)]
 
 
+ABI_VERSION = 2          # UBN_ABI_VERSION of include/ubnerf_b200.h this binding was written against
 FLAG_QUERIED, FLAG_LISTED, FLAG_SCANNED, FLAG_KEEP, FLAG_INNER = 1, 2, 4, 8, 16
 
 # name -> argtypes (all functions return int unless listed in _RESTYPE)
@@ -72,7 +73,7 @@ _SIGNATURES = {
     'ubn_composite_fwd': [c_p, c_p, c_p, c_i64, c_i64, c_p, c_p, c_p, c_p],
     'ubn_composite_bwd': [c_p, c_p, c_p, c_p, c_i64, c_p, c_p, c_p],
     'ubn_distortion_loss': [c_p, c_p, c_p, c_i64, c_i64, c_f, c_p, c_p, c_p, c_p, c_p, c_i64, c_p],
-    'ubn_render_loss': [c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_i64, c_f, c_f, c_f, c_p, c_p, c_p, c_p, c_p, c_i64, c_p],
+    'ubn_render_loss': [c_p] * 7 + [c_i64, c_i64] + [c_f] * 6 + [c_p] * 6 + [c_i64, c_p],
     'ubn_grid_sample_fwd': [c_p, ctypes.POINTER(UbnGridDesc), c_p, c_i64, c_p, c_p],
     'ubn_grid_sample_bwd': [c_p, ctypes.POINTER(UbnGridDesc), c_p, c_i64, c_p, c_p],
     'ubn_march_density_fwd': [c_p, c_p, c_p, c_p, ctypes.POINTER(UbnGridDesc), c_p, ctypes.POINTER(UbnMarchCfg), c_i64,
@@ -110,7 +111,7 @@ def load():
         fn = getattr(lib, name)
         fn.argtypes = argtypes
         fn.restype = _RESTYPE.get(name, c_int)
-    if lib.ubn_abi_version() != 1:
+    if lib.ubn_abi_version() != ABI_VERSION:
         raise RuntimeError('libubnerf_b200.so ABI version mismatch')
     _lib = lib
     return lib

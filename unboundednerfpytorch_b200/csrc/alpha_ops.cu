@@ -429,9 +429,10 @@ __device__ __forceinline__ float warp_incl_scan(float v, int lane) {
 
 __global__ void __launch_bounds__(128) k_distortion_loss(const float* __restrict__ w, const float* __restrict__ s,
                                                          const int64_t* __restrict__ i_start, const int64_t* __restrict__ i_end,
-                                                         int64_t n_rays, float interval, float inv_r,
+                                                         int64_t n_rays, float interval, const int64_t* __restrict__ last_id,
                                                          float* __restrict__ grad_w, double* __restrict__ ray_loss) {
   const int lane = threadIdx.x & 31;
+  const float inv_r = 1.f / (float)(*last_id + 1);     // R = ray_id.max() + 1 = id of the last (sorted) sample + 1, like the library
   const int64_t ray = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
   if (ray >= n_rays) return;
   const int64_t b = i_start[ray], e = i_end[ray];
@@ -468,9 +469,10 @@ __global__ void __launch_bounds__(128) k_distortion_loss(const float* __restrict
   }
 }
 
-__global__ void __launch_bounds__(256) k_distortion_finish(const double* __restrict__ ray_loss, int64_t n_rays, float inv_r,
-                                                           float* __restrict__ out) {
+__global__ void __launch_bounds__(256) k_distortion_finish(const double* __restrict__ ray_loss, int64_t n_rays,
+                                                           const int64_t* __restrict__ last_id, float* __restrict__ out) {
   __shared__ double sh[256];
+  const float inv_r = 1.f / (float)(*last_id + 1);
   double a = 0;
   for (int64_t r = threadIdx.x; r < n_rays; r += 256) a += ray_loss[r];   // fixed assignment -> deterministic
   sh[threadIdx.x] = a;
@@ -499,10 +501,11 @@ extern "C" int ubn_distortion_loss(const float* w, const float* s, const int64_t
     k_segment_bounds<<<blocks_for(n_pts, 256), 256, 0, st>>>(ray_id, n_pts, i_start, i_end);
     UBN_LAUNCH_CHECK();
   }
-  const float inv_r = 1.f / (float)n_rays;
-  k_distortion_loss<<<blocks_for(n_rays, 4), 128, 0, st>>>(w, s, i_start, i_end, n_rays, interval, inv_r, grad_w, scratch);
+  if (n_pts <= 0) return finish(cudaErrorInvalidValue);
+  const int64_t* last_id = ray_id + (n_pts - 1);      // read on the device: no host sync for R
+  k_distortion_loss<<<blocks_for(n_rays, 4), 128, 0, st>>>(w, s, i_start, i_end, n_rays, interval, last_id, grad_w, scratch);
   UBN_LAUNCH_CHECK();
-  k_distortion_finish<<<1, 256, 0, st>>>(scratch, n_rays, inv_r, out1);
+  k_distortion_finish<<<1, 256, 0, st>>>(scratch, n_rays, last_id, out1);
   UBN_LAUNCH_CHECK();
   return 0;
 }

@@ -171,12 +171,14 @@ def segment_coo(src, index, out, reduce='sum'):
 # in-kernel training losses (run_train.py:254-279): MSE + entropy_last + per-point rgb loss
 # --------------------------------------------------------------------------------------------------
 class RenderLoss(torch.autograd.Function):
-    """loss = w_main * mse(rgb_marched, target) + w_entropy * entropy_last(alphainv_last) + w_rgbper * rgbper, value and
-    gradients from two launches (ubn_render_loss).  Returns a [4] tensor {loss, mse, entropy_last, rgbper}; only element 0
-    carries gradient (the other three are the detached terms the training loop logs, e.g. psnr = mse2psnr(out[1]))."""
+    """loss = w_main * mse(rgb_marched, target) + w_freq * FourierMSE(rgb_marched, target) + w_entropy * entropy_last(alphainv_last)
+    + w_nearclip * nearclip(raw_density, t) + w_rgbper * rgbper, value and gradients from two launches (ubn_render_loss).
+    Returns a [5] tensor {loss, mse, entropy_last, rgbper, freq}; only element 0 carries gradient (the others are the detached
+    terms the training loop logs, e.g. psnr = mse2psnr(out[1]))."""
 
     @staticmethod
-    def forward(ctx, rgb_marched, alphainv_last, raw_rgb, weights, ray_id, target, w_main, w_entropy, w_rgbper):
+    def forward(ctx, rgb_marched, alphainv_last, raw_rgb, weights, ray_id, target, raw_density, t_pts, w_main, w_entropy, w_rgbper,
+                w_freq, w_nearclip, near_thres):
         from ._cabi import c_f, c_i64, check, ptr, stream_of
         dev = rgb_marched.device
         for t, nm in ((rgb_marched, 'rgb_marched'), (target, 'target')):
@@ -185,42 +187,62 @@ class RenderLoss(torch.autograd.Function):
         n_rays = rgb_marched.shape[0]
         use_ent = alphainv_last is not None and w_entropy != 0
         use_per = raw_rgb is not None and w_rgbper != 0 and raw_rgb.shape[0] > 0
+        use_clip = raw_density is not None and t_pts is not None and w_nearclip != 0 and raw_density.numel() > 0
         if use_ent:
             alphainv_last = alphainv_last.contiguous()
         if use_per:
             raw_rgb, weights, ray_id = raw_rgb.contiguous(), weights.detach().contiguous(), ray_id.contiguous()
-        n_pts = raw_rgb.shape[0] if use_per else 0
-        scratch = torch.empty(3 * 1024, dtype=torch.float64, device=dev)   # per call: safe under concurrent streams
-        out = torch.empty(4, device=dev)
+        if use_clip:
+            t_pts = t_pts.contiguous()
+        n_pts = raw_rgb.shape[0] if use_per else (raw_density.numel() if use_clip else 0)
+        scratch = torch.empty(4 * 1024, dtype=torch.float64, device=dev)   # per call: safe under concurrent streams
+        out = torch.empty(5, device=dev)
         g_rgb = torch.empty_like(rgb_marched)
         g_last = torch.empty_like(alphainv_last) if use_ent else None
         g_raw = torch.empty_like(raw_rgb) if use_per else None
+        g_dens = torch.empty(raw_density.shape, dtype=torch.float32, device=dev) if use_clip else None
         with ops._Guard(rgb_marched) as lib:
             check(lib.ubn_render_loss(ptr(rgb_marched), ptr(alphainv_last if use_ent else None), ptr(raw_rgb if use_per else None),
                                       ptr(weights if use_per else None), ptr(ray_id if use_per else None), ptr(target),
-                                      c_i64(n_rays), c_i64(n_pts), c_f(float(w_main)), c_f(float(w_entropy)),
-                                      c_f(float(w_rgbper)), ptr(out), ptr(g_rgb), ptr(g_last), ptr(g_raw), ptr(scratch),
+                                      ptr(t_pts if use_clip else None), c_i64(n_rays), c_i64(n_pts), c_f(float(w_main)),
+                                      c_f(float(w_entropy)), c_f(float(w_rgbper)), c_f(float(w_freq)),
+                                      c_f(float(w_nearclip) if use_clip else 0.0), c_f(float(near_thres) if use_clip else 0.0),
+                                      ptr(out), ptr(g_rgb), ptr(g_last), ptr(g_raw), ptr(g_dens), ptr(scratch),
                                       c_i64(scratch.numel()), stream_of(rgb_marched)))
-        ctx.save_for_backward(g_rgb, g_last, g_raw)
+        ctx.save_for_backward(g_rgb, g_last, g_raw, g_dens)
         return out
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, grad_out):
-        g_rgb, g_last, g_raw = ctx.saved_tensors
+        g_rgb, g_last, g_raw, g_dens = ctx.saved_tensors
         s = grad_out[0]
-        return (g_rgb * s, None if g_last is None else g_last * s, None if g_raw is None else g_raw * s,
-                None, None, None, None, None, None)
+        sc = lambda g: None if g is None else g * s
+        return (sc(g_rgb), sc(g_last), sc(g_raw), None, None, None, sc(g_dens), None, None, None, None, None, None, None)
 
 
-def render_loss(render_result, target, weight_main=1.0, weight_entropy_last=0.0, weight_rgbper=0.0):
-    """The always-on loss terms of the reference training loop (run_train.py:254-279) from a model ``ret_dict``.
-    Returns (loss, {'mse', 'entropy_last', 'rgbper'}) -- loss is differentiable, the terms are detached scalars."""
+def render_loss(render_result, target, weight_main=1.0, weight_entropy_last=0.0, weight_rgbper=0.0, weight_freq=0.0,
+                weight_nearclip=0.0, near_thres=None, weight_distortion=0.0):
+    """The loss terms of the reference training loop (run_train.py:253-279) from a model ``ret_dict``:
+    main (mse) + freq (FourierMSELoss) + entropy_last + nearclip + rgbper in two launches, + distortion (flatten_eff_distloss,
+    one warp-per-ray kernel) when ``weight_distortion`` > 0.  ``near_thres`` = data_dict['near_clip'] / model.scene_radius[0]
+    (run_train.py:263).  Returns (loss, {'mse', 'entropy_last', 'rgbper', 'freq', 'distortion'}) -- loss is differentiable, the
+    terms are detached scalars."""
+    clip = weight_nearclip > 0 and near_thres is not None
     out = RenderLoss.apply(render_result['rgb_marched'], render_result.get('alphainv_last'), render_result.get('raw_rgb'),
                            render_result.get('weights'), render_result.get('ray_id'), target.contiguous(),
-                           weight_main, weight_entropy_last, weight_rgbper)
+                           render_result.get('raw_density') if clip else None, render_result.get('t') if clip else None,
+                           weight_main, weight_entropy_last, weight_rgbper, weight_freq, weight_nearclip if clip else 0.0,
+                           near_thres if clip else 0.0)
     d = out.detach()
-    return out[0], {'mse': d[1], 'entropy_last': d[2], 'rgbper': d[3]}
+    loss = out[0]
+    terms = {'mse': d[1], 'entropy_last': d[2], 'rgbper': d[3], 'freq': d[4]}
+    if weight_distortion > 0:
+        dl = flatten_eff_distloss(render_result['weights'], render_result['s'], 1 / render_result['n_max'], render_result['ray_id'],
+                                  n_rays=render_result['rgb_marched'].shape[0])
+        loss = loss + weight_distortion * dl
+        terms['distortion'] = dl.detach()
+    return loss, terms
 
 
 # --------------------------------------------------------------------------------------------------
@@ -253,10 +275,12 @@ class DistortionLoss(torch.autograd.Function):
         return gw * g, None, None, None, None
 
 
-def flatten_eff_distloss(w, s, interval, ray_id):
-    """Same call as torch_efficient_distloss.flatten_eff_distloss (run_train.py:273): mean over max(ray_id)+1 rays.
-    One host read (the ray count) unless ``ray_id`` is empty."""
+def flatten_eff_distloss(w, s, interval, ray_id, n_rays=None):
+    """Same call as torch_efficient_distloss.flatten_eff_distloss (run_train.py:273): mean over ray_id.max()+1 rays (the kernel
+    reads that count on the device).  ``n_rays``: an upper bound of it (the batch size) used only to size the per-ray scratch;
+    without it one host read of ray_id[-1] supplies the bound."""
     if w.numel() == 0:
         return w.sum() * 0
-    n_rays = int(ray_id[-1]) + 1                      # sorted ids: the last one is the maximum
+    if n_rays is None:
+        n_rays = int(ray_id[-1]) + 1                  # sorted ids: the last one is the maximum
     return DistortionLoss.apply(w, s, interval, ray_id, n_rays)

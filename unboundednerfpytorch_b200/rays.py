@@ -161,7 +161,7 @@ def gather_ray_batch(sel_i, *arrays, validate_device_indices=True):
             raise RuntimeError('arrays must be contiguous CUDA fp32 [N,3] tensors of the same length')
     if not sel_i.is_cuda:
         # validate where the indices already live (batch_indices_generator yields CPU LongTensors): no device round trip
-        if sel_i.numel() and (int(sel_i.min()) < 0 or int(sel_i.max()) >= a0.shape[0]):
+        if sel_i.numel() and (int(sel_i.min()) < -a0.shape[0] or int(sel_i.max()) >= a0.shape[0]):   # negatives wrap like Python
             raise IndexError('index out of range in gather_ray_batch')
         check_device = False
     else:

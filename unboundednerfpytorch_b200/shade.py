@@ -21,15 +21,16 @@ BWD_MODE = os.environ.get('UBN_RGBNET_BWD_MODE', 'tc3')
 
 class _ShadeFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, feat, vb, ray_id, W1k, W2, b2, W3, b3):
+    def forward(ctx, feat, vb, ray_id, W1k, W2, b2, W3, b3, need_grad):
         feat, vb, ray_id = feat.contiguous(), vb.contiguous(), ray_id.contiguous()
         W1k, W2, b2, W3, b3 = (t.contiguous() for t in (W1k, W2, b2, W3, b3))
         M = feat.shape[0]
         dev = feat.device
         rgb = torch.empty(M, 3, dtype=torch.float32, device=dev)
-        # needs_input_grad mirrors requires_grad of the inputs even under torch.no_grad(): render / eval forwards must not
-        # allocate and stream the two [M,128] activation saves
-        need_grad = torch.is_grad_enabled() and any(ctx.needs_input_grad)
+        # need_grad comes from the caller (shade()): inside Function.forward grad mode is always off, and needs_input_grad
+        # mirrors requires_grad of the inputs even under torch.no_grad() -- render / eval forwards must not allocate and stream
+        # the two [M,128] activation saves
+        need_grad = bool(need_grad) and any(ctx.needs_input_grad)
         h1 = torch.empty(M, 128, dtype=torch.float32, device=dev) if need_grad else None
         h2 = torch.empty(M, 128, dtype=torch.float32, device=dev) if need_grad else None
         with ops._Guard(feat) as lib:
@@ -66,12 +67,12 @@ class _ShadeFn(torch.autograd.Function):
                     check(lib.ubn_rgbnet_bwd_small(ptr(feat), ptr(ray_id), ptr(W1k), ptr(W3), ptr(rgb), ptr(h2), ptr(g_rgb),
                                                    ptr(dz1), c_i64(M), ptr(g_feat), ptr(g_vb), ptr(gW1k), ptr(gb2), ptr(gW3),
                                                    ptr(gb3), stream_of(feat)))
-                return g_feat, g_vb, None, gW1k, gW2, gb2, gW3, gb3
+                return g_feat, g_vb, None, gW1k, gW2, gb2, gW3, gb3, None
             with _cabi.timed('rgbnet_bwd'):
                 check(lib.ubn_rgbnet_bwd(ptr(feat), ptr(ray_id), ptr(W1k), ptr(W2), ptr(W3), ptr(rgb), ptr(h1), ptr(h2),
                                          ptr(g_rgb), c_i64(M), ptr(g_feat), ptr(g_vb), ptr(gW1k), ptr(gW2), ptr(gb2),
                                          ptr(gW3), ptr(gb3), stream_of(feat)))
-        return g_feat, g_vb, None, gW1k, gW2, gb2, gW3, gb3
+        return g_feat, g_vb, None, gW1k, gW2, gb2, gW3, gb3, None
 
 
 def supported(rgbnet, k0_dim):
@@ -89,4 +90,4 @@ def shade(rgbnet, k0, view_emb, ray_id):
     l1, l2, l3 = rgbnet[0], rgbnet[2][0], rgbnet[3]
     kd = k0.shape[1]
     vb = torch.addmm(l1.bias, view_emb, l1.weight[:, kd:].t())
-    return _ShadeFn.apply(k0, vb, ray_id, l1.weight[:, :kd], l2.weight, l2.bias, l3.weight, l3.bias)
+    return _ShadeFn.apply(k0, vb, ray_id, l1.weight[:, :kd], l2.weight, l2.bias, l3.weight, l3.bias, torch.is_grad_enabled())
