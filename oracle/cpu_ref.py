@@ -441,7 +441,7 @@ _fn_cache = {}
 
 
 def model_forward(flavor, p, rays_o, rays_d, viewdirs, stepsize, bg=1, rand_bkgd=False, is_train=False,
-                  render_depth=True, ext=None):
+                  render_depth=True, ext=None, keep_intermediates=False):
     """CPU restatement of FourierGridModel.forward (flavor='fouriergrid', FourierGrid_model.py:554-672) and
     DirectContractedVoxGO.forward (flavor='dcvgo', dcvgo.py:264-384).
 
@@ -522,6 +522,8 @@ def model_forward(flavor, p, rays_o, rays_d, viewdirs, stepsize, bg=1, rand_bkgd
     if render_depth:
         with torch.no_grad():
             ret['depth'] = torch.zeros(N, device=dev).index_add_(0, ray_id, weights * s)
+    if keep_intermediates:      # for the fp64 re-evaluation of the colour branch in tests/parity_at_size.py
+        ret['_ray_pts'], ret['_k0'] = ray_pts.detach(), k0.detach()
     return ret
 
 

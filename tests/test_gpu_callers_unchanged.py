@@ -137,10 +137,29 @@ def test_unmodified_reference_callers_run_on_this_library(ref_modules, flavor):
             loss.backward()
             m.density_total_variation_add_grad(1e-6 / N, True)
             m.k0_total_variation_add_grad(1e-7 / N, True)
-            opt.step()
+        # gradients (incl. the TV term) before the optimiser.  density.grid does not pass through the ReLU MLP: tight.  k0.grid and
+        # the rgbnet do: a pre-activation within fp32 rounding of zero flips its ReLU mask between cuBLAS (reference) and the
+        # tcgen05 kernels (ours), which changes that sample's contribution (tests/parity_at_size.py quantifies this against fp64)
+        ref_sd, ours_named = dict(ref.named_parameters()), dict(ours.named_parameters())
+        assert _stat(ours_named['density.grid'].grad, ref_sd['density.grid'].grad) <= 2e-5
+        gk, gr = ours_named['k0.grid'].grad, ref_sd['k0.grid'].grad
+        beyond = ((gk - gr).abs() > 1e-5 * gr.abs().max()).float().mean().item()
+        assert beyond <= 1e-3, f'{flavor} k0.grid grad: {beyond:.2e} of the elements beyond 1e-5 of scale'
+        for k, v in ours_named.items():
+            if k.startswith('rgbnet'):
+                assert _stat(v.grad, ref_sd[k].grad) <= 5e-4, f'{flavor} grad {k}'
+        # the optimiser step itself: the reference's unmodified MaskedAdam (over legacy adam_upd_cuda) and this library's
+        # MaskedAdam must agree BIT FOR BIT when fed the same gradients (Adam's m / (sqrt(v) + eps) ~ sign(g) at step 1 would
+        # otherwise turn a last-bit gradient difference into a 2 lr parameter difference)
+        from unboundednerfpytorch_b200 import grid as G
+        for k, v in ours_named.items():
+            if v.grad is not None:
+                g = ref_sd[k].grad.detach().clone()
+                v.grad = G._as_cl3d(g) if g.dim() == 5 else g
+        opt_ref.step()
+        opt_ours.step()
         for k, v in ours.state_dict().items():
             if k in ('density.grid', 'k0.grid') or k.startswith('rgbnet'):
-                e = _stat(v, ref.state_dict()[k])
-                assert e <= 1e-5, f'{flavor} parameter {k} after one step: {e:.2e} of scale'
+                assert torch.equal(v, ref.state_dict()[k]), f'{flavor} parameter {k} after MaskedAdam.step differs'
     finally:
         _default_cuda(False)
