@@ -18,7 +18,7 @@ the same step: torch F.grid_sample CPU path + C restatement of the CUDA-only ops
 thread count that is fastest for it.  `psnr_delta_vs_ref` = second half of the metric (oracle/psnr_check.py).
 `--impl reference-gpu` (informative, not part of the driver contract) = the reference's GPU path on this B200: its
 algorithm op by op with its own CUDA extension from oracle/_ref + ATen / cuBLAS.
-A/B switches (env): UBN_BENCH_TAIL=pipelined|sequential (multi-GPU tail), UBN_BENCH_LOSS=fused|torch,
+A/B switches (env): UBN_BENCH_TAIL=peer|pipelined|sequential (training-step tail), UBN_BENCH_LOSS=fused|torch,
 UBN_TV_IMPL=1|0 (streaming / element-per-thread TV), UBN_DENSITY_RED_PAIRS=1|0, UBN_FEATURE_IMPL, UBN_RGBNET_MODE,
 UBN_RGBNET_BWD_MODE, UBN_NCCL_HIGH_PRIORITY=1|0.
 """
@@ -360,7 +360,12 @@ def main():
     opt = create_optimizer_or_freeze_model(model, cfg_train, global_step=0)
     rk = dict(near=0., far=1e9, bg=1, rand_bkgd=False, stepsize=stepsize)
     params = [p for p in model.parameters() if p.requires_grad]
-    tv_terms = model.tv_terms(1e-6 / N_RAYS, 1e-7 / N_RAYS, True)
+    # TV weight / (global ray count): with the mean-over-ranks gradient exchange the N-GPU step equals the 1-GPU step on the
+    # concatenated batch of world x 8192 rays (run_train.py:283-287 divides by len(rays_o))
+    n_global = N_RAYS * world
+    tv_terms = model.tv_terms(1e-6 / n_global, 1e-7 / n_global, True)
+    tail_mode = os.environ.get('UBN_BENCH_TAIL', 'peer')
+    peer_tail = ubdist.PeerTail(opt) if tail_mode == 'peer' else None
 
     # every rank gets its own 8192-ray batch (weak scaling); host copies are pinned for the e2e leg
     host = [t.pin_memory() for t in synth_batch(N_RAYS, SEED + rank)]
@@ -378,16 +383,17 @@ def main():
         loss.backward()
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
         ev[0].record()
-        # all-reduce (N > 1) -> dense TV -> MaskedAdam; per slab, so the sweeps of slab p overlap the transfer of slab p+1
-        if os.environ.get('UBN_BENCH_TAIL', 'pipelined') == 'pingpong' and world == 1:   # single-sweep TV + Adam (WIP)
+        if peer_tail is not None:         # default: ONE sweep per grid over NVLink peer memory (reduce-scatter -> TV -> Adam -> all-gather)
+            peer_tail.step(tv_terms)
+        elif tail_mode == 'pingpong' and world == 1:      # A/B: single-sweep TV + Adam without the persistent gradient buffers
             opt.step_fused_tv(tv_terms, write_grad=False)
-        elif os.environ.get('UBN_BENCH_TAIL', 'pipelined') == 'sequential':     # A/B switch: whole-tensor all-reduce first
+        elif tail_mode == 'sequential':   # A/B: whole-tensor all-reduce first, then the two sweeps
             if world > 1:
                 ubdist.allreduce_grads(params)
-            model.density_total_variation_add_grad(1e-6 / N_RAYS, True)
-            model.k0_total_variation_add_grad(1e-7 / N_RAYS, True)
+            model.density_total_variation_add_grad(1e-6 / n_global, True)
+            model.k0_total_variation_add_grad(1e-7 / n_global, True)
             opt.step()
-        else:
+        else:                             # A/B: slab-pipelined NCCL all-reduce || TV || Adam
             ubdist.reduce_tv_step(opt, tv_terms)
         ev[1].record()
         tail_events.append(ev)
@@ -502,7 +508,7 @@ def main():
                     'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4, 'ms_per_step': ms_e2e / args.steps},
             'gpu_launches': launches, 'roofline': roof,
             'tail_ms': {'value': tail_ms, 'what': 'gradient all-reduce (N>1) + dense TV + MaskedAdam, per step',
-                        'mode': os.environ.get('UBN_BENCH_TAIL', 'pipelined')},
+                        'mode': tail_mode},
             'fwd_only': {'value': samples_per_step / (ms_fwd / args.steps * 1e-3), 'unit': 'ray-samples/s',
                          'ms_per_step': ms_fwd / args.steps}}
     if not args.no_cpu_baseline and world == 1:              # rank 0 at N = 1 only

@@ -155,6 +155,21 @@ int ubn_tv_adam_pingpong(const float* param, float* param_out, float* grad, floa
                          int dense_mode, int step, float beta1, float beta2, float lr, float eps, int adam_mode,
                          int write_grad, void* stream);
 
+/* Multi-GPU training-step tail in one sweep over NVLink peer memory (no reference counterpart -- the reference has
+ * no distributed code): for the planes [plane_begin, plane_end) of the flattened (lead, sz_i) axis that this rank OWNS,
+ *   g = mean over the n_peers ranks of grad_peers[q]   (P2P loads = reduce-scatter),  g += TV(param)  (K20, as above),
+ *   (masked) Adam on this rank's exp_avg / exp_avg_sq   (K17 / K18),
+ *   param_out_peers[q] <- updated parameters for EVERY rank q  (P2P stores = all-gather; ping-pong buffer, != param).
+ * param: this rank's replica (old values, read with halos).  grad_peers / param_out_peers: HOST arrays of n_peers DEVICE pointers
+ * to whole-grid buffers that are peer-mapped into this process (n_peers in {1, 2, 4, 8}; entry order = rank order = summation
+ * order).  Channels-last layout and limits as ubn_tv_adam_pingpong.  The caller provides the two cross-rank barriers (all
+ * gradients complete before the launch, all stores complete before anyone reads param_out) and re-zeroes its own gradient.
+ * n_peers = 1 gives bit-identical parameters and moments to ubn_total_variation_add_grad + ubn_adam_upd. */
+int ubn_tv_adam_peer(const float* param, float* const* param_out_peers, const float* const* grad_peers, int n_peers,
+                     float* exp_avg, float* exp_avg_sq, float wx, float wy, float wz, int64_t lead, int64_t sz_i, int64_t sz_j,
+                     int64_t sz_k, int64_t inner, int dense_mode, int64_t plane_begin, int64_t plane_end, int step, float beta1,
+                     float beta2, float lr, float eps, int adam_mode, void* stream);
+
 /* ---- ub360_utils_cuda (FourierGrid/cuda/ub360_utils.cpp:20-22) -------------------------------- */
 /* ub360_utils_cuda.cumdist_thres              ub360_utils.cpp:13-18 / ub360_utils_kernel.cu:13-47 */
 int ubn_cumdist_thres(const float* dist, float thres, int64_t n_rays, int64_t n_pts, uint8_t* mask,

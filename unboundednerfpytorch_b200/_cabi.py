@@ -67,6 +67,8 @@ _SIGNATURES = {
                           c_f, c_f, c_f, c_f, c_int, c_int, c_p],
     'ubn_tv_adam_pingpong': [c_p, c_p, c_p, c_p, c_p, c_f, c_f, c_f, c_i64, c_i64, c_i64, c_i64, c_i64, c_int, c_int,
                              c_f, c_f, c_f, c_f, c_int, c_int, c_p],
+    'ubn_tv_adam_peer': [c_p, c_p, c_p, c_int, c_p, c_p, c_f, c_f, c_f, c_i64, c_i64, c_i64, c_i64, c_i64, c_int, c_i64, c_i64,
+                         c_int, c_f, c_f, c_f, c_f, c_int, c_p],
     'ubn_cumdist_thres': [c_p, c_f, c_i64, c_i64, c_p, c_p],
     'ubn_get_rays_of_a_view': [c_int, c_int, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_p, c_p, c_p, c_p, c_p],
     'ubn_gather_rays': [c_p, c_p, c_int, c_p, c_i64, c_i64, c_p, c_p],

@@ -283,6 +283,81 @@ __global__ void __launch_bounds__(kTaThreads, 2) k_tv_adam_stream(const float4* 
   }
 }
 
+// ---- multi-GPU tail: reduce-scatter -> TV -> Adam -> all-gather in ONE sweep over NVLink peer memory ---------------------
+// Ray-sharded data parallelism leaves every rank with its own gradient of a replicated grid.  Instead of all-reducing the
+// whole gradient and then letting every rank repeat the full-grid TV + Adam sweeps, rank r OWNS a contiguous range of (slab, i)
+// planes.  For its range it
+//   reads the gradient of all n ranks through peer pointers (P2P loads over NVLink; the sum in fixed rank order, scaled by
+//   1/n = mean over ranks, is the reduce-scatter),
+//   adds the TV term from its local (replicated, still old) parameters, runs (masked) Adam on its moments,
+//   and stores the updated parameters into the "next" parameter buffer of EVERY rank (P2P stores = the all-gather).
+// The parameters ping-pong between two buffers (as in k_tv_adam_stream), so the TV stencils of neighbouring owners keep
+// reading old values while new ones arrive.  Sweep work and Adam state traffic divide by n; each link carries (n-1)/n of the
+// grid once in each direction, overlapped element by element with the arithmetic.  The caller brackets the launch with two
+// cross-rank barriers (gradients complete before / parameter stores complete after) and re-zeroes its own gradient buffer.
+// n = 1 degenerates to k_tv_adam_stream without the gradient write-back (bit-identical parameters and moments).
+constexpr int kMaxPeers = 8;
+struct PeerPtrs {
+  const float4* grad[kMaxPeers];
+  float4* param_out[kMaxPeers];
+  float scale;
+};
+
+template <bool kDense, int kMode, int kN>
+__global__ void __launch_bounds__(kTaThreads, 2) k_tv_adam_peer(const float4* __restrict__ param, PeerPtrs peers,
+                                                                float4* __restrict__ exp_avg, float4* __restrict__ exp_avg_sq,
+                                                                float wy, float wz, TvStreamShape s, int lead, int i_lo, int i_hi,
+                                                                AdamHyper h) {
+  int b = blockIdx.x;
+  const int seg = b % s.n_seg;
+  const int jt = b / s.n_seg;
+  const int j0 = jt * s.tj;
+  const int rows = min(s.tj, s.sz_j - j0);
+  const int i0 = i_lo + seg * s.seg_len;
+  const int i1 = min(i0 + s.seg_len, i_hi);
+  const int64_t plane4 = (int64_t)s.sz_j * s.row4;
+  const int col = threadIdx.x;
+  if (col >= rows * s.row4 || i0 >= i1) return;
+  const int jj = col / s.row4, r = col - jj * s.row4;
+  int64_t off = ((int64_t)lead * s.sz_i + i0) * plane4 + (int64_t)(j0 + jj) * s.row4 + r;
+  const bool hkm = r >= s.inner4, hkp = r < s.row4 - s.inner4, hjm = j0 + jj > 0, hjp = j0 + jj < s.sz_j - 1;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 prev = i0 > 0 ? param[off - plane4] : zero4;
+  float4 cur = param[off];
+  for (int i = i0; i < i1; ++i, off += plane4) {
+    const bool him = i > 0, hip = i < s.sz_i - 1;
+    float4 gr[kN];
+#pragma unroll
+    for (int q = 0; q < kN; ++q) gr[q] = peers.grad[q][off];            // n independent (mostly remote) loads in flight
+    const float4 next = hip ? param[off + plane4] : zero4;
+    float4 m = exp_avg[off], v = exp_avg_sq[off];
+    const float4 p = cur;
+    const float4 km = hkm ? param[off - s.inner4] : zero4;
+    const float4 kp = hkp ? param[off + s.inner4] : zero4;
+    const float4 jm = hjm ? param[off - s.row4] : zero4;
+    const float4 jp = hjp ? param[off + s.row4] : zero4;
+    float4 g = gr[0];
+#pragma unroll
+    for (int q = 1; q < kN; ++q) { g.x += gr[q].x; g.y += gr[q].y; g.z += gr[q].z; g.w += gr[q].w; }
+    if (kN > 1) { g.x *= peers.scale; g.y *= peers.scale; g.z *= peers.scale; g.w *= peers.scale; }
+    if (kDense || g.x != 0) g.x = g.x + tv_term_vals(p.x, km.x, kp.x, jm.x, jp.x, prev.x, next.x, hkm, hkp, hjm, hjp, him, hip, wy, wz);
+    if (kDense || g.y != 0) g.y = g.y + tv_term_vals(p.y, km.y, kp.y, jm.y, jp.y, prev.y, next.y, hkm, hkp, hjm, hjp, him, hip, wy, wz);
+    if (kDense || g.z != 0) g.z = g.z + tv_term_vals(p.z, km.z, kp.z, jm.z, jp.z, prev.z, next.z, hkm, hkp, hjm, hjp, him, hip, wy, wz);
+    if (kDense || g.w != 0) g.w = g.w + tv_term_vals(p.w, km.w, kp.w, jm.w, jp.w, prev.w, next.w, hkm, hkp, hjm, hjp, him, hip, wy, wz);
+    float4 q4 = p;
+    bool any = false;
+    if (kMode == 0 || g.x != 0) { adam_one<kMode>(q4.x, g.x, m.x, v.x, 0.f, h); any = true; }
+    if (kMode == 0 || g.y != 0) { adam_one<kMode>(q4.y, g.y, m.y, v.y, 0.f, h); any = true; }
+    if (kMode == 0 || g.z != 0) { adam_one<kMode>(q4.z, g.z, m.z, v.z, 0.f, h); any = true; }
+    if (kMode == 0 || g.w != 0) { adam_one<kMode>(q4.w, g.w, m.w, v.w, 0.f, h); any = true; }
+#pragma unroll
+    for (int q = 0; q < kN; ++q) peers.param_out[q][off] = q4;
+    if (any) { exp_avg[off] = m; exp_avg_sq[off] = v; }
+    prev = p;
+    cur = next;
+  }
+}
+
 // vectorised (float4) main body + scalar tail
 template <int kMode>
 __global__ void __launch_bounds__(256) k_adam_vec4(float4* __restrict__ param, const float4* __restrict__ grad,
@@ -546,6 +621,66 @@ int ubn_tv_adam_pingpong(const float* param, float* param_out, float* grad, floa
   }
 #undef UBN_TA
   UBN_LAUNCH_CHECK();
+  return 0;
+}
+
+int ubn_tv_adam_peer(const float* param, float* const* param_out_peers, const float* const* grad_peers, int n_peers,
+                     float* exp_avg, float* exp_avg_sq, float wx, float wy, float wz, int64_t lead, int64_t sz_i, int64_t sz_j,
+                     int64_t sz_k, int64_t inner, int dense_mode, int64_t plane_begin, int64_t plane_end, int step, float beta1,
+                     float beta2, float lr, float eps, int adam_mode, void* stream) {
+  (void)wx;
+  if (plane_begin >= plane_end) return 0;
+  if (n_peers != 1 && n_peers != 2 && n_peers != 4 && n_peers != 8) return finish(cudaErrorInvalidValue);
+  if (inner % 4 != 0 || sz_i < 8 || (adam_mode != 0 && adam_mode != 1)) return finish(cudaErrorInvalidValue);
+  if (plane_begin < 0 || plane_end > lead * sz_i) return finish(cudaErrorInvalidValue);
+  uintptr_t bits = ((uintptr_t)param) | ((uintptr_t)exp_avg) | ((uintptr_t)exp_avg_sq);
+  PeerPtrs pp;
+  for (int q = 0; q < kMaxPeers; ++q) { pp.grad[q] = nullptr; pp.param_out[q] = nullptr; }
+  for (int q = 0; q < n_peers; ++q) {
+    if (param_out_peers[q] == param) return finish(cudaErrorInvalidValue);
+    bits |= ((uintptr_t)param_out_peers[q]) | ((uintptr_t)grad_peers[q]);
+    pp.grad[q] = (const float4*)grad_peers[q];
+    pp.param_out[q] = (float4*)param_out_peers[q];
+  }
+  if (bits & 15) return finish(cudaErrorInvalidValue);
+  pp.scale = 1.f / (float)n_peers;
+  const int64_t row4 = sz_k * inner / 4;
+  if (row4 > kTaThreads || row4 < 32) return finish(cudaErrorInvalidValue);
+  TvStreamShape s;
+  s.sz_i = (int)sz_i; s.sz_j = (int)sz_j; s.row4 = (int)row4; s.inner4 = (int)(inner / 4);
+  s.tj = (int)std::max<int64_t>(1, kTaThreads / row4);
+  s.n_jt = (int)((sz_j + s.tj - 1) / s.tj);
+  const AdamHyper h = make_hyper(step, beta1, beta2, lr, eps);
+  wy /= 6; wz /= 6;
+  cudaStream_t st = as_stream(stream);
+  const float4* p = (const float4*)param;
+  float4 *m = (float4*)exp_avg, *v = (float4*)exp_avg_sq;
+  // the owned plane range [plane_begin, plane_end) of the flattened (slab, i) axis, one launch per slab it touches
+  for (int64_t ld = plane_begin / sz_i; ld <= (plane_end - 1) / sz_i; ++ld) {
+    const int i_lo = (int)std::max<int64_t>(plane_begin - ld * sz_i, 0);
+    const int i_hi = (int)std::min<int64_t>(plane_end - ld * sz_i, sz_i);
+    const int64_t planes = i_hi - i_lo;
+    // ~8 waves of 2 x 148 resident CTAs over the whole owned range, segments no shorter than 8 planes
+    int64_t n_seg = (8 * 2 * 148 * planes + (plane_end - plane_begin) * s.n_jt - 1) / ((plane_end - plane_begin) * s.n_jt);
+    n_seg = std::max<int64_t>(1, std::min<int64_t>(n_seg, std::max<int64_t>(planes / 8, 1)));
+    s.seg_len = (int)((planes + n_seg - 1) / n_seg);
+    s.n_seg = (int)((planes + s.seg_len - 1) / s.seg_len);
+    const int64_t nb = (int64_t)s.n_jt * s.n_seg;
+    if (nb > 0x7fffffffll) return finish(cudaErrorInvalidValue);
+#define UBN_TP(D, M, N) k_tv_adam_peer<D, M, N><<<(unsigned)nb, kTaThreads, 0, st>>>(p, pp, m, v, wy, wz, s, (int)ld, i_lo, i_hi, h)
+#define UBN_TPN(D, M)                                     \
+    switch (n_peers) {                                    \
+      case 1: UBN_TP(D, M, 1); break;                     \
+      case 2: UBN_TP(D, M, 2); break;                     \
+      case 4: UBN_TP(D, M, 4); break;                     \
+      default: UBN_TP(D, M, 8); break;                    \
+    }
+    if (dense_mode) { if (adam_mode) { UBN_TPN(true, 1) } else { UBN_TPN(true, 0) } }
+    else            { if (adam_mode) { UBN_TPN(false, 1) } else { UBN_TPN(false, 0) } }
+#undef UBN_TPN
+#undef UBN_TP
+    UBN_LAUNCH_CHECK();
+  }
   return 0;
 }
 

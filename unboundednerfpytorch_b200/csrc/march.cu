@@ -28,14 +28,14 @@ __device__ __forceinline__ float grid_density(const GridView& g, float x, float 
   const float nx = norm_coord(x, g.mn[0], g.len[0]);
   const float ny = norm_coord(y, g.mn[1], g.len[1]);
   const float nz = norm_coord(z, g.mn[2], g.len[2]);
-  float acc = 0.f;
+  SlabMean acc;
   for (int s = 0; s < g.P; ++s) {
     const float cx = src_index(fourier_gamma(s, nx), g.X);
     const float cy = src_index(fourier_gamma(s, ny), g.Y);
     const float cz = src_index(fourier_gamma(s, nz), g.Z);
-    acc += trilerp1(g.data + s * g.sp, g.sv, g.X, g.Y, g.Z, cx, cy, cz);
+    acc.add(s, trilerp1(g.data + s * g.sp, g.sv, g.X, g.Y, g.Z, cx, cy, cz));
   }
-  return (g.P > 1) ? acc / (float)g.P : acc;
+  return acc.mean(g.P);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(32 * kMarchWarps) k_march_feature(
       float4 gin = make_float4(0, 0, 0, 0);
       if (kBackward) {
         if (quad_on) gin = *reinterpret_cast<const float4*>(feat + pt * g.C + quad * 4);
-        if (g.P > 1) { gin.x = gin.x / (float)g.P; gin.y = gin.y / (float)g.P; gin.z = gin.z / (float)g.P; gin.w = gin.w / (float)g.P; }
+        gin.x = slab_mean_scale(gin.x, g.P); gin.y = slab_mean_scale(gin.y, g.P); gin.z = slab_mean_scale(gin.z, g.P); gin.w = slab_mean_scale(gin.w, g.P);
       }
       for (int sl = 0; sl < g.P; ++sl) {
         const float4 ci = my_idx[i * g.P + sl];
@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(32 * kMarchWarps) k_march_feature(
           acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
         }
         if (corner == 0 && quad_on) {
-          if (g.P > 1) { acc.x = acc.x / (float)g.P; acc.y = acc.y / (float)g.P; acc.z = acc.z / (float)g.P; acc.w = acc.w / (float)g.P; }
+          acc.x = slab_mean_scale(acc.x, g.P); acc.y = slab_mean_scale(acc.y, g.P); acc.z = slab_mean_scale(acc.z, g.P); acc.w = slab_mean_scale(acc.w, g.P);
           *reinterpret_cast<float4*>(feat + pt * g.C + quad * 4) = acc;
         }
       }
@@ -314,7 +314,7 @@ __global__ void __launch_bounds__(32 * kMarchWarps) k_march_density_bwd(
     const float nx = norm_coord(x, g.mn[0], g.len[0]);
     const float ny = norm_coord(y, g.mn[1], g.len[1]);
     const float nz = norm_coord(z, g.mn[2], g.len[2]);
-    if (g.P > 1) gd = gd / (float)g.P;
+    gd = slab_mean_scale(gd, g.P);
     for (int sl = 0; sl < g.P; ++sl) {
       const float cx = src_index(fourier_gamma(sl, nx), g.X);
       const float cy = src_index(fourier_gamma(sl, ny), g.Y);

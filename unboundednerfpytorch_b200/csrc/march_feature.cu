@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(32 * kMarchWarps, (kGroup <= 1 ? 8 : (kGroup <
         gin[j] = make_float4(0, 0, 0, 0);
         if (kBackward) {
           if (quad_on && g0 + j < n_here) gin[j] = *reinterpret_cast<const float4*>(feat + (out_base + g0 + j) * g.C + quad * 4);
-          if (kP > 1) { gin[j].x = gin[j].x / (float)kP; gin[j].y = gin[j].y / (float)kP; gin[j].z = gin[j].z / (float)kP; gin[j].w = gin[j].w / (float)kP; }
+          gin[j].x = slab_mean_scale(gin[j].x, kP); gin[j].y = slab_mean_scale(gin[j].y, kP); gin[j].z = slab_mean_scale(gin[j].z, kP); gin[j].w = slab_mean_scale(gin[j].w, kP);
         }
       }
 #pragma unroll
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(32 * kMarchWarps, (kGroup <= 1 ? 8 : (kGroup <
         for (int j = 0; j < kGroup; ++j) {
           if (corner == j && quad_on && g0 + j < n_here) {
             float4 v = acc[j];
-            if (kP > 1) { v.x = v.x / (float)kP; v.y = v.y / (float)kP; v.z = v.z / (float)kP; v.w = v.w / (float)kP; }
+            v.x = slab_mean_scale(v.x, kP); v.y = slab_mean_scale(v.y, kP); v.z = slab_mean_scale(v.z, kP); v.w = slab_mean_scale(v.w, kP);
             *reinterpret_cast<float4*>(feat + (out_base + g0 + j) * g.C + quad * 4) = v;
           }
         }

@@ -20,14 +20,14 @@ __global__ void __launch_bounds__(256) k_grid_fwd_c1(GridView g, const float* __
   const float nx = norm_coord(xyz[3 * p], g.mn[0], g.len[0]);
   const float ny = norm_coord(xyz[3 * p + 1], g.mn[1], g.len[1]);
   const float nz = norm_coord(xyz[3 * p + 2], g.mn[2], g.len[2]);
-  float acc = 0.f;
+  SlabMean acc;
   for (int s = 0; s < g.P; ++s) {
     const float cx = src_index(fourier_gamma(s, nx), g.X);
     const float cy = src_index(fourier_gamma(s, ny), g.Y);
     const float cz = src_index(fourier_gamma(s, nz), g.Z);
-    acc += trilerp1(g.data + s * g.sp, g.sv, g.X, g.Y, g.Z, cx, cy, cz);
+    acc.add(s, trilerp1(g.data + s * g.sp, g.sv, g.X, g.Y, g.Z, cx, cy, cz));
   }
-  out[p] = (g.P > 1) ? acc / (float)g.P : acc;
+  out[p] = acc.mean(g.P);
 }
 
 __global__ void __launch_bounds__(256) k_grid_bwd_c1(GridView g, const float* __restrict__ xyz, int64_t n_pts,
@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(256) k_grid_bwd_c1(GridView g, const float* __
   if (p >= n_pts) return;
   float go = grad_out[p];
   if (go == 0.f) return;
-  if (g.P > 1) go = go / (float)g.P;   // d mean / d slab
+  go = slab_mean_scale(go, g.P);   // d mean / d slab
   const float nx = norm_coord(xyz[3 * p], g.mn[0], g.len[0]);
   const float ny = norm_coord(xyz[3 * p + 1], g.mn[1], g.len[1]);
   const float nz = norm_coord(xyz[3 * p + 2], g.mn[2], g.len[2]);
@@ -59,14 +59,14 @@ __global__ void __launch_bounds__(256) k_grid_fwd_generic(GridView g, const floa
   const float ny = norm_coord(xyz[3 * p + 1], g.mn[1], g.len[1]);
   const float nz = norm_coord(xyz[3 * p + 2], g.mn[2], g.len[2]);
   for (int c = 0; c < g.C; ++c) {
-    float acc = 0.f;
+    SlabMean acc;
     for (int s = 0; s < g.P; ++s) {
       const float cx = src_index(fourier_gamma(s, nx), g.X);
       const float cy = src_index(fourier_gamma(s, ny), g.Y);
       const float cz = src_index(fourier_gamma(s, nz), g.Z);
-      acc += trilerp1(g.data + s * g.sp + c * g.sc, g.sv, g.X, g.Y, g.Z, cx, cy, cz);
+      acc.add(s, trilerp1(g.data + s * g.sp + c * g.sc, g.sv, g.X, g.Y, g.Z, cx, cy, cz));
     }
-    out[p * g.C + c] = (g.P > 1) ? acc / (float)g.P : acc;
+    out[p * g.C + c] = acc.mean(g.P);
   }
 }
 
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(256) k_grid_bwd_generic(GridView g, const floa
     const float cz = src_index(fourier_gamma(s, nz), g.Z);
     for (int c = 0; c < g.C; ++c) {
       float go = grad_out[p * g.C + c];
-      if (g.P > 1) go = go / (float)g.P;
+      go = slab_mean_scale(go, g.P);
       trilerp1_scatter(grad_grid + s * g.sp + c * g.sc, g.sv, g.X, g.Y, g.Z, cx, cy, cz, go);
     }
   }
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(32 * kCoopWarps) k_grid_coop(GridView g, const
       if (kBackward) {
         if (quad_on) gin = *reinterpret_cast<const float4*>(out_or_gin + pt * g.C + quad * 4);
         if (inv_p_is_needed != 0.f) {
-          gin.x = gin.x / (float)g.P; gin.y = gin.y / (float)g.P; gin.z = gin.z / (float)g.P; gin.w = gin.w / (float)g.P;
+          gin.x = slab_mean_scale(gin.x, g.P); gin.y = slab_mean_scale(gin.y, g.P); gin.z = slab_mean_scale(gin.z, g.P); gin.w = slab_mean_scale(gin.w, g.P);
         }
       }
       for (int s = 0; s < g.P; ++s) {
@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(32 * kCoopWarps) k_grid_coop(GridView g, const
           acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
         }
         if (corner == 0 && quad_on) {
-          if (g.P > 1) { acc.x = acc.x / (float)g.P; acc.y = acc.y / (float)g.P; acc.z = acc.z / (float)g.P; acc.w = acc.w / (float)g.P; }
+          acc.x = slab_mean_scale(acc.x, g.P); acc.y = slab_mean_scale(acc.y, g.P); acc.z = slab_mean_scale(acc.z, g.P); acc.w = slab_mean_scale(acc.w, g.P);
           *reinterpret_cast<float4*>(out_or_gin + pt * g.C + quad * 4) = acc;
         }
       }

@@ -52,6 +52,31 @@ __device__ __forceinline__ float src_index(float coord, int size) {
   return __fmul_rn(__fmul_rn(__fadd_rn(coord, 1.f), 0.5f), (float)(size - 1));
 }
 
+// Mean over the P slabs exactly as torch-CUDA evaluates `out.mean(0)` on the grid_sample output (FourierGrid_grid.py:72), probed
+// on B200 (scripts/probe_mean_order.py: 0 mismatches in 4 M elements for P = 3..11; the sequential and the pairwise-tree orders
+// mismatch in ~58 %): ATen's reduction keeps four interleaved accumulators a[i & 3] += x_i, combines them ((a0 + a1) + a2) + a3
+// and multiplies by the fp32 reciprocal of P.  Matching it makes raw_density -- and with it alpha, the weights and every
+// threshold decision downstream -- bit-identical to the reference's GPU path (alpha = 1 - (1+e)^-interval is ill-conditioned:
+// one ulp of density can move a dense-mode alpha by 1e-3 of its value).
+struct SlabMean {
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  __device__ __forceinline__ void add(int slab, float v) {
+    switch (slab & 3) {
+      case 0: a0 = __fadd_rn(a0, v); break;
+      case 1: a1 = __fadd_rn(a1, v); break;
+      case 2: a2 = __fadd_rn(a2, v); break;
+      default: a3 = __fadd_rn(a3, v); break;
+    }
+  }
+  __device__ __forceinline__ float mean(int P) const {
+    const float sum = __fadd_rn(__fadd_rn(__fadd_rn(a0, a1), a2), a3);
+    return (P > 1) ? __fmul_rn(sum, __frcp_rn((float)P)) : sum;
+  }
+};
+
+// d mean / d slab as torch's autograd evaluates it: grad / P is a multiplication by the fp32 reciprocal on CUDA
+__device__ __forceinline__ float slab_mean_scale(float g, int P) { return (P > 1) ? __fmul_rn(g, __frcp_rn((float)P)) : g; }
+
 struct Cell {
   int x0, y0, z0;
   float wx0, wx1, wy0, wy1, wz0, wz1;   // weight of corner 0 / corner 1 along each axis

@@ -193,6 +193,178 @@ def reduce_tv_step(opt, tv=None):
         opt._apply(group, param, states[id(param)], sl)
 
 
+# ----------------------------------------------------------------------------------------------------------------------
+# Multi-GPU tail over NVLink peer memory: reduce-scatter -> TV -> Adam -> all-gather in one sweep (csrc/grid_sweep.cu,
+# k_tv_adam_peer).  Replaces "all-reduce 1.7 GB of gradient, then every rank repeats the full TV + Adam sweeps".
+# ----------------------------------------------------------------------------------------------------------------------
+def peer_mapped_buffers(numel, device, count):
+    """``count`` fp32 buffers of ``numel`` elements on every rank, each mapped into every other rank's address space.
+    Returns [(local flat tensor, [device address of that buffer on rank 0..world-1, valid in THIS process], keepalive), ...].
+    Collective (same call order on all ranks).  Mapping: torch symmetric memory (CUDA VMM handles exchanged by the c10d store);
+    fallback: CUDA IPC handles of ordinary allocations (the torch.multiprocessing tensor-sharing mechanism).  world == 1: plain
+    allocations."""
+    world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+    out = []
+    if world == 1:
+        for _ in range(count):
+            t = torch.zeros(numel, dtype=torch.float32, device=device)
+            out.append((t, [t.data_ptr()], None))
+        return out
+    mode = os.environ.get('UBN_PEER_MAP', 'auto')
+    if mode in ('auto', 'symm'):
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            made = []
+            for _ in range(count):
+                t = symm_mem.empty(numel, dtype=torch.float32, device=device)
+                hdl = symm_mem.rendezvous(t, dist.group.WORLD)
+                t.zero_()
+                made.append((t, [int(a) for a in hdl.buffer_ptrs], hdl))
+            return made
+        except Exception as e:                       # pragma: no cover  (depends on the box)
+            if mode == 'symm':
+                raise
+            print(f'[ubn.dist] symmetric memory unavailable ({e!r}); falling back to CUDA IPC', flush=True)
+    rank = dist.get_rank()
+    for _ in range(count):
+        t = torch.zeros(numel, dtype=torch.float32, device=device)
+        meta = (t.untyped_storage()._share_cuda_(), t.storage_offset() * t.element_size())
+        metas = [None] * world
+        dist.all_gather_object(metas, meta)
+        ptrs, keep = [], []
+        for r in range(world):
+            if r == rank:
+                ptrs.append(t.data_ptr())
+                continue
+            st = torch.UntypedStorage._new_shared_cuda(*metas[r][0])
+            keep.append(st)
+            ptrs.append(st.data_ptr() + metas[r][1])
+        out.append((t, ptrs, keep))
+    return out
+
+
+class _PeerGrid:
+    """A replicated channels-last grid parameter with its gradient buffer and both ping-pong parameter buffers peer-mapped."""
+
+    def __init__(self, param, rank, world):
+        P, C, X, Y, Z = param.shape
+        n = param.numel()
+        (self.g, self.g_ptrs, k0), (self.a, self.a_ptrs, k1), (self.b, self.b_ptrs, k2) = peer_mapped_buffers(n, param.device, 3)
+        self._keep = (k0, k1, k2)
+        view = lambda flat: flat.view(P, X, Y, Z, C).permute(0, 4, 1, 2, 3)
+        self.view = view
+        with torch.no_grad():
+            view(self.a).copy_(param.detach())
+            param.data = view(self.a)
+        param._ubn_grad_buffer = view(self.g)
+        self.param = param
+        self.planes = P * X
+        self.lo, self.hi = shard_range(self.planes, rank, world)
+
+    def swap(self):
+        self.a, self.b = self.b, self.a
+        self.a_ptrs, self.b_ptrs = self.b_ptrs, self.a_ptrs
+        self.param.data = self.view(self.a)
+
+
+class PeerTail:
+    """Tail of a ray-sharded training step with the big grids exchanged over NVLink peer memory.
+
+        tail = PeerTail(opt)                 # once, after the optimizer exists (collective); moves eligible grids to peer memory
+        loss.backward()                      # the march scatters straight into the persistent peer-visible gradient buffers
+        tail.step(tv_terms)                  # == mean-all-reduce -> total_variation_add_grad -> opt.step(), see below
+
+    Per eligible grid (channels-last [P,C,X,Y,Z], C % 4 == 0, no per-voxel lr) rank r owns planes shard_range(P*X, r, world) of
+    the flattened (slab, X) axis and runs ONE kernel on them: mean of all ranks' gradients (P2P loads) -> TV -> (masked) Adam on
+    its own moments -> the updated parameters stored into every rank's spare parameter buffer (P2P stores).  Parameters
+    ping-pong, so nobody overwrites values a neighbour's TV stencil still reads.  Two cross-rank barriers bracket the sweeps
+    (gradients complete / stores complete); then each rank zeroes its gradient buffer and swaps the parameter buffers.  The
+    sweep work and the Adam state traffic divide by world, each NVLink direction carries (world-1)/world of the grid once.
+    Everything else (C == 1 density grids, the rgbnet) takes the classic route: mean all-reduce over NCCL + TV + MaskedAdam.
+    Exactness: identical to reduce_tv_step up to the fp32 summation order of the ranks' gradients (fixed: rank order);
+    world == 1 is bit-identical to total_variation_add_grad + opt.step().  Adam moments of a peer grid are only maintained for
+    the owned planes (use gather_moments() before saving an optimizer state dict)."""
+
+    def __init__(self, opt):
+        from . import ops
+        self.opt = opt
+        self.world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+        self.rank = dist.get_rank() if self.world > 1 else 0
+        if self.world not in (1, 2, 4, 8):
+            raise RuntimeError('PeerTail supports 1, 2, 4 or 8 ranks')
+        self.grids = {}
+        for group in opt.param_groups:
+            for param in group['params']:
+                if opt.per_lr is None and param.requires_grad and ops.tv_adam_pingpong_supported(param):
+                    self.grids[param] = _PeerGrid(param, self.rank, self.world)
+        self._flag = None
+        if self.world > 1:
+            self._flag = torch.zeros(1, device=next(iter(self.grids)).device if self.grids else 'cuda')
+            dist.barrier()
+
+    def _barrier(self):
+        """Stream-ordered cross-rank barrier: a 4-byte NCCL all-reduce.  It starts on a rank once that rank's stream has reached
+        this point and completes nowhere before every rank has joined."""
+        if self.world > 1:
+            dist.all_reduce(self._flag)
+
+    @torch.no_grad()
+    def step(self, tv=None):
+        from . import ops
+        tv = tv or {}
+        opt = self.opt
+        classic = []
+        for group in opt.param_groups:
+            group['skip_zero_grad']
+            for param in group['params']:
+                if param in self.grids:
+                    if param.grad is None:                                  # not touched this step: still consume a zero gradient
+                        param.grad = param._ubn_grad_buffer
+                    continue
+                if param.grad is not None:
+                    _normalise_grad_layout(param)
+                    classic.append((group, param))
+        classic.sort(key=lambda w: w[1].numel())
+        handles = [_MeanReduce(_memory_order(param.grad)) for _, param in classic] if self.world > 1 else []
+        self._barrier()                                                     # every rank's gradient buffers are complete
+        for group in opt.param_groups:
+            for param in group['params']:
+                pg = self.grids.get(param)
+                if pg is None:
+                    continue
+                state = opt._begin(param)
+                wx, wy, wz, dense = tv.get(param, (0.0, 0.0, 0.0, True))
+                beta1, beta2 = group['betas']
+                ops.tv_adam_peer(param, pg.b_ptrs, pg.g_ptrs, state['exp_avg'], state['exp_avg_sq'], wx, wy, wz, dense, pg.lo, pg.hi,
+                                 state['step'], beta1, beta2, group['lr'], group['eps'], skip_zero_grad=group['skip_zero_grad'])
+        self._barrier()                                                     # every rank's parameter stores have landed
+        for pg in self.grids.values():
+            pg.g.zero_()
+            pg.swap()
+            pg.param.grad = None
+        for i, (group, param) in enumerate(classic):
+            if handles:
+                handles[i].wait()
+            if param in tv:
+                ops.total_variation_add_grad(param, param.grad, *tv[param])
+            opt._apply(group, param, opt._begin(param))
+
+    @torch.no_grad()
+    def gather_moments(self):
+        """Make exp_avg / exp_avg_sq of the peer grids whole on every rank (each rank maintains only its owned planes): one
+        all-reduce of the moments masked to the owned range.  For checkpointing; not part of the step."""
+        if self.world == 1:
+            return
+        for param, pg in self.grids.items():
+            st = self.opt.state.get(param, {})
+            for k in ('exp_avg', 'exp_avg_sq'):
+                if k in st:
+                    flat = _memory_order(st[k]).reshape(pg.planes, -1)
+                    flat[:pg.lo].zero_()
+                    flat[pg.hi:].zero_()
+                    dist.all_reduce(flat)
+
+
 def gather_frame(local_out, n_total, rank, world, dst=0):
     """Render path: every rank rendered its contiguous shard of a frame ([n_local, K] rgb/depth/...) -> all ranks get
     the assembled [n_total, K] tensor (one all_gather of at most ceil(n_total/world) rows per rank)."""

@@ -90,6 +90,17 @@ class MaskedAdam(torch.optim.Optimizer):
                 param.data = state['pingpong']
                 state['pingpong'] = old
 
+    def zero_grad(self, set_to_none=True):
+        """torch.optim.Optimizer.zero_grad; a parameter that owns a persistent gradient buffer (dist.PeerTail) has the BUFFER
+        zeroed when it still holds an unconsumed gradient, and .grad detached from it."""
+        for group in self.param_groups:
+            for param in group['params']:
+                buf = getattr(param, '_ubn_grad_buffer', None)
+                if buf is not None and param.grad is not None:
+                    buf.zero_()
+                    param.grad = None
+        super().zero_grad(set_to_none=set_to_none)
+
     @torch.no_grad()
     def step(self):
         for group in self.param_groups:

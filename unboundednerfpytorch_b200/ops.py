@@ -314,6 +314,29 @@ def tv_adam_pingpong(param, param_out, grad, exp_avg, exp_avg_sq, wx, wy, wz, de
                                        c_int(1 if write_grad else 0), stream_of(param)))
 
 
+def tv_adam_peer(param, param_out_ptrs, grad_ptrs, exp_avg, exp_avg_sq, wx, wy, wz, dense_mode, plane_begin, plane_end, step,
+                 beta1, beta2, lr, eps, skip_zero_grad=True):
+    """Multi-GPU tail sweep (ubn_tv_adam_peer): mean of the ranks' gradients -> TV -> (masked) Adam -> updated parameters stored
+    into every rank's ping-pong buffer, for the planes [plane_begin, plane_end) of the flattened (slab, X) axis this rank owns.
+    ``param_out_ptrs`` / ``grad_ptrs``: device addresses (ints, rank order) of whole-grid buffers mapped into this process."""
+    import ctypes
+    if not tv_adam_pingpong_supported(param):
+        raise RuntimeError('tv_adam_peer needs a channels-last [P,C,X,Y,Z] grid with C % 4 == 0')
+    n = len(grad_ptrs)
+    if n != len(param_out_ptrs) or n not in (1, 2, 4, 8):
+        raise RuntimeError('tv_adam_peer needs 1, 2, 4 or 8 peers')
+    lead, inner = _sweep_layout(param)
+    _dense_like(param, exp_avg, 'exp_avg'); _dense_like(param, exp_avg_sq, 'exp_avg_sq')
+    po = (ctypes.c_void_p * n)(*[int(a) for a in param_out_ptrs])
+    gp = (ctypes.c_void_p * n)(*[int(a) for a in grad_ptrs])
+    with _Guard(param) as lib:
+        check(lib.ubn_tv_adam_peer(ptr(param), po, gp, c_int(n), ptr(exp_avg), ptr(exp_avg_sq), c_f(float(wx)), c_f(float(wy)),
+                                   c_f(float(wz)), c_i64(lead), c_i64(param.shape[2]), c_i64(param.shape[3]), c_i64(param.shape[4]),
+                                   c_i64(inner), c_int(int(bool(dense_mode))), c_i64(int(plane_begin)), c_i64(int(plane_end)),
+                                   c_int(int(step)), c_f(beta1), c_f(beta2), c_f(lr), c_f(eps), c_int(1 if skip_zero_grad else 0),
+                                   stream_of(param)))
+
+
 def cumdist_thres(dist, thres):
     _chk(dist, 'dist')
     mask = torch.empty(dist.shape, dtype=torch.bool, device=dist.device)
