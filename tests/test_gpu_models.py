@@ -198,12 +198,12 @@ def test_training_step_reduces_loss():
     assert all(torch.isfinite(p).all() for p in student.parameters())
 
 
-@pytest.mark.parametrize('mode', ['simt', 'tc3', 'tc1', 'tc3+tcbwd'])
+@pytest.mark.parametrize('mode', ['simt', 'tc3', 'tc1', 'tc3+tcbwd', 'tc3+fused'])
 def test_fused_rgbnet_vs_torch(mode, monkeypatch):
     """csrc/shade.cu (fp32 FFMA) and csrc/shade_tc.cu (tcgen05: 3xTF32 fp32-grade, single-pass TF32 preview) vs the torch
     nn.Sequential they replace: forward and every gradient."""
     from unboundednerfpytorch_b200 import models, shade as shade_mod
-    monkeypatch.setattr(shade_mod, 'BWD_MODE', 'tc3' if mode.endswith('tcbwd') else 'simt')
+    monkeypatch.setattr(shade_mod, 'BWD_MODE', 'tc3' if mode.endswith('tcbwd') else ('fused' if mode.endswith('fused') else 'simt'))
     mode = mode.split('+')[0]
     monkeypatch.setattr(shade_mod, 'MODE', mode)
     fwd_tol = dict(rtol=1e-5, atol=1e-6) if mode != 'tc1' else dict(rtol=5e-3, atol=5e-3)
@@ -211,7 +211,7 @@ def test_fused_rgbnet_vs_torch(mode, monkeypatch):
     net = models._make_rgbnet(39, 128, 3).to(DEV)
     with torch.no_grad():
         net[3].bias.normal_(0, 0.1)
-    for M, n_rays in ((1, 1), (77, 5), (300, 300), (20000, 37)):
+    for M, n_rays in ((1, 1), (77, 5), (300, 300), (20000, 37), (150001, 613)):
         g = torch.Generator().manual_seed(M)
         k0 = torch.randn(M, 12, generator=g).to(DEV).requires_grad_(True)
         emb = torch.randn(n_rays, 27, generator=g).to(DEV)

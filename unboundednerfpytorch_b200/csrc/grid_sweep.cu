@@ -304,32 +304,37 @@ struct PeerPtrs {
 };
 
 template <bool kDense, int kMode, int kN>
-__global__ void __launch_bounds__(kTaThreads, 2) k_tv_adam_peer(const float4* __restrict__ param, PeerPtrs peers,
+__global__ void __launch_bounds__(kTaThreads, (kN >= 4 ? 1 : 2)) k_tv_adam_peer(const float4* __restrict__ param, PeerPtrs peers,
                                                                 float4* __restrict__ exp_avg, float4* __restrict__ exp_avg_sq,
-                                                                float wy, float wz, TvStreamShape s, int lead, int i_lo, int i_hi,
+                                                                float wy, float wz, TvStreamShape s, int q_lo, int q_hi,
                                                                 AdamHyper h) {
+  // the grid is ONE stack of lead * sz_i planes (q = lead * sz_i + i is the memory order); a CTA owns a tile of tj (k, inner)
+  // rows and a segment of planes of the owned range [q_lo, q_hi), which may cross slab boundaries: the i - 1 / i + 1 values
+  // it carries are then the neighbouring slab's planes and are masked out by him / hip exactly like the grid faces
   int b = blockIdx.x;
   const int seg = b % s.n_seg;
   const int jt = b / s.n_seg;
   const int j0 = jt * s.tj;
   const int rows = min(s.tj, s.sz_j - j0);
-  const int i0 = i_lo + seg * s.seg_len;
-  const int i1 = min(i0 + s.seg_len, i_hi);
+  const int q0 = q_lo + seg * s.seg_len;
+  const int q1 = min(q0 + s.seg_len, q_hi);
   const int64_t plane4 = (int64_t)s.sz_j * s.row4;
   const int col = threadIdx.x;
-  if (col >= rows * s.row4 || i0 >= i1) return;
+  if (col >= rows * s.row4 || q0 >= q1) return;
   const int jj = col / s.row4, r = col - jj * s.row4;
-  int64_t off = ((int64_t)lead * s.sz_i + i0) * plane4 + (int64_t)(j0 + jj) * s.row4 + r;
+  int64_t off = (int64_t)q0 * plane4 + (int64_t)(j0 + jj) * s.row4 + r;
   const bool hkm = r >= s.inner4, hkp = r < s.row4 - s.inner4, hjm = j0 + jj > 0, hjp = j0 + jj < s.sz_j - 1;
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  float4 prev = i0 > 0 ? param[off - plane4] : zero4;
+  int i = q0 % s.sz_i;
+  float4 prev = i > 0 ? param[off - plane4] : zero4;
   float4 cur = param[off];
-  for (int i = i0; i < i1; ++i, off += plane4) {
+  for (int q = q0; q < q1; ++q, off += plane4) {
     const bool him = i > 0, hip = i < s.sz_i - 1;
     float4 gr[kN];
 #pragma unroll
-    for (int q = 0; q < kN; ++q) gr[q] = peers.grad[q][off];            // n independent (mostly remote) loads in flight
-    const float4 next = hip ? param[off + plane4] : zero4;
+    for (int t = 0; t < kN; ++t) gr[t] = peers.grad[t][off];            // n independent (mostly remote) loads in flight
+    const bool more = q + 1 < q1 || hip;                                 // the next plane exists in memory and is needed
+    const float4 next = more ? param[off + plane4] : zero4;
     float4 m = exp_avg[off], v = exp_avg_sq[off];
     const float4 p = cur;
     const float4 km = hkm ? param[off - s.inner4] : zero4;
@@ -338,7 +343,7 @@ __global__ void __launch_bounds__(kTaThreads, 2) k_tv_adam_peer(const float4* __
     const float4 jp = hjp ? param[off + s.row4] : zero4;
     float4 g = gr[0];
 #pragma unroll
-    for (int q = 1; q < kN; ++q) { g.x += gr[q].x; g.y += gr[q].y; g.z += gr[q].z; g.w += gr[q].w; }
+    for (int t = 1; t < kN; ++t) { g.x += gr[t].x; g.y += gr[t].y; g.z += gr[t].z; g.w += gr[t].w; }
     if (kN > 1) { g.x *= peers.scale; g.y *= peers.scale; g.z *= peers.scale; g.w *= peers.scale; }
     if (kDense || g.x != 0) g.x = g.x + tv_term_vals(p.x, km.x, kp.x, jm.x, jp.x, prev.x, next.x, hkm, hkp, hjm, hjp, him, hip, wy, wz);
     if (kDense || g.y != 0) g.y = g.y + tv_term_vals(p.y, km.y, kp.y, jm.y, jp.y, prev.y, next.y, hkm, hkp, hjm, hjp, him, hip, wy, wz);
@@ -351,10 +356,11 @@ __global__ void __launch_bounds__(kTaThreads, 2) k_tv_adam_peer(const float4* __
     if (kMode == 0 || g.z != 0) { adam_one<kMode>(q4.z, g.z, m.z, v.z, 0.f, h); any = true; }
     if (kMode == 0 || g.w != 0) { adam_one<kMode>(q4.w, g.w, m.w, v.w, 0.f, h); any = true; }
 #pragma unroll
-    for (int q = 0; q < kN; ++q) peers.param_out[q][off] = q4;
+    for (int t = 0; t < kN; ++t) peers.param_out[t][off] = q4;
     if (any) { exp_avg[off] = m; exp_avg_sq[off] = v; }
     prev = p;
     cur = next;
+    i = (i + 1 == s.sz_i) ? 0 : i + 1;
   }
 }
 
@@ -655,32 +661,29 @@ int ubn_tv_adam_peer(const float* param, float* const* param_out_peers, const fl
   cudaStream_t st = as_stream(stream);
   const float4* p = (const float4*)param;
   float4 *m = (float4*)exp_avg, *v = (float4*)exp_avg_sq;
-  // the owned plane range [plane_begin, plane_end) of the flattened (slab, i) axis, one launch per slab it touches
-  for (int64_t ld = plane_begin / sz_i; ld <= (plane_end - 1) / sz_i; ++ld) {
-    const int i_lo = (int)std::max<int64_t>(plane_begin - ld * sz_i, 0);
-    const int i_hi = (int)std::min<int64_t>(plane_end - ld * sz_i, sz_i);
-    const int64_t planes = i_hi - i_lo;
-    // ~8 waves of 2 x 148 resident CTAs over the whole owned range, segments no shorter than 8 planes
-    int64_t n_seg = (8 * 2 * 148 * planes + (plane_end - plane_begin) * s.n_jt - 1) / ((plane_end - plane_begin) * s.n_jt);
-    n_seg = std::max<int64_t>(1, std::min<int64_t>(n_seg, std::max<int64_t>(planes / 8, 1)));
-    s.seg_len = (int)((planes + n_seg - 1) / n_seg);
-    s.n_seg = (int)((planes + s.seg_len - 1) / s.seg_len);
-    const int64_t nb = (int64_t)s.n_jt * s.n_seg;
-    if (nb > 0x7fffffffll) return finish(cudaErrorInvalidValue);
-#define UBN_TP(D, M, N) k_tv_adam_peer<D, M, N><<<(unsigned)nb, kTaThreads, 0, st>>>(p, pp, m, v, wy, wz, s, (int)ld, i_lo, i_hi, h)
+  // ONE launch over the owned planes [plane_begin, plane_end) of the flattened (slab, i) axis: ~8 waves of resident CTAs, segments
+  // no shorter than 8 planes (each segment re-reads one halo plane)
+  const int64_t planes = plane_end - plane_begin;
+  const int resident = (n_peers >= 4 ? 1 : 2) * kNumSMs;
+  int64_t n_seg = (8 * resident + s.n_jt - 1) / s.n_jt;
+  n_seg = std::max<int64_t>(1, std::min<int64_t>(n_seg, std::max<int64_t>(planes / 8, 1)));
+  s.seg_len = (int)((planes + n_seg - 1) / n_seg);
+  s.n_seg = (int)((planes + s.seg_len - 1) / s.seg_len);
+  const int64_t nb = (int64_t)s.n_jt * s.n_seg;
+  if (nb > 0x7fffffffll || lead * sz_i > 0x7fffffffll) return finish(cudaErrorInvalidValue);
+#define UBN_TP(D, M, N) k_tv_adam_peer<D, M, N><<<(unsigned)nb, kTaThreads, 0, st>>>(p, pp, m, v, wy, wz, s, (int)plane_begin, (int)plane_end, h)
 #define UBN_TPN(D, M)                                     \
-    switch (n_peers) {                                    \
-      case 1: UBN_TP(D, M, 1); break;                     \
-      case 2: UBN_TP(D, M, 2); break;                     \
-      case 4: UBN_TP(D, M, 4); break;                     \
-      default: UBN_TP(D, M, 8); break;                    \
-    }
-    if (dense_mode) { if (adam_mode) { UBN_TPN(true, 1) } else { UBN_TPN(true, 0) } }
-    else            { if (adam_mode) { UBN_TPN(false, 1) } else { UBN_TPN(false, 0) } }
+  switch (n_peers) {                                      \
+    case 1: UBN_TP(D, M, 1); break;                       \
+    case 2: UBN_TP(D, M, 2); break;                       \
+    case 4: UBN_TP(D, M, 4); break;                       \
+    default: UBN_TP(D, M, 8); break;                      \
+  }
+  if (dense_mode) { if (adam_mode) { UBN_TPN(true, 1) } else { UBN_TPN(true, 0) } }
+  else            { if (adam_mode) { UBN_TPN(false, 1) } else { UBN_TPN(false, 0) } }
 #undef UBN_TPN
 #undef UBN_TP
-    UBN_LAUNCH_CHECK();
-  }
+  UBN_LAUNCH_CHECK();
   return 0;
 }
 

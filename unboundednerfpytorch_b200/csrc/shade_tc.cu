@@ -569,6 +569,349 @@ __global__ void __launch_bounds__(kRows, 1) k_shade_bwd_tc(
 }
 
 
+// =====================================================================================================================
+// Fused data-path backward: everything except dW2 in ONE kernel, nothing but dX written back.
+//   dZ2 = (dz3 . W3) * [H2 > 0]        row-owner threads, CUDA cores  -> TMEM (hi / lo), A operand of
+//   dH1 = dZ2 . W2                     TS MMA, B = W2^T K-major panels (as k_shade_bwd_tc)
+//   dZ1 = dH1 * [H1 > 0]               epilogue -> TMEM (hi / lo) again, A operand of
+//   dX  = dZ1 . W1k                    TS MMA with N = 16 (12 used), B = W1k^T K-major panels  -> g_feat
+// and every reduction over SAMPLES that k_shade_bwd_small did in a second pass over dZ1 / H2 (4.2 + 2.1 GB of re-reads, 2.1 GB
+// of dZ1 writes): each warp transposes its 32-row x 32-column chunk through a 4.5 KB staging tile, after which LANE = COLUMN
+// (hidden unit) and the sample sums are plain per-lane loops:
+//   db2[j]  += sum_s dZ2[s][j]               dW3[c][j] += sum_s dz3[s][c] H2[s][j]         (from the staged H2 chunk)
+//   dvb[ray][j] += sum_{s in ray} dZ1[s][j]  dW1k[j][c] += sum_s dZ1[s][j] X[s][c]         (from the staged dZ1 chunk)
+// CTA-level partials live in shared memory and are flushed once.  dZ1 never reaches HBM.
+// TMEM: [0,128) A hi, [128,256) A lo (dZ2, then dZ1), [256,384) dH1, [384,400) dX.
+// =====================================================================================================================
+namespace bf {
+constexpr uint32_t kPanelN16 = 16 * 16;                         // one 16-byte K-slice of the 16 rows of W1k^T
+constexpr uint32_t oVThi = 0;
+constexpr uint32_t oVTlo = oVThi + (kHidden / 4) * kPanelBytes;
+constexpr uint32_t oV1hi = oVTlo + (kHidden / 4) * kPanelBytes;
+constexpr uint32_t oV1lo = oV1hi + (kHidden / 4) * kPanelN16;
+constexpr uint32_t oStgF = oV1lo + (kHidden / 4) * kPanelN16;   // 4 warps x 32 x 36 floats
+constexpr uint32_t oXf = oStgF + 4 * kStgBytesPerWarp;          // [128][12] fp32
+constexpr uint32_t oDz3 = oXf + kRows * kFeat * 4;              // [128][4]
+constexpr uint32_t oRayF = oDz3 + kRows * 16;                   // int[128]
+constexpr uint32_t oW3f = oRayF + kRows * 4;                    // [3][128]
+constexpr uint32_t oAccW1 = oW3f + 3 * kHidden * 4;             // [128][12]
+constexpr uint32_t oAccW3 = oAccW1 + kHidden * kFeat * 4;       // [3][128]
+constexpr uint32_t oAccB2 = oAccW3 + 3 * kHidden * 4;           // [128]
+constexpr uint32_t oAccB3 = oAccB2 + kHidden * 4;               // [4]
+constexpr uint32_t oBarF = oAccB3 + 16;
+constexpr uint32_t kSmemBytesF = oBarF + 16;
+constexpr uint32_t cAhi = 0, cAlo = 128, cDHf = 256, cDX = 384;
+constexpr uint32_t kIdescN16 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(kRows >> 4) << 24);
+}  // namespace bf
+
+__device__ __forceinline__ uint64_t make_desc_lbo(uint32_t smem_addr, uint32_t lbo) {
+  return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(kSBO >> 4) << 32) | (1ull << 46);
+}
+
+__device__ __forceinline__ void mma_ts_idesc(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// 32 lanes x 16 columns
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// stage this warp's 32 x 32 chunk (thread = row) so that afterwards lane = column: stg[row * 36 + col]
+__device__ __forceinline__ void warp_stage_chunk(float* stg, const float4 (&q)[8], int lane) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(stg + lane * kStgStride + i * 4) = q[i];
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(kRows, 1) k_shade_bwd_fused(
+    const float* __restrict__ feat, const int64_t* __restrict__ ray_id, const float* __restrict__ W1k,
+    const float* __restrict__ W2, const float* __restrict__ W3, const float* __restrict__ rgb,
+    const float* __restrict__ h1, const float* __restrict__ h2, const float* __restrict__ g_rgb, int64_t n_pts,
+    float* __restrict__ g_feat, float* __restrict__ g_vb, float* __restrict__ gW1k, float* __restrict__ gb2,
+    float* __restrict__ gW3, float* __restrict__ gb3) {
+  using namespace bf;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float* sW3 = reinterpret_cast<float*>(smem + oW3f);
+  float* sX = reinterpret_cast<float*>(smem + oXf);
+  float4* sDz3 = reinterpret_cast<float4*>(smem + oDz3);
+  int* sRay = reinterpret_cast<int*>(smem + oRayF);
+  float* sAccW1 = reinterpret_cast<float*>(smem + oAccW1);
+  float* sAccW3 = reinterpret_cast<float*>(smem + oAccW3);
+  float* sAccB2 = reinterpret_cast<float*>(smem + oAccB2);
+  float* sAccB3 = reinterpret_cast<float*>(smem + oAccB3);
+  float* stg = reinterpret_cast<float*>(smem + oStgF + warp * kStgBytesPerWarp);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + oBarF);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + oBarF + 8);
+  const uint32_t bar_addr = smem_u32(bar);
+
+  // W2^T as the K-major B operand of dH1[s][k] = sum_j dZ2[s][j] W2[j][k]:  B[n = k][kk = j] = W2[j][k]
+  for (int i = tid; i < kHidden * kHidden; i += kRows) {
+    const int j = i / kHidden, k = i % kHidden;
+    const float w = W2[i];
+    const uint32_t hb = tf32_hi_bits(w);
+    const uint32_t off = (uint32_t)(j >> 2) * kPanelBytes + (uint32_t)k * 16 + (uint32_t)(j & 3) * 4;
+    *reinterpret_cast<uint32_t*>(smem + oVThi + off) = hb;
+    *reinterpret_cast<float*>(smem + oVTlo + off) = w - __uint_as_float(hb);
+  }
+  // W1k^T as the K-major B operand of dX[s][c] = sum_j dZ1[s][j] W1k[j][c]:  B[n = c][kk = j] = W1k[j][c], rows 12..15 zero
+  for (int i = tid; i < kHidden * 16; i += kRows) {
+    const int j = i >> 4, c = i & 15;
+    const float w = (c < kFeat) ? W1k[j * kFeat + c] : 0.f;
+    const uint32_t hb = tf32_hi_bits(w);
+    const uint32_t off = (uint32_t)(j >> 2) * kPanelN16 + (uint32_t)c * 16 + (uint32_t)(j & 3) * 4;
+    *reinterpret_cast<uint32_t*>(smem + oV1hi + off) = hb;
+    *reinterpret_cast<float*>(smem + oV1lo + off) = w - __uint_as_float(hb);
+  }
+  for (int i = tid; i < 3 * kHidden; i += kRows) { sW3[i] = W3[i]; sAccW3[i] = 0.f; }
+  for (int i = tid; i < kHidden * kFeat; i += kRows) sAccW1[i] = 0.f;
+  sAccB2[tid] = 0.f;
+  if (tid < 4) sAccB3[tid] = 0.f;
+  if (tid == 0) {
+    mbar_init(bar_addr, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+  uint32_t phase = 0;
+  const uint64_t dWThi = make_desc(smem_u32(smem + oVThi)), dWTlo = make_desc(smem_u32(smem + oVTlo));
+  const uint64_t dW1hi = make_desc_lbo(smem_u32(smem + oV1hi), kPanelN16), dW1lo = make_desc_lbo(smem_u32(smem + oV1lo), kPanelN16);
+  constexpr uint64_t kStepK = (uint64_t)((2 * kPanelBytes) >> 4);
+  constexpr uint64_t kStepK16 = (uint64_t)((2 * kPanelN16) >> 4);
+  float b3a = 0.f, b3b = 0.f, b3c = 0.f;      // db3 partial of this thread's rows
+
+  const int64_t n_tiles = (n_pts + kRows - 1) / kRows;
+  const int64_t per_cta = (n_tiles + gridDim.x - 1) / gridDim.x;
+  const int64_t tile_end = min(n_tiles, (int64_t)(blockIdx.x + 1) * per_cta);
+  for (int64_t tile = (int64_t)blockIdx.x * per_cta; tile < tile_end; ++tile) {
+    const int64_t row = tile * kRows + tid;
+    const bool live = row < n_pts;
+    float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+    int my_ray = -1;
+    {
+      float4 x0 = make_float4(0, 0, 0, 0), x1 = x0, x2 = x0;
+      if (live) {
+        const float* o = rgb + row * 3;
+        const float* g = g_rgb + row * 3;
+        d0 = g[0] * (o[0] * (1.f - o[0]));
+        d1 = g[1] * (o[1] * (1.f - o[1]));
+        d2 = g[2] * (o[2] * (1.f - o[2]));
+        my_ray = (int)ray_id[row];
+        const float4* xr = reinterpret_cast<const float4*>(feat + row * kFeat);
+        x0 = __ldg(xr); x1 = __ldg(xr + 1); x2 = __ldg(xr + 2);
+      }
+      sDz3[tid] = make_float4(d0, d1, d2, 0.f);
+      sRay[tid] = my_ray;
+      float4* xs = reinterpret_cast<float4*>(sX + tid * kFeat);
+      xs[0] = x0; xs[1] = x1; xs[2] = x2;
+      b3a += d0; b3b += d1; b3c += d2;
+    }
+    // ---- H2 row: dZ2 -> TMEM, and (staged, lane = column) db2 / dW3 ----
+    float4 hrow[kHidden / 4];
+#pragma unroll
+    for (int q = 0; q < kHidden / 4; ++q) {
+      hrow[q] = make_float4(0, 0, 0, 0);
+      if (live) hrow[q] = __ldg(reinterpret_cast<const float4*>(h2 + row * kHidden + q * 4));
+    }
+    __syncwarp();      // sDz3 / sRay / sX rows of this warp are complete (each warp only reads its own 32 rows)
+#pragma unroll
+    for (int c = 0; c < kHidden / 32; ++c) {
+      uint32_t hi[32], lo[32];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 hv = hrow[c * 8 + q];
+        const float4 wa = *reinterpret_cast<const float4*>(sW3 + c * 32 + q * 4);
+        const float4 wb = *reinterpret_cast<const float4*>(sW3 + kHidden + c * 32 + q * 4);
+        const float4 wc = *reinterpret_cast<const float4*>(sW3 + 2 * kHidden + c * 32 + q * 4);
+        const float z[4] = {hv.x > 0.f ? fmaf(d2, wc.x, fmaf(d1, wb.x, d0 * wa.x)) : 0.f,
+                            hv.y > 0.f ? fmaf(d2, wc.y, fmaf(d1, wb.y, d0 * wa.y)) : 0.f,
+                            hv.z > 0.f ? fmaf(d2, wc.z, fmaf(d1, wb.z, d0 * wa.z)) : 0.f,
+                            hv.w > 0.f ? fmaf(d2, wc.w, fmaf(d1, wb.w, d0 * wa.w)) : 0.f};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const uint32_t hb = tf32_hi_bits(z[e]);
+          hi[q * 4 + e] = hb;
+          lo[q * 4 + e] = __float_as_uint(z[e] - __uint_as_float(hb));
+        }
+      }
+      tmem_st32(tmem + lane_base + cAhi + c * 32, hi);
+      tmem_st32(tmem + lane_base + cAlo + c * 32, lo);
+      // lane = hidden unit j of this chunk: sums over the warp's 32 samples
+      {
+        float4 q8[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) q8[q] = hrow[c * 8 + q];
+        warp_stage_chunk(stg, q8, lane);
+        const int j = c * 32 + lane;
+        const float w3a = sW3[j], w3b = sW3[kHidden + j], w3c = sW3[2 * kHidden + j];
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, ab = 0.f;
+#pragma unroll 8
+        for (int sidx = 0; sidx < 32; ++sidx) {
+          const float h = stg[sidx * kStgStride + lane];
+          const float4 dz = sDz3[warp * 32 + sidx];
+          a0 = fmaf(dz.x, h, a0); a1 = fmaf(dz.y, h, a1); a2 = fmaf(dz.z, h, a2);
+          ab += h > 0.f ? fmaf(dz.z, w3c, fmaf(dz.y, w3b, dz.x * w3a)) : 0.f;
+        }
+        atomicAdd(sAccW3 + j, a0); atomicAdd(sAccW3 + kHidden + j, a1); atomicAdd(sAccW3 + 2 * kHidden + j, a2);
+        atomicAdd(sAccB2 + j, ab);
+        __syncwarp();
+      }
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    __syncthreads();
+    // ---- dH1 = dZ2 . W2 ----
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll 4
+      for (int ks = 0; ks < kHidden / 8; ++ks) {
+        mma_ts(tmem + cDHf, tmem + cAhi + ks * 8, dWThi + ks * kStepK, ks > 0);
+        mma_ts(tmem + cDHf, tmem + cAlo + ks * 8, dWThi + ks * kStepK, 1);
+        mma_ts(tmem + cDHf, tmem + cAhi + ks * 8, dWTlo + ks * kStepK, 1);
+      }
+      mma_commit(bar_addr);
+    }
+#pragma unroll
+    for (int q = 0; q < kHidden / 4; ++q) {
+      hrow[q] = make_float4(0, 0, 0, 0);
+      if (live) hrow[q] = __ldg(reinterpret_cast<const float4*>(h1 + row * kHidden + q * 4));
+    }
+    // is the whole warp inside one ray?  (the common case: 128-sample tiles, hundreds of samples per ray)
+    const int ray0 = __shfl_sync(0xffffffffu, my_ray, 0);
+    const bool one_ray = __all_sync(0xffffffffu, my_ray == ray0) && ray0 >= 0;
+    mbar_wait(bar_addr, phase);
+    phase ^= 1;
+    tc_fence_after();
+    // ---- dZ1 = dH1 * [H1 > 0]: -> TMEM (A of the dX MMA); staged: dvb, dW1k ----
+#pragma unroll
+    for (int c = 0; c < kHidden / 32; ++c) {
+      float v[32];
+      tmem_ld32(tmem + lane_base + cDHf + c * 32, v);
+      uint32_t hi[32], lo[32];
+      float4 q8[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 hv = hrow[c * 8 + q];
+        q8[q].x = hv.x > 0.f ? v[q * 4] : 0.f; q8[q].y = hv.y > 0.f ? v[q * 4 + 1] : 0.f;
+        q8[q].z = hv.z > 0.f ? v[q * 4 + 2] : 0.f; q8[q].w = hv.w > 0.f ? v[q * 4 + 3] : 0.f;
+        const float zs[4] = {q8[q].x, q8[q].y, q8[q].z, q8[q].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const uint32_t hb = tf32_hi_bits(zs[e]);
+          hi[q * 4 + e] = hb;
+          lo[q * 4 + e] = __float_as_uint(zs[e] - __uint_as_float(hb));
+        }
+      }
+      tmem_st32(tmem + lane_base + cAhi + c * 32, hi);      // the dH1 MMA has completed: the dZ2 operand columns are free
+      tmem_st32(tmem + lane_base + cAlo + c * 32, lo);
+      warp_stage_chunk(stg, q8, lane);
+      const int j = c * 32 + lane;
+      // dvb[ray][j]: per-ray sums of column j over the warp's rows (rows are sorted by ray)
+      if (one_ray) {
+        float sum = 0.f;
+#pragma unroll 8
+        for (int sidx = 0; sidx < 32; ++sidx) sum += stg[sidx * kStgStride + lane];
+        atomicAdd(g_vb + (int64_t)ray0 * kHidden + j, sum);
+      } else {
+        float run = 0.f;
+        int run_ray = -1;
+        for (int sidx = 0; sidx < 32; ++sidx) {
+          const int r = sRay[warp * 32 + sidx];          // warp-uniform
+          if (r != run_ray) {
+            if (run_ray >= 0) atomicAdd(g_vb + (int64_t)run_ray * kHidden + j, run);
+            run_ray = r;
+            run = 0.f;
+          }
+          run += stg[sidx * kStgStride + lane];
+        }
+        if (run_ray >= 0) atomicAdd(g_vb + (int64_t)run_ray * kHidden + j, run);
+      }
+      // dW1k[j][0..11] += sum_s dZ1[s][j] X[s][0..11]
+      float acc[kFeat];
+#pragma unroll
+      for (int k = 0; k < kFeat; ++k) acc[k] = 0.f;
+#pragma unroll 4
+      for (int sidx = 0; sidx < 32; ++sidx) {
+        const float d = stg[sidx * kStgStride + lane];
+        const float4* xs = reinterpret_cast<const float4*>(sX + (warp * 32 + sidx) * kFeat);
+        const float4 xa = xs[0], xb = xs[1], xc = xs[2];
+        acc[0] = fmaf(d, xa.x, acc[0]); acc[1] = fmaf(d, xa.y, acc[1]); acc[2] = fmaf(d, xa.z, acc[2]); acc[3] = fmaf(d, xa.w, acc[3]);
+        acc[4] = fmaf(d, xb.x, acc[4]); acc[5] = fmaf(d, xb.y, acc[5]); acc[6] = fmaf(d, xb.z, acc[6]); acc[7] = fmaf(d, xb.w, acc[7]);
+        acc[8] = fmaf(d, xc.x, acc[8]); acc[9] = fmaf(d, xc.y, acc[9]); acc[10] = fmaf(d, xc.z, acc[10]); acc[11] = fmaf(d, xc.w, acc[11]);
+      }
+#pragma unroll
+      for (int k = 0; k < kFeat; ++k) atomicAdd(sAccW1 + j * kFeat + k, acc[k]);
+      __syncwarp();
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    __syncthreads();
+    // ---- dX = dZ1 . W1k  (N = 16) ----
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll 4
+      for (int ks = 0; ks < kHidden / 8; ++ks) {
+        mma_ts_idesc(tmem + cDX, tmem + cAhi + ks * 8, dW1hi + ks * kStepK16, kIdescN16, ks > 0);
+        mma_ts_idesc(tmem + cDX, tmem + cAlo + ks * 8, dW1hi + ks * kStepK16, kIdescN16, 1);
+        mma_ts_idesc(tmem + cDX, tmem + cAhi + ks * 8, dW1lo + ks * kStepK16, kIdescN16, 1);
+      }
+      mma_commit(bar_addr);
+    }
+    mbar_wait(bar_addr, phase);
+    phase ^= 1;
+    tc_fence_after();
+    {
+      float v[16];
+      tmem_ld16(tmem + lane_base + cDX, v);
+      if (live) {
+        float4* o = reinterpret_cast<float4*>(g_feat + row * kFeat);
+        o[0] = make_float4(v[0], v[1], v[2], v[3]);
+        o[1] = make_float4(v[4], v[5], v[6], v[7]);
+        o[2] = make_float4(v[8], v[9], v[10], v[11]);
+      }
+    }
+    tc_fence_before();
+    __syncthreads();     // TMEM reads done, smem row tables free for the next tile
+  }
+
+  // ---- flush the CTA partials ----
+  atomicAdd(sAccB3 + 0, b3a); atomicAdd(sAccB3 + 1, b3b); atomicAdd(sAccB3 + 2, b3c);
+  __syncthreads();
+  for (int i = tid; i < kHidden * kFeat; i += kRows) atomicAdd(gW1k + i, sAccW1[i]);
+  for (int i = tid; i < 3 * kHidden; i += kRows) atomicAdd(gW3 + i, sAccW3[i]);
+  atomicAdd(gb2 + tid, sAccB2[tid]);
+  if (tid < 3) atomicAdd(gb3 + tid, sAccB3[tid]);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+  }
+}
+
+
 // ---- dW2 += dZ2^T . H1 as its own split-K GEMM ----------------------------------------------------------------------
 // Round = 32 consecutive samples.  Warp w stages rows 4w..4w+3; lane l serves row (l & 3) and hidden units j = 8*jj + (l >> 2)
 // (jj < 16): for one store instruction the 32 lanes hit 32 distinct banks of one K-major panel (conflict free).
@@ -750,6 +1093,33 @@ extern "C" int ubn_rgbnet_bwd_tc_data(const float* W2, const float* W3, const fl
     if (e != cudaSuccess) return finish(e);
     tc::k_shade_dw2_tc<<<grid, tc::dw::kThreadsDW, tc::dw::kSmemBytesD, st>>>(W3, rgb, h1_save, h2_save, grad_rgb, n_pts,
                                                                              grad_W2);
+    UBN_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+
+extern "C" int ubn_rgbnet_bwd_tc_fused(const float* feat, const int64_t* ray_id, const float* W1k, const float* W2, const float* W3,
+                                       const float* rgb, const float* h1_save, const float* h2_save, const float* grad_rgb,
+                                       int64_t n_pts, float* grad_feat, float* grad_view_bias, float* grad_W1k, float* grad_W2,
+                                       float* grad_b2, float* grad_W3, float* grad_b3, void* stream) {
+  if (n_pts <= 0) return 0;
+  cudaStream_t st = as_stream(stream);
+  {   // dX + every sample reduction except dW2
+    const int64_t n_tiles = (n_pts + tc::kRows - 1) / tc::kRows;
+    const unsigned grid = (unsigned)std::min<int64_t>(kNumSMs, n_tiles);
+    cudaError_t e = cudaFuncSetAttribute(tc::k_shade_bwd_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::bf::kSmemBytesF);
+    if (e != cudaSuccess) return finish(e);
+    tc::k_shade_bwd_fused<<<grid, tc::kRows, tc::bf::kSmemBytesF, st>>>(feat, ray_id, W1k, W2, W3, rgb, h1_save, h2_save, grad_rgb, n_pts,
+                                                                        grad_feat, grad_view_bias, grad_W1k, grad_b2, grad_W3, grad_b3);
+    UBN_LAUNCH_CHECK();
+  }
+  {   // dW2 (split-K GEMM over all samples)
+    const int64_t n_rounds = (n_pts + tc::dw::kK - 1) / tc::dw::kK;
+    const unsigned grid = (unsigned)std::min<int64_t>((int64_t)kNumSMs * tc::dw::kCtasPerSM, n_rounds);
+    cudaError_t e = cudaFuncSetAttribute(tc::k_shade_dw2_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::dw::kSmemBytesD);
+    if (e != cudaSuccess) return finish(e);
+    tc::k_shade_dw2_tc<<<grid, tc::dw::kThreadsDW, tc::dw::kSmemBytesD, st>>>(W3, rgb, h1_save, h2_save, grad_rgb, n_pts, grad_W2);
     UBN_LAUNCH_CHECK();
   }
   return 0;
