@@ -272,13 +272,133 @@ def tune_cpu_reference(flavor, kwargs, stepsize, cores, n_steps, max_rays, budge
 
 
 # ----------------------------------------------------------------------------------------------------------
+FRAME_HW = (1067, 1600)      # Mip-NeRF-360 'garden' at the resolution BASELINE config 4 names
+
+
+def frame_rays(dev, H, W):
+    """One pinhole view (focal = W) from inside the unit scene, rays built on the device (ray_gen.cu)."""
+    import numpy as np
+    from unboundednerfpytorch_b200 import rays as R
+    K = np.array([[float(W), 0, W / 2], [0, float(W), H / 2], [0, 0, 1]], dtype=np.float64)
+    c2w = torch.tensor([[1., 0., 0., 0.15], [0., 1., 0., -0.10], [0., 0., 1., 0.35]])
+    ro, rd, vd = R._rays_of_a_view(H, W, K, c2w, False, False, False, False, 'center', device=dev)
+    return ro.view(-1, 3), rd.view(-1, 3), vd.view(-1, 3)
+
+
+def block_model(seed, dev):
+    from unboundednerfpytorch_b200 import models
+    flavor, kwargs, stepsize = workload_kwargs('bicycle')
+    torch.manual_seed(seed)
+    m = models.DirectContractedVoxGO(**kwargs).to(dev)
+    g = torch.Generator(device=dev).manual_seed(seed)
+    with torch.no_grad():
+        m.density.grid.copy_(torch.randn(m.density.grid.shape, generator=g, device=dev))
+        m.k0.grid.copy_(torch.randn(m.k0.grid.shape, generator=g, device=dev))
+    return m, stepsize
+
+
+def render_workload(args, emit):
+    """BASELINE configs 4 and 5 (forward only, strong scaling: the frame is fixed, the ranks divide it / hold one block each).
+    garden:     one 1600x1067 frame = 1 707 200 rays in 8192-ray chunks (run_render.py:56), DCVGO 320^3 + 12-ch k0 + rgbnet
+                replicated, contiguous ray shards per rank, one all-gather of [rays, 5] (render.render_frame_sharded).
+    missionbay: one block model per rank (seed 777 + rank, centroid on a line through the scene), every rank renders the
+                whole frame, visibility gate + inverse-distance-weighted composite in one all-reduce (render.render_blocks_idw;
+                eval_block_nerf.py:95-133, :215-216).  Rank 0 afterwards checks the composite against a single-GPU loop over all
+                block models (outside the timed region)."""
+    from unboundednerfpytorch_b200 import dist as ubdist, render as RD
+    rank, world, local = ubdist.init_from_env()
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    H, W = FRAME_HW
+    ro, rd, vd = frame_rays(dev, H, W)
+    n_rays = ro.shape[0]
+    rk = dict(near=0., far=1e9, bg=1, rand_bkgd=False, stepsize=1.045)
+    if args.workload == 'garden':
+        model, _ = block_model(SEED, dev)
+        fn = lambda: RD.render_frame_sharded(model, ro, rd, vd, rk)
+    else:
+        model, _ = block_model(SEED + rank, dev)
+        cen = lambda r: [(-0.7 + 1.4 * r / max(world - 1, 1)) if world > 1 else 0.0, 0.0, 0.0]
+        fn = lambda: RD.render_blocks_idw(model, ro, rd, vd, rk, centroid=cen(rank), cam_origin=ro[0])
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    for _ in range(max(args.warmup, 1)):
+        out = fn()
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    clocks.mark()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = fn()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+    ms_frame = ms.item() / args.steps
+    clk = clocks.stop() if rank == 0 else None
+    check = {}
+    if args.workload == 'garden':
+        frame = out['rgb_marched']
+        # rank 0 re-renders three chunks that other ranks produced: the gathered frame must equal a local render bit for bit
+        if rank == 0:
+            worst = 0.0
+            for c in (0, (n_rays // 8192) // 2, n_rays // 8192 - 1):
+                sl = slice(c * 8192, min((c + 1) * 8192, n_rays))
+                loc = RD.render_rays(model, ro[sl], rd[sl], vd[sl], rk)['rgb_marched']
+                worst = max(worst, float((loc - frame[sl]).abs().max()))
+            check = {'gathered_vs_local_max_abs': worst, 'frame_mean': float(frame.mean())}
+    else:
+        frame, info = out
+        if world > 1:
+            vis = torch.zeros(world, device=dev)
+            vis[rank] = info['visible'].float()
+            torch.distributed.all_reduce(vis)
+        if rank == 0:
+            num = torch.zeros(n_rays, 3, device=dev)
+            den = torch.zeros((), device=dev)
+            for r in range(world):                       # single-GPU restatement: loop over all block models on this GPU
+                mb, _ = block_model(SEED + r, dev)
+                o = RD.render_rays(mb, ro, rd, vd, rk, keys=('rgb_marched', 'alphainv_last'))
+                v = ((1.0 - o['alphainv_last']).mean() > 0.05).float()
+                w = (ro[0] - torch.tensor(cen(r), device=dev)).norm().clamp_min(1e-8).pow(-4) * v
+                num += o['rgb_marched'] * w
+                den += w
+                del mb
+            want = num / den.clamp_min(1e-30)
+            check = {'composite_vs_single_gpu_loop_max_abs': float((frame - want).abs().max()), 'frame_mean': float(frame.mean()),
+                     'visible_blocks': int(vis.sum()) if world > 1 else int(info['visible'])}
+    if rank == 0:
+        rays_total = n_rays * (world if args.workload == 'missionbay' else 1)
+        emit({'metric': 'rays/sec (render, fwd only, 512 samples per ray)', 'value': rays_total / (ms_frame * 1e-3), 'unit': 'rays/s',
+              'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_frame, 'higher_is_better': True,
+              'scaling': 'strong' if args.workload == 'garden' else 'weak (one block model per GPU, same frame)',
+              'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+              'config': {'workload': f'{args.workload}: DCVGO 320^3 DenseGrid + 12-ch k0 + rgbnet, one {W}x{H} frame = {n_rays} rays in '
+                                     f'8192-ray chunks, 512 samples per ray, dense mode (thres=0)',
+                         'step': 'one full frame (render, forward only)' + (' + IDW composite all-reduce' if args.workload == 'missionbay'
+                                                                          else ' + frame all-gather'),
+                         'parallelism': (f'rays sharded contiguously over {world} GPUs, grids replicated' if args.workload == 'garden'
+                                         else f'{world} block models, one per GPU'),
+                         'l2_policy': 'inputs larger than L2 (1.7 GB of grids)'},
+              'ray_samples_per_s': rays_total * N_SAMPLES / (ms_frame * 1e-3), 'clocks': clk, 'check': check})
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference', 'reference-gpu'])
-    ap.add_argument('--workload', default='truck', choices=['truck', 'bicycle'])
+    ap.add_argument('--workload', default='truck', choices=['truck', 'bicycle', 'garden', 'missionbay'])
     ap.add_argument('--cpu-rays', type=int, default=1024, help='upper bound of the ray sample of the CPU legs (shrunk to fit the time budget)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--only-timed', action='store_true', help='warm-up + timed region only (for ncu captures)')
@@ -293,6 +413,13 @@ def main():
     def emit(obj):
         os.write(json_fd, (json.dumps(obj) + '\n').encode())
 
+    if args.workload in ('garden', 'missionbay'):
+        if args.impl != 'ours':
+            if int(os.environ.get('RANK', '0')) == 0:
+                emit({'impl': args.impl, 'unavailable': 'the reference arm is defined for the training workloads (truck / bicycle) only'})
+            return
+        args.steps = min(args.steps, 5)
+        return render_workload(args, emit)
     from unboundednerfpytorch_b200 import dist as ubdist
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
