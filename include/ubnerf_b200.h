@@ -239,6 +239,30 @@ int ubn_grid_sample_fwd(const float* grid, const UbnGridDesc* desc, const float*
 int ubn_grid_sample_bwd(const float* grad_out, const UbnGridDesc* desc, const float* xyz, int64_t n_pts,
                         float* grad_grid, void* stream);
 
+/* ---- grid-native occupancy / progressive-growing utilities ---------------------------------------------
+ * The reference builds these from whole-grid torch ops (meshgrid + grid_sample + max_pool3d, F.interpolate, an autograd backward
+ * per 10 000 rays); each is one or two kernels here, lattice / sample coordinates generated in registers. */
+
+/* update_occupancy_cache, step 1 (FourierGrid_model.py:443-450, dcvgo.py:216-222): alpha[i,j,k] = Raw2Alpha(density(p_ijk)),
+ * p = lattice of linspace(lattice_min[a], lattice_max[a], m_a) points (HOST float[3] arrays), density = C = 1 grid `desc`. */
+int ubn_lattice_alpha(const float* grid, const UbnGridDesc* desc, const float* lattice_min, const float* lattice_max, int64_t mX,
+                      int64_t mY, int64_t mZ, float act_shift, float interval, float* alpha, void* stream);
+/* step 2 (:451-452): mask &= F.max_pool3d(alpha, kernel 3, stride 1, padding 1) > thres.  mask: torch.bool bytes [X,Y,Z]. */
+int ubn_maxpool3_gt_and(const float* alpha, int64_t X, int64_t Y, int64_t Z, float thres, uint8_t* mask, void* stream);
+/* scale_volume_grid (grid.py:63-68, FourierGrid_grid.py:80-85): out = F.interpolate(in, size = out dims, mode = 'trilinear',
+ * align_corners = True) for every slab / channel; either layout on either side (strides from the descriptors). */
+int ubn_resample_grid(const float* in, const UbnGridDesc* in_desc, float* out, const UbnGridDesc* out_desc, void* stream);
+/* voxel_count_views inner loop (FourierGrid_model.py:405-417, dvgo.py:255-270): grad += adjoint of DenseGrid(1, dims)(pts).sum() for
+ * pts = o + d * (t_min + step * i / |d|), i < n_samples, t_min from the AABB of `desc` clamped to [near, far]; grad: [X,Y,Z]. */
+int ubn_view_scatter_ones(const float* rays_o, const float* rays_d, int64_t n_rays, int64_t n_samples, float near, float far,
+                          float step, const UbnGridDesc* desc, float* grad, void* stream);
+/* count += (grad > thres)      (:418-419 `count += (ones.grid.grad > 1)`) */
+int ubn_count_gt(const float* grad, float thres, int64_t n, float* count, void* stream);
+/* maskout_near_cam_vox (FourierGrid_model.py:375-388): slab[v] = fill where min_c |lattice(v) - cams[c]| <= near_clip, lattice =
+ * linspace(-1, 1, size) per axis, cams [n_cams, 3] device array already in the slab's (embedded, flipped) coordinates. */
+int ubn_maskout_near_cam(float* slab, int64_t voxel_stride, int64_t X, int64_t Y, int64_t Z, const float* cams, int64_t n_cams,
+                         float near_clip, float fill, void* stream);
+
 /* ---- fused ray march: sample_ray + density query + Raw2Alpha + Alphas2Weights + thresholds + k0 query
  *      for FourierGridModel.forward (FourierGrid_model.py:509-621) and DirectContractedVoxGO.forward
  *      (dcvgo.py:228-331) ------------------------------------------------------------------------ */

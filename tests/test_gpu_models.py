@@ -234,14 +234,16 @@ def test_fused_rgbnet_vs_torch(mode, monkeypatch):
 
 
 def test_progressive_growing_and_occupancy_utilities(oracle):
-    """scale_volume_grid / update_occupancy_cache / voxel_count_views / hit_coarse_geo are consumers of
-    the trilinear read and of its adjoint; check them against torch-CPU restatements."""
+    """scale_volume_grid / update_occupancy_cache / voxel_count_views / maskout_near_cam_vox / hit_coarse_geo as
+    grid-native kernels (csrc/grid_utils.cu), each against the reference's own torch composition (FourierGrid_model.py:375-456)
+    evaluated with torch ops on the same GPU: masks and counts element for element, resampled grids to fp32 rounding."""
     import torch.nn.functional as F
     from unboundednerfpytorch_b200 import grid as G
     m, kw = _fresh_model('fouriergrid', 24, 2, 1e-4, 5, dens_mean=1.0, dens_std=3.0)
     m = m.to(DEV)
     g = torch.Generator().manual_seed(11)
-    # voxel_count_views: adjoint-of-ones counting vs torch F.grid_sample autograd on CPU
+
+    # ---- voxel_count_views vs the reference composition on torch-CPU autograd (oracle.dense_grid_forward = F.grid_sample) ----
     H = W = 12
     ro = (torch.rand(2 * H, W, 3, generator=g) - 0.5)
     rd = torch.randn(2 * H, W, 3, generator=g)
@@ -260,18 +262,57 @@ def test_progressive_growing_and_occupancy_utilities(oracle):
         pts = o_[..., None, :] + d_[..., None, :] * interpx[..., None]
         oracle.dense_grid_forward(ones, pts, m.xyz_min.cpu(), m.xyz_max.cpu()).sum().backward()
         ref += (ones.grad > 1)
+    assert cnt.shape == ref.shape and float(cnt.max()) == 2.0
     mism = (cnt.cpu() != ref).float().mean().item()
-    assert mism < 2e-3, mism            # voxels whose accumulated weight sits within float noise of the threshold 1
-    # scale_volume_grid keeps the layout contract and matches F.interpolate on CPU
-    before = m.k0.grid.detach().cpu().contiguous()
+    assert mism < 2e-4, mism            # voxels whose accumulated weight sits within float noise of the threshold 1
+
+    # ---- scale_volume_grid: layout contract + F.interpolate (ATen upsample_trilinear3d) on the same device ----
+    before_k0 = m.k0.grid.detach().clone()
+    before_d = m.density.grid.detach().clone()
     m.scale_volume_grid(30 ** 3, 30 ** 3)
-    want = F.interpolate(before, size=tuple(int(v) for v in m.world_size_rgb), mode='trilinear', align_corners=True)
-    assert m.k0.grid.stride()[1] == 1
-    assert_close(m.k0.grid, want, rtol=1e-5, atol=1e-6, what='scale_volume_grid')
-    # occupancy cache update only ever clears cells, and the render still runs afterwards
+    size = tuple(int(v) for v in m.world_size_rgb)
+    want_k0 = F.interpolate(before_k0.contiguous(), size=size, mode='trilinear', align_corners=True)
+    want_d = F.interpolate(before_d.contiguous(), size=size, mode='trilinear', align_corners=True)
+    assert m.k0.grid.stride()[1] == 1 and m.k0.grid.shape == want_k0.shape
+    assert_close(m.k0.grid, want_k0, rtol=1e-6, atol=1e-6, what='scale_volume_grid k0')
+    assert_close(m.density.grid, want_d, rtol=1e-6, atol=1e-6, what='scale_volume_grid density')
+
+    # ---- update_occupancy_cache: the reference's meshgrid -> density -> activate -> max_pool3d -> AND, in torch ops ----
+    with torch.no_grad():
+        m.mask_cache.mask.copy_(torch.rand(m.mask_cache.mask.shape, generator=g) > 0.2)
     occ0 = m.mask_cache.mask.clone()
+    ms = occ0.shape
+    axes = [torch.linspace(float(m.xyz_min[a]), float(m.xyz_max[a]), ms[a], device=DEV) for a in range(3)]
+    xyz = torch.stack(torch.meshgrid(*axes, indexing='ij'), -1)
+    with torch.no_grad():
+        alpha = F.max_pool3d(m.activate_density(m.density(xyz)[None, None]), kernel_size=3, padding=1, stride=1)[0, 0]
+    want_mask = occ0 & (alpha > m.fast_color_thres)
     m.update_occupancy_cache()
     assert (m.mask_cache.mask & ~occ0).sum() == 0
+    flips = int((m.mask_cache.mask != want_mask).sum())
+    assert flips <= 1e-4 * want_mask.numel(), f'{flips} cells differ from the torch composition'
+    assert 0.05 < float(m.mask_cache.mask.float().mean()) < 0.95, 'degenerate occupancy test scene'
+
+    # ---- maskout_near_cam_vox vs the reference loop (FourierGrid_model.py:375-388) in torch ops ----
+    cams = (torch.rand(23, 3, generator=g) - 0.5).to(DEV)
+    near_clip = 0.35
+    want_grid = m.density.grid.detach().clone().contiguous()
+    ind_norm = ((cams - m.xyz_min) / (m.xyz_max - m.xyz_min)).flip((-1,)) * 2 - 1
+    F_ = m.density.nerf_pos_num_freq
+    freqs = 2 ** torch.linspace(0, F_ - 1, F_, device=DEV)
+    emb = [ind_norm] + [f(fr * ind_norm) for fr in freqs for f in (torch.sin, torch.cos)]
+    wsd = [int(v) for v in m.world_size_density]
+    lat = torch.stack(torch.meshgrid(*[torch.linspace(-1, 1, wsd[a], device=DEV) for a in range(3)], indexing='ij'), -1)
+    for i, cam in enumerate(emb):
+        nearest = torch.stack([(lat.unsqueeze(-2) - co).pow(2).sum(-1).sqrt().amin(-1) for co in cam.split(10)]).amin(0)
+        want_grid[0][i][nearest <= near_clip] = -100
+    m.maskout_near_cam_vox(cams, near_clip)
+    n_hit = int((want_grid == -100).sum())
+    assert n_hit > 0
+    diff = int((m.density.grid.detach() != want_grid).sum())
+    assert diff <= 1e-4 * want_grid.numel(), f'{diff} voxels differ from the reference loop ({n_hit} masked)'
+
+    # the model still renders, and hit_coarse_geo has the reference's shape / dtype contract
     ro1, rd1, vd1 = seeded_rays(64, 3, DEV)
     out = m(ro1, rd1, vd1, near=0., far=1e9, bg=1, rand_bkgd=False, stepsize=0.5)
     assert torch.isfinite(out['rgb_marched']).all()

@@ -70,6 +70,12 @@ _SIGNATURES = {
                              c_f, c_f, c_f, c_f, c_int, c_int, c_p],
     'ubn_tv_adam_peer': [c_p, c_p, c_p, c_int, c_p, c_p, c_f, c_f, c_f, c_i64, c_i64, c_i64, c_i64, c_i64, c_int, c_i64, c_i64,
                          c_int, c_f, c_f, c_f, c_f, c_int, c_p],
+    'ubn_lattice_alpha': [c_p, ctypes.POINTER(UbnGridDesc), c_p, c_p, c_i64, c_i64, c_i64, c_f, c_f, c_p, c_p],
+    'ubn_maxpool3_gt_and': [c_p, c_i64, c_i64, c_i64, c_f, c_p, c_p],
+    'ubn_resample_grid': [c_p, ctypes.POINTER(UbnGridDesc), c_p, ctypes.POINTER(UbnGridDesc), c_p],
+    'ubn_view_scatter_ones': [c_p, c_p, c_i64, c_i64, c_f, c_f, c_f, ctypes.POINTER(UbnGridDesc), c_p, c_p],
+    'ubn_count_gt': [c_p, c_f, c_i64, c_p, c_p],
+    'ubn_maskout_near_cam': [c_p, c_i64, c_i64, c_i64, c_i64, c_p, c_i64, c_f, c_f, c_p],
     'ubn_cumdist_thres': [c_p, c_f, c_i64, c_i64, c_p, c_p],
     'ubn_get_rays_of_a_view': [c_int, c_int, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_p, c_p, c_p, c_p, c_p],
     'ubn_gather_rays': [c_p, c_p, c_int, c_p, c_i64, c_i64, c_p, c_p],

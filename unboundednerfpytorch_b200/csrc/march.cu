@@ -24,19 +24,7 @@
 
 namespace ubn {
 
-__device__ __forceinline__ float grid_density(const GridView& g, float x, float y, float z) {
-  const float nx = norm_coord(x, g.mn[0], g.len[0]);
-  const float ny = norm_coord(y, g.mn[1], g.len[1]);
-  const float nz = norm_coord(z, g.mn[2], g.len[2]);
-  SlabMean acc;
-  for (int s = 0; s < g.P; ++s) {
-    const float cx = src_index(fourier_gamma(s, nx), g.X);
-    const float cy = src_index(fourier_gamma(s, ny), g.Y);
-    const float cz = src_index(fourier_gamma(s, nz), g.Z);
-    acc.add(s, trilerp1(g.data + s * g.sp, g.sv, g.X, g.Y, g.Z, cx, cy, cz));
-  }
-  return acc.mean(g.P);
-}
+__device__ __forceinline__ float grid_density(const GridView& g, float x, float y, float z) { return grid_density_at(g, x, y, z); }
 
 // ------------------------------------------------------------------------------------------------
 // pass A forward

@@ -119,6 +119,22 @@ __device__ __forceinline__ float trilerp1(const float* __restrict__ slab, int64_
   return acc;
 }
 
+// single-channel grid value at world position (x, y, z): mean over the P slabs of the trilinear reads at gamma_s(normalised coords)
+// -- DenseGrid.forward (grid.py:50-61) for P = 1, FourierGrid.forward (FourierGrid_grid.py:60-78) otherwise
+__device__ __forceinline__ float grid_density_at(const GridView& g, float x, float y, float z) {
+  const float nx = norm_coord(x, g.mn[0], g.len[0]);
+  const float ny = norm_coord(y, g.mn[1], g.len[1]);
+  const float nz = norm_coord(z, g.mn[2], g.len[2]);
+  SlabMean acc;
+  for (int s = 0; s < g.P; ++s) {
+    const float cx = src_index(fourier_gamma(s, nx), g.X);
+    const float cy = src_index(fourier_gamma(s, ny), g.Y);
+    const float cz = src_index(fourier_gamma(s, nz), g.Z);
+    acc.add(s, trilerp1(g.data + s * g.sp, g.sv, g.X, g.Y, g.Z, cx, cy, cz));
+  }
+  return acc.mean(g.P);
+}
+
 // adjoint of trilerp1: grad_slab[corner] += w_corner * g
 __device__ __forceinline__ void trilerp1_scatter(float* __restrict__ slab, int64_t sv, int X, int Y, int Z,
                                                  float cx, float cy, float cz, float g) {

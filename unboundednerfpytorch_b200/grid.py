@@ -149,8 +149,9 @@ class _VoxelGridBase(nn.Module):
         if self.channels == 0:
             self.grid = nn.Parameter(torch.zeros([1, self.channels, *ws], device=self.grid.device))
         else:
-            new = F.interpolate(self.grid.data.contiguous(), size=tuple(ws), mode='trilinear', align_corners=True)
-            self.grid = nn.Parameter(_as_cl3d(new))
+            # one kernel, layout-preserving (the reference: F.interpolate(..., mode='trilinear', align_corners=True) on a
+            # contiguous copy; here no [P,C,X,Y,Z] <-> channels-last round trips)
+            self.grid = nn.Parameter(ops.resample_grid(self.grid.data, ws))
         self.world_size = new_world_size
 
     def total_variation_add_grad(self, wx, wy, wz, dense_mode):

@@ -172,6 +172,17 @@ class _ContractedBase(nn.Module):
         return float(max(g.grid.shape[2:]))
 
 
+@torch.no_grad()
+def _occupancy_update(model, density, mask_cache, interval):
+    """mask &= max_pool3d(Raw2Alpha(density(lattice of the mask grid))) > fast_color_thres  (two launches, 4 B + 1 B per cell)."""
+    from . import ops
+    from .functional import host_scalar
+    mn, mx = density._bounds()
+    alpha = ops.lattice_alpha(density.grid.data, mn, mx, density.num_freqs, model.xyz_min.tolist(), model.xyz_max.tolist(),
+                              mask_cache.mask.shape, host_scalar(model.act_shift), interval)
+    ops.maxpool3_gt_and_(mask_cache.mask, alpha, model.fast_color_thres)
+
+
 # ======================================================================================================
 class FourierGridModel(_ContractedBase):
     """FourierGrid/FourierGrid_model.py:134-681."""
@@ -279,57 +290,44 @@ class FourierGridModel(_ContractedBase):
 
     @torch.no_grad()
     def update_occupancy_cache(self):
-        dev = self.density.grid.device
-        ms = self.mask_cache.mask.shape
-        axes = [torch.linspace(float(self.xyz_min[a]), float(self.xyz_max[a]), ms[a], device=dev) for a in range(3)]
-        xyz = torch.stack(torch.meshgrid(*axes, indexing='ij'), -1)
-        dens = self.density(xyz)[None, None]
-        alpha = F.max_pool3d(self.activate_density(dens), kernel_size=3, padding=1, stride=1)[0, 0]
-        self.mask_cache.mask &= (alpha > self.fast_color_thres)
+        """FourierGrid_model.py:441-456: mask_cache.mask &= max_pool3d(alpha(density(mask lattice))) > fast_color_thres, as two
+        kernels (ops.lattice_alpha generates the lattice points in registers; ops.maxpool3_gt_and_ pools, thresholds and ANDs)."""
+        _occupancy_update(self, self.density, self.mask_cache, float(self.voxel_size_ratio_density))
 
     @torch.no_grad()
     def maskout_near_cam_vox(self, cam_o, near_clip):
-        """FourierGrid_model.py:375-388: set the density of grid points closer than near_clip to any (embedded) camera
-        position to -100, slab by slab."""
+        """FourierGrid_model.py:375-388: density of the grid points closer than near_clip to any camera position (taken in each
+        slab's own embedded coordinates gamma_i) is set to -100.  One kernel per slab: every voxel scans the camera list."""
+        from . import ops
         dev = self.density.grid.device
         ind_norm = ((cam_o.to(dev) - self.xyz_min) / (self.xyz_max - self.xyz_min)).flip((-1,)) * 2 - 1
         F_ = self.density.nerf_pos_num_freq
         freqs = 2 ** torch.linspace(0, F_ - 1, F_, device=dev)
-        emb = [ind_norm] + [f(fr * ind_norm) for fr in freqs for f in (torch.sin, torch.cos)]
-        ws = [int(v) for v in self.world_size_density]
-        axes = [torch.linspace(-1, 1, ws[a], device=dev) for a in range(3)]
-        xyz = torch.stack(torch.meshgrid(*axes, indexing='ij'), -1)
+        emb = [ind_norm] + [f(fr * ind_norm) for fr in freqs for f in (torch.sin, torch.cos)]      # gamma_i of FourierGrid_grid.py:32-36
         for i, cam in enumerate(emb):
-            nearest = torch.stack([(xyz.unsqueeze(-2) - co).pow(2).sum(-1).sqrt().amin(-1) for co in cam.split(10)]).amin(0)
-            self.density.grid[0][i][nearest <= near_clip] = -100      # same indexing as the reference (:388)
+            ops.maskout_near_cam_(self.density.grid.data[0][i], cam.reshape(-1, 3), near_clip, -100.0)   # same indexing as :388
 
     def voxel_count_views(self, rays_o_tr, rays_d_tr, imsz, near, far, stepsize, downrate=1, irregular_shape=False):
-        """FourierGrid_model.py:390-420: per-voxel number of training views, counted with the adjoint of the trilinear read
-        (ones(pts).sum().backward(); count += grad > 1) -- here the scatter kernel of libubnerf_b200."""
+        """FourierGrid_model.py:390-420: per-voxel number of training views that see it.  The reference materialises the sample
+        points of 10 000 rays at a time and runs DenseGrid(ones).sum().backward(); here one kernel per view scatters the
+        trilinear weights of every (ray, sample) straight into a per-view buffer, a second adds (buffer > 1) to the count."""
+        from . import ops
         far = 1e9
         dev = self.density.grid.device
-        n_samples = int(np.linalg.norm(np.array([int(v) for v in self.world_size_density]) + 1) / stepsize) + 1
-        rng = torch.arange(n_samples, device=dev)[None].float()
-        count = torch.zeros_like(self.density.get_dense_grid())
+        ws = [int(v) for v in self.world_size_density]
+        n_samples = int(np.linalg.norm(np.array(ws) + 1) / stepsize) + 1
+        step = float(stepsize * self.voxel_size_density)
+        mn, mx = self.density._bounds()
+        count = torch.zeros(1, 1, *ws, device=dev)
+        buf = torch.empty(*ws, device=dev)
         for rays_o_, rays_d_ in zip(rays_o_tr.split(imsz), rays_d_tr.split(imsz)):
-            ones = G.DenseGrid(1, self.world_size_density, self.xyz_min, self.xyz_max).to(dev)
-            if irregular_shape:
-                rays_o_, rays_d_ = rays_o_.split(10000), rays_d_.split(10000)
-            else:
-                rays_o_ = rays_o_[::downrate, ::downrate].to(dev).flatten(0, -2).split(10000)
-                rays_d_ = rays_d_[::downrate, ::downrate].to(dev).flatten(0, -2).split(10000)
-            for rays_o, rays_d in zip(rays_o_, rays_d_):
-                rays_o, rays_d = rays_o.to(dev), rays_d.to(dev)
-                vec = torch.where(rays_d == 0, torch.full_like(rays_d, 1e-6), rays_d)
-                rate_a = (self.xyz_max - rays_o) / vec
-                rate_b = (self.xyz_min - rays_o) / vec
-                t_min = torch.minimum(rate_a, rate_b).amax(-1).clamp(min=near, max=far)
-                step = stepsize * self.voxel_size_density * rng
-                interpx = t_min[..., None] + step / rays_d.norm(dim=-1, keepdim=True)
-                rays_pts = rays_o[..., None, :] + rays_d[..., None, :] * interpx[..., None]
-                ones(rays_pts).sum().backward()
-            with torch.no_grad():
-                count += (ones.grid.grad > 1)
+            if not irregular_shape:
+                rays_o_, rays_d_ = rays_o_[::downrate, ::downrate], rays_d_[::downrate, ::downrate]
+            ro = rays_o_.to(dev).reshape(-1, 3).contiguous().float()
+            rd = rays_d_.to(dev).reshape(-1, 3).contiguous().float()
+            buf.zero_()
+            ops.view_scatter_ones(ro, rd, mn, mx, ws, n_samples, near, far, step, buf)
+            ops.count_gt_(count, buf, 1.0)
         return count
 
     def hit_coarse_geo(self, rays_o, rays_d, near, far, stepsize, **render_kwargs):
@@ -493,13 +491,9 @@ class DirectContractedVoxGO(_ContractedBase):
 
     @torch.no_grad()
     def update_occupancy_cache(self):
-        dev = self.density.grid.device
-        ms = self.mask_cache.mask.shape
-        axes = [torch.linspace(float(self.xyz_min[a]), float(self.xyz_max[a]), ms[a], device=dev) for a in range(3)]
-        xyz = torch.stack(torch.meshgrid(*axes, indexing='ij'), -1)
-        dens = self.density(xyz)[None, None]
-        alpha = F.max_pool3d(self.activate_density(dens), kernel_size=3, padding=1, stride=1)[0, 0]
-        self.mask_cache.mask &= (alpha > self.fast_color_thres)
+        """dcvgo.py:214-226 (same composition as FourierGrid_model.py:441-456)."""
+        _occupancy_update(self, self.density, self.mask_cache, float(self.voxel_size_ratio))
+        self._mask_host = None
 
     def sample_ray(self, ori_rays_o, ori_rays_d, stepsize, is_train=False, **render_kwargs):
         """dcvgo.py:228-262 return tuple (ray_pts, inner_mask, t)."""

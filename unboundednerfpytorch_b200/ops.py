@@ -16,10 +16,10 @@ from . import _cabi
 from ._cabi import c_f, c_i64, c_int, check, ptr, stream_of
 
 
-def _chk(x, name, dtype=torch.float32):
+def _chk(x, name, dtype=torch.float32, contiguous=True):
     if not isinstance(x, torch.Tensor) or not x.is_cuda:
         raise RuntimeError(f'{name} must be a CUDA tensor')
-    if not x.is_contiguous():
+    if contiguous and not x.is_contiguous():
         raise RuntimeError(f'{name} must be contiguous')
     if dtype is not None and x.dtype != dtype:
         raise RuntimeError(f'{name} must be {dtype} (got {x.dtype})')
@@ -335,6 +335,98 @@ def tv_adam_peer(param, param_out_ptrs, grad_ptrs, exp_avg, exp_avg_sq, wx, wy, 
                                    c_i64(inner), c_int(int(bool(dense_mode))), c_i64(int(plane_begin)), c_i64(int(plane_end)),
                                    c_int(int(step)), c_f(beta1), c_f(beta2), c_f(lr), c_f(eps), c_int(1 if skip_zero_grad else 0),
                                    stream_of(param)))
+
+
+# --------------------------------------------------------------------------------------------------
+# grid-native occupancy / progressive-growing utilities (csrc/grid_utils.cu)
+# --------------------------------------------------------------------------------------------------
+def lattice_alpha(density_grid, xyz_min, xyz_max, num_freqs, lattice_min, lattice_max, lattice_shape, act_shift, interval):
+    """alpha = Raw2Alpha(density(p)) on the [mX,mY,mZ] lattice of linspace(lattice_min, lattice_max) points -- steps 1-3 of
+    update_occupancy_cache (FourierGrid_model.py:443-450) without the meshgrid / grid_sample / activation tensors."""
+    import ctypes
+    from .grid import grid_desc
+    _chk(density_grid, 'density_grid', contiguous=False)
+    d = grid_desc(density_grid, xyz_min, xyz_max, num_freqs)
+    if d.C != 1:
+        raise RuntimeError('lattice_alpha needs a single-channel (density) grid')
+    mX, mY, mZ = [int(v) for v in lattice_shape]
+    alpha = torch.empty(mX, mY, mZ, dtype=torch.float32, device=density_grid.device)
+    lo = (ctypes.c_float * 3)(*[float(v) for v in lattice_min])
+    hi = (ctypes.c_float * 3)(*[float(v) for v in lattice_max])
+    with _Guard(density_grid) as lib:
+        check(lib.ubn_lattice_alpha(ptr(density_grid), d, lo, hi, c_i64(mX), c_i64(mY), c_i64(mZ), c_f(float(act_shift)),
+                                    c_f(float(interval)), ptr(alpha), stream_of(density_grid)))
+    return alpha
+
+
+def maxpool3_gt_and_(mask, alpha, thres):
+    """mask &= F.max_pool3d(alpha, 3, stride 1, padding 1) > thres, in place (FourierGrid_model.py:451-452)."""
+    if not (mask.is_cuda and mask.dtype == torch.bool and mask.is_contiguous() and mask.dim() == 3):
+        raise RuntimeError('mask must be a contiguous CUDA bool [X,Y,Z] tensor')
+    if alpha.shape != mask.shape or not alpha.is_contiguous() or alpha.dtype != torch.float32:
+        raise RuntimeError('alpha must be a contiguous fp32 tensor of the mask shape')
+    X, Y, Z = mask.shape
+    with _Guard(mask) as lib:
+        check(lib.ubn_maxpool3_gt_and(ptr(alpha), c_i64(X), c_i64(Y), c_i64(Z), c_f(float(thres)), ptr(mask), stream_of(mask)))
+    return mask
+
+
+def resample_grid(grid, new_world_size):
+    """F.interpolate(grid, size, mode='trilinear', align_corners=True) for a [P,C,X,Y,Z] grid in its own layout (the result is
+    channels-last when C > 1) -- scale_volume_grid (grid.py:63-68, FourierGrid_grid.py:80-85)."""
+    from .grid import grid_desc, zeros_grid
+    _chk(grid, 'grid', contiguous=False)
+    P, C = grid.shape[0], grid.shape[1]
+    ws = [int(v) for v in new_world_size]
+    out = zeros_grid([P, C, *ws], device=grid.device)
+    zero3 = [0.0, 0.0, 0.0]
+    with _Guard(grid) as lib:
+        check(lib.ubn_resample_grid(ptr(grid), grid_desc(grid, zero3, zero3, 0), ptr(out), grid_desc(out, zero3, zero3, 0),
+                                    stream_of(grid)))
+    return out
+
+
+def view_scatter_ones(rays_o, rays_d, xyz_min, xyz_max, world_size, n_samples, near, far, step, grad):
+    """grad [X,Y,Z] += adjoint of DenseGrid(1, world_size)(pts).sum() over the sample points of the rays
+    (FourierGrid_model.py:405-417); ``step`` = stepsize * voxel_size."""
+    from ._cabi import UbnGridDesc
+    _chk(rays_o, 'rays_o'); _chk(rays_d, 'rays_d'); _chk(grad, 'grad')
+    d = UbnGridDesc()
+    d.P, d.C, d.num_freqs = 1, 1, 0
+    d.X, d.Y, d.Z = [int(v) for v in world_size]
+    d.stride_p, d.stride_c, d.stride_v = d.X * d.Y * d.Z, 1, 1
+    for a in range(3):
+        d.xyz_min[a], d.xyz_max[a] = float(xyz_min[a]), float(xyz_max[a])
+    n = rays_o.shape[0]
+    with _Guard(rays_o) as lib:
+        check(lib.ubn_view_scatter_ones(ptr(rays_o), ptr(rays_d), c_i64(n), c_i64(int(n_samples)), c_f(float(near)), c_f(float(far)),
+                                        c_f(float(step)), d, ptr(grad), stream_of(rays_o)))
+
+
+def count_gt_(count, grad, thres=1.0):
+    """count += (grad > thres), in place (FourierGrid_model.py:418-419)."""
+    _chk(count, 'count', contiguous=False); _chk(grad, 'grad', contiguous=False)
+    if count.numel() != grad.numel():
+        raise RuntimeError('count / grad size mismatch')
+    with _Guard(count) as lib:
+        check(lib.ubn_count_gt(ptr(grad), c_f(float(thres)), c_i64(grad.numel()), ptr(count), stream_of(count)))
+    return count
+
+
+def maskout_near_cam_(slab, cams, near_clip, fill=-100.0):
+    """slab [X,Y,Z] (a view of one grid slab; unit or channel stride) <- fill where the nearest of ``cams`` [n,3] is within
+    near_clip of the lattice point (FourierGrid_model.py:383-388)."""
+    if slab.dim() != 3:
+        raise RuntimeError('slab must be [X,Y,Z]')
+    X, Y, Z = slab.shape
+    sv = slab.stride(2)
+    if slab.stride(1) != Z * sv or slab.stride(0) != Y * Z * sv:
+        raise RuntimeError('slab must be a dense [X,Y,Z] view')
+    cams = cams.contiguous().float()
+    with _Guard(slab) as lib:
+        check(lib.ubn_maskout_near_cam(ptr(slab), c_i64(sv), c_i64(X), c_i64(Y), c_i64(Z), ptr(cams), c_i64(cams.shape[0]),
+                                       c_f(float(near_clip)), c_f(float(fill)), stream_of(slab)))
+    return slab
 
 
 def cumdist_thres(dist, thres):
