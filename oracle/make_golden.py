@@ -227,6 +227,28 @@ def golden_models():
     _save('l2_models.pt', out)
 
 
+from tests.util import cfg1_scene  # noqa: E402  (seeded scene shared with tests/test_gpu_models.py)
+
+
+def golden_cfg1():
+    """SURVEY.md 8c deliverable: the config-1 fixture (64^3, 1024 rays, reference python forward on CPU = torch F.grid_sample path)."""
+    kw, dens, k0, net, ro, rd, vd = cfg1_scene()
+    torch.manual_seed(SEED + 64)
+    m = ref_dvgo.DirectVoxGO(**kw)
+    with torch.no_grad():
+        m.density.grid.copy_(dens)
+        m.k0.grid.copy_(k0)
+    m.load_state_dict(net, strict=False)
+    rk = dict(near=0.2, far=6.0, bg=1, stepsize=0.5, render_depth=True)
+    with torch.no_grad():
+        ret = m(ro, rd, vd, **rk)
+    ray_id = ret['ray_id']
+    _save('l2_cfg1.pt', dict(seed=SEED + 64, render_kwargs=rk, n_survivors=int(ray_id.numel()),
+                             per_ray_count=torch.bincount(ray_id, minlength=len(ro)).to(torch.int32),
+                             rgb_marched=_c(ret['rgb_marched']), depth=_c(ret['depth']), alphainv_last=_c(ret['alphainv_last']),
+                             weights_sum=torch.zeros(len(ro)).index_add_(0, ray_id, ret['weights'])))
+
+
 def golden_rays():
     """dvgo.get_rays_of_a_view / get_training_rays_flatten (dvgo.py:492-612) on small views, every flag combination."""
     g = torch.Generator().manual_seed(SEED + 5)
@@ -263,4 +285,5 @@ if __name__ == '__main__':
     golden_autograd_fns()
     golden_masked_adam()
     golden_models()
+    golden_cfg1()
     golden_rays()

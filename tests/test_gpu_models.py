@@ -72,6 +72,29 @@ def test_dvgo_model_golden():
     _check_against_golden(m, rec, m.forward, 'dvgo')
 
 
+def test_dvgo_config1_fixture_64cubed_1024_rays():
+    """SURVEY.md 8c / BASELINE config 1: DVGO 64^3 DenseGrid, 1024 rays, stepsize 0.5 -- the fixture was produced by the reference's
+    own dvgo.py on CPU (torch F.grid_sample path; oracle/make_golden.py::golden_cfg1), the grids are regenerated from the seed."""
+    from tests.util import cfg1_scene
+    from unboundednerfpytorch_b200 import models
+    rec = load_golden('l2_cfg1.pt')
+    kw, dens, k0, net, ro, rd, vd = cfg1_scene(rec['seed'])
+    m = models.DirectVoxGO(**kw)
+    with torch.no_grad():
+        m.density.grid.copy_(dens)
+        m.k0.grid.copy_(k0)
+    m.load_state_dict(net, strict=False)
+    m = m.to(DEV)
+    with torch.no_grad():
+        ret = m(ro.to(DEV), rd.to(DEV), vd.to(DEV), **rec['render_kwargs'])
+    assert ret['ray_id'].numel() == rec['n_survivors']
+    assert_equal(torch.bincount(ret['ray_id'], minlength=1024).to(torch.int32), rec['per_ray_count'], 'survivors per ray')
+    for k in ('rgb_marched', 'depth', 'alphainv_last'):
+        assert_close(ret[k], rec[k], rtol=1e-5, atol=1e-5 * float(rec[k].abs().max()), what=f'cfg1 {k}')
+    wsum = torch.zeros(1024, device=DEV).index_add_(0, ret['ray_id'], ret['weights'])
+    assert_close(wsum, rec['weights_sum'], rtol=1e-5, atol=1e-6, what='cfg1 weights sum')
+
+
 def _fresh_model(flavor, world, F_, thres, seed, dens_mean=0.0, dens_std=1.0, norm='inf'):
     from unboundednerfpytorch_b200 import models
     torch.manual_seed(seed)
