@@ -401,6 +401,7 @@ def main():
     ap.add_argument('--workload', default='truck', choices=['truck', 'bicycle', 'garden', 'missionbay'])
     ap.add_argument('--cpu-rays', type=int, default=1024, help='upper bound of the ray sample of the CPU legs (shrunk to fit the time budget)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-reference-gpu', action='store_true', help='skip the reference-GPU baseline leg (oracle/_ref + ATen) of the N = 1 line')
     ap.add_argument('--only-timed', action='store_true', help='warm-up + timed region only (for ncu captures)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
@@ -499,9 +500,11 @@ def main():
     dev_batch = [t.to(dev) for t in host]
 
     tail_events = []
+    survivors = [N_RAYS * N_SAMPLES]
 
     def train_step(ro, rd, vd, target, it):
         ret = model(ro, rd, vd, global_step=it, is_train=True, **rk)
+        survivors[0] = int(ret['weights'].numel())        # M: samples that reach the feature grid / rgbnet (no sync: a shape)
         opt.zero_grad(set_to_none=True)
         if os.environ.get('UBN_BENCH_LOSS', 'fused') == 'torch':     # A/B switch: the reference's torch composition
             loss = step_loss(ret, target, N_RAYS)
@@ -604,16 +607,22 @@ def main():
     # rgbnet kernels are FLOP-bound: 2*(12*128 + 128*128 + 128*3) FLOP/sample forward, 2x that backward (dX and dW GEMMs)
     aflops = {'rgbnet_fwd': 2 * (12 * 128 + 128 * 128 + 128 * 3), 'rgbnet_bwd': 4 * (128 * 128)}   # bwd: dH1 + dW2 GEMMs
     abytes['rgbnet_bwd_small'] = 128 * 4 * 2 + 12 * 4 * 2 + 3 * 4 * 2   # streams dZ1 + H2 rows, X, rgb/grad_rgb, writes dX
+    # B = 32 P_d per NOMINAL sample + rho * 32 C P_k per nominal sample, rho = M / (N S): the density pass touches
+    # every nominal sample, the feature / rgbnet kernels only the M survivors of cumdist + mask cache + thresholds
+    M = survivors[0]
+    units = {k: (N_RAYS * N_SAMPLES if k.startswith('march_density') else M) for k in list(abytes) + list(aflops)}
+    traffic_src = 'profiles/traffic.json (static: dram__bytes_read.sum + dram__bytes_write.sum of the committed ncu --set full capture of this kernel on the truck workload, not re-measured in this run)'
 
     def kernel_roof(name, kms):
         if name in abytes:
-            ach = abytes[name] * N_RAYS * N_SAMPLES / (kms * 1e-3) / 1e9
+            ach = abytes[name] * units[name] / (kms * 1e-3) / 1e9
             return {'kernel': name, 'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
-                    'traffic': load_traffic(name), 'kernel_ms': kms, 'algorithmic_bytes_per_sample': abytes[name],
-                    'peak_source': peak_src}
-        ach = aflops[name] * N_RAYS * N_SAMPLES / (kms * 1e-3) / 1e12
+                    'traffic': load_traffic(name) if args.workload == 'truck' else None, 'traffic_source': traffic_src, 'kernel_ms': kms,
+                    'algorithmic_bytes_per_sample': abytes[name], 'samples_per_launch': units[name], 'peak_source': peak_src}
+        ach = aflops[name] * units[name] / (kms * 1e-3) / 1e12
         return {'kernel': name, 'bound': 'tensor', 'achieved': ach, 'peak': tpeak, 'unit': 'TFLOP/s', 'frac': ach / tpeak,
-                'traffic': load_traffic(name), 'kernel_ms': kms, 'algorithmic_flops_per_sample': aflops[name],
+                'traffic': load_traffic(name) if args.workload == 'truck' else None, 'traffic_source': traffic_src, 'kernel_ms': kms,
+                'algorithmic_flops_per_sample': aflops[name], 'samples_per_launch': units[name],
                 'peak_source': tsrc, 'note': 'tcgen05 kind::tf32 with 3-pass split accumulation (fp32-grade, needed for the 1e-5 parity gate): useful FLOPs are '
                                              'counted once, the tensor pipe executes 3x that at half the bf16 rate; measured against the bf16 peak'}
 
@@ -633,11 +642,24 @@ def main():
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': config, 'clocks': clk,
             'e2e': {'value': samples_per_step / (ms_e2e / args.steps * 1e-3), 'unit': 'ray-samples/s',
                     'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4, 'ms_per_step': ms_e2e / args.steps},
-            'gpu_launches': launches, 'roofline': roof,
+            'gpu_launches': launches, 'survivors_per_step': M, 'rho': M / (N_RAYS * N_SAMPLES), 'roofline': roof,
             'tail_ms': {'value': tail_ms, 'what': 'gradient all-reduce (N>1) + dense TV + MaskedAdam, per step',
                         'mode': tail_mode},
             'fwd_only': {'value': samples_per_step / (ms_fwd / args.steps * 1e-3), 'unit': 'ray-samples/s',
                          'ms_per_step': ms_fwd / args.steps}}
+    if world == 1 and not args.no_reference_gpu:
+        # the real competitor: the reference's GPU path on this same B200 -- its algorithm op by op with its own CUDA
+        # extension (oracle/_ref) + ATen grid_sample + cuBLAS; a baseline leg like cpu_baseline, outside every timed region above
+        try:
+            torch.cuda.empty_cache()
+            out = gpu_reference_step(flavor, kwargs, stepsize, 5, 2, dev)
+            line['reference_gpu'] = ({'ms_per_step': out[0], 'value': N_RAYS * N_SAMPLES / (out[0] * 1e-3), 'unit': 'ray-samples/s',
+                                      'survivors': out[1], 'speedup_vs_reference_gpu': out[0] / ms_per_step,
+                                      'what': "reference algorithm op by op on this GPU: ATen grid_sample + cuBLAS rgbnet + the reference's own "
+                                              "CUDA extension (oracle/_ref) for raw2alpha / alpha2weight / TV / masked Adam; same step, same grids"}
+                                     if out is not None else {'unavailable': 'oracle/_ref not built'})
+        except Exception as e:
+            line['reference_gpu'] = {'unavailable': f'failed: {e}'}
     if not args.no_cpu_baseline and world == 1:              # rank 0 at N = 1 only
         try:
             cores, args.cpu_rays = tune_cpu_reference(flavor, kwargs, stepsize, cores, 2, args.cpu_rays, budget_s=30.0)

@@ -249,6 +249,33 @@ def golden_cfg1():
                              weights_sum=torch.zeros(len(ro)).index_add_(0, ray_id, ret['weights'])))
 
 
+def golden_checkpoint():
+    """A reference-format checkpoint written by the reference's own classes: FourierGridModel + its MaskedAdam after two steps,
+    saved exactly like FourierGridCheckpointManager.save_model (FourierGrid_ckpt_manager.py:44-51) -> tests/golden/ref_fine_last.tar."""
+    torch.manual_seed(SEED + 9)
+    gen = torch.Generator().manual_seed(SEED + 9)
+    kw = dict(xyz_min=np.array([-1., -1., -1.], dtype=np.float32), xyz_max=np.array([1., 1., 1.], dtype=np.float32),
+              num_voxels_density=8 ** 3, num_voxels_base_density=8 ** 3, num_voxels_rgb=8 ** 3, num_voxels_base_rgb=8 ** 3,
+              num_voxels_viewdir=-1, alpha_init=1e-2, fast_color_thres=1e-4, rgbnet_dim=12, fourier_freq_num=2)
+    m = ref_fgmodel.FourierGridModel(**kw)
+    with torch.no_grad():
+        m.density.grid.copy_(torch.randn(m.density.grid.shape, generator=gen) * 3)
+        m.k0.grid.copy_(torch.randn(m.k0.grid.shape, generator=gen))
+    opt = ref_adam.MaskedAdam([{'params': [m.density.grid], 'lr': 0.1, 'skip_zero_grad': True},
+                               {'params': [m.k0.grid], 'lr': 0.1, 'skip_zero_grad': True},
+                               {'params': list(m.rgbnet.parameters()), 'lr': 1e-3, 'skip_zero_grad': False}])
+    ro, rd, vd = _rays(16, gen)
+    rk = dict(near=0.0, far=1e9, bg=1, rand_bkgd=False, stepsize=0.5, inverse_y=False, flip_x=False, flip_y=False)
+    for it in range(2):
+        opt.zero_grad(set_to_none=True)
+        m(ro, rd, vd, global_step=it, is_train=True, **rk)['rgb_marched'].sum().backward()
+        opt.step()
+    path = os.path.join(OUT, 'ref_fine_last.tar')
+    torch.save({'global_step': 2, 'model_kwargs': m.get_kwargs(), 'model_state_dict': m.state_dict(),
+                'optimizer_state_dict': opt.state_dict()}, path)
+    print(f'ref_fine_last.tar: {os.path.getsize(path) / 1024:.1f} KiB')
+
+
 def golden_rays():
     """dvgo.get_rays_of_a_view / get_training_rays_flatten (dvgo.py:492-612) on small views, every flag combination."""
     g = torch.Generator().manual_seed(SEED + 5)
@@ -286,4 +313,5 @@ if __name__ == '__main__':
     golden_masked_adam()
     golden_models()
     golden_cfg1()
+    golden_checkpoint()
     golden_rays()

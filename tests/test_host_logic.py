@@ -168,3 +168,37 @@ def test_rays_host_side_pieces():
     assert nxt.shape == (4,) and int(nxt.max()) < 10
     with pytest.raises(NotImplementedError):
         R._rays_of_a_view(2, 2, np.eye(3), np.eye(4)[:3], False, False, False, False, 'bogus')
+
+
+def test_reference_checkpoint_interchange(tmp_path):
+    """a checkpoint written by the REFERENCE's classes (tests/golden/ref_fine_last.tar, produced by
+    oracle/make_golden.py::golden_checkpoint with FourierGrid_model.py + masked_adam.py) loads into this library's model and
+    optimizer; a checkpoint written here has the reference's keys, contiguous [P,C,X,Y,Z] grids, and loads back unchanged."""
+    import os
+    import numpy as np
+    import torch
+    from unboundednerfpytorch_b200 import ckpt, models
+    from unboundednerfpytorch_b200.masked_adam import MaskedAdam
+    path = os.path.join(ROOT, 'tests', 'golden', 'ref_fine_last.tar')
+    raw = torch.load(path, map_location='cpu', weights_only=False)
+    assert set(raw) == {'global_step', 'model_kwargs', 'model_state_dict', 'optimizer_state_dict'}
+    assert isinstance(raw['model_kwargs']['xyz_min'], np.ndarray)            # why weights_only=True cannot load reference files
+    m = ckpt.load_model(models.FourierGridModel, path)
+    for k, v in raw['model_state_dict'].items():
+        assert torch.equal(m.state_dict()[k].contiguous(), v), k
+    assert m.k0.grid.stride()[1] == 1                                        # copied into the channels-last layout
+    opt = MaskedAdam([{'params': [m.density.grid], 'lr': 0.1, 'skip_zero_grad': True},
+                      {'params': [m.k0.grid], 'lr': 0.1, 'skip_zero_grad': True},
+                      {'params': list(m.rgbnet.parameters()), 'lr': 1e-3, 'skip_zero_grad': False}])
+    m2, opt2, start = ckpt.load_checkpoint(m, opt, path, no_reload_optimizer=False)
+    assert start == 2 and opt2.state[m.k0.grid]['step'] == 2
+    assert opt2.state[m.k0.grid]['exp_avg'].stride() == m.k0.grid.stride()
+    assert torch.equal(opt2.state[m.k0.grid]['exp_avg'].contiguous(), raw['optimizer_state_dict']['state'][1]['exp_avg'])
+    out = tmp_path / 'fine_last.tar'
+    ckpt.save_checkpoint(7, m, opt, str(out))
+    back = torch.load(str(out), map_location='cpu', weights_only=False)
+    assert back['global_step'] == 7 and set(back) == set(raw)
+    assert back['model_state_dict']['k0.grid'].is_contiguous()
+    for k, v in raw['model_state_dict'].items():
+        assert torch.equal(back['model_state_dict'][k], v), k
+    assert sorted(back['model_kwargs']) == sorted(raw['model_kwargs'])
