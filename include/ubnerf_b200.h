@@ -317,6 +317,19 @@ int ubn_march_feature_fwd(const float* rays_o, const float* rays_d, const float*
                           float* k0_feat, float* out_density, float* out_alpha, float* out_weight,
                           int64_t* ray_id, int64_t* step_id, float* out_t, uint8_t* out_inner, void* stream);
 
+/* Pass B forward for COHERENT rays (a frame's image-ordered 8192-ray chunks, run_render.py:43-63) on a single-slab 12-channel
+ * channels-last feature grid (DenseGrid k0 of DirectContractedVoxGO / DirectVoxGO): same arguments and outputs as
+ * ubn_march_feature_fwd, but warp = 32 consecutive rays and the voxel brick a warp's 32 rays x 4 steps touch is staged in shared
+ * memory by ONE TMA tensor load (cp.async.bulk.tensor 4-D box [8,8,8,12], mbarrier-signalled); blocks whose cells span more than
+ * 7 lattice steps on an axis fall back to direct loads.  Correct for any rays (incoherent rays simply take the fallback).
+ * Features are accumulated in ATen's corner order (bit-identical to F.grid_sample / ubn_grid_sample_fwd).
+ * stats2: optional device uint64[2], += {blocks served by TMA, blocks served by the fallback}. */
+int ubn_march_feature_fwd_tma(const float* rays_o, const float* rays_d, const float* t_table, const float* k0_grid,
+                              const UbnGridDesc* k0_desc, const UbnMarchCfg* cfg, int64_t n_rays, const uint8_t* flags,
+                              const int64_t* offsets, const float* density, const float* alpha, const float* weight, float* feat,
+                              float* o_density, float* o_alpha, float* o_weight, int64_t* o_ray_id, int64_t* o_step_id, float* o_t,
+                              uint8_t* o_inner, unsigned long long* stats2, void* stream);
+
 /* Backward of pass B: scatter grad_feat[M,C] into grad_k0 (adjoint of the trilinear read). */
 int ubn_march_feature_bwd(const float* rays_o, const float* rays_d, const float* t_table,
                           const UbnGridDesc* k0_desc, const UbnMarchCfg* cfg, int64_t n_rays,

@@ -45,6 +45,15 @@ def t_schedule(world_len, stepsize, bg_len, t_boundary, device):
     return hit
 
 
+TMA_STATS = None          # optional torch.int64[2] CUDA tensor: += {blocks served by TMA, blocks served by the fallback} (tests / bench)
+
+
+def tma_supported(k0_grid):
+    """Single-slab 12-channel channels-last feature grid (DenseGrid k0 of the DCVGO / DVGO family)."""
+    return (k0_grid.is_cuda and k0_grid.dim() == 5 and k0_grid.shape[0] == 1 and k0_grid.shape[1] == 12 and k0_grid.stride(1) == 1
+            and min(k0_grid.shape[2:]) >= 2)
+
+
 def make_cfg(scene_center, scene_radius, bg_len, contracted_norm, n_samples, act_shift, interval,
              fast_color_thres, cumdist_thres=None, mask=None, mask_scale=None, mask_shift=None):
     c = UbnMarchCfg()
@@ -84,7 +93,7 @@ class March(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, density_grid, k0_grid, rays_o, rays_d, t_table, mask_world, cfg, ddesc, kdesc, dense_known):
+    def forward(ctx, density_grid, k0_grid, rays_o, rays_d, t_table, mask_world, cfg, ddesc, kdesc, dense_known, coherent=False):
         dev = rays_o.device
         rays_o = rays_o.contiguous().float()
         rays_d = rays_d.contiguous().float()
@@ -117,11 +126,18 @@ class March(torch.autograd.Function):
             step_id = torch.empty(M, dtype=torch.int64, device=dev)
             o_t = torch.empty(M, **f32)
             o_inner = torch.empty(M, dtype=torch.bool, device=dev)
-            with _cabi.timed('march_feature_fwd'):
-                check(lib.ubn_march_feature_fwd(ptr(rays_o), ptr(rays_d), ptr(t_table), ptr(k0_grid), kdesc, cfg, c_i64(N),
-                                                ptr(flags), ptr(offsets), ptr(dens), ptr(alpha), ptr(weight), ptr(feat),
-                                                ptr(o_dens), ptr(o_alpha), ptr(o_weight), ptr(ray_id), ptr(step_id),
-                                                ptr(o_t), ptr(o_inner), st))
+            use_tma = coherent and tma_supported(k0_grid) and not torch.is_grad_enabled()
+            with _cabi.timed('march_feature_fwd_tma' if use_tma else 'march_feature_fwd'):
+                if use_tma:       # render path: bricks of the feature grid staged by TMA for 32 adjacent rays x 4 steps
+                    check(lib.ubn_march_feature_fwd_tma(ptr(rays_o), ptr(rays_d), ptr(t_table), ptr(k0_grid), kdesc, cfg, c_i64(N),
+                                                        ptr(flags), ptr(offsets), ptr(dens), ptr(alpha), ptr(weight), ptr(feat),
+                                                        ptr(o_dens), ptr(o_alpha), ptr(o_weight), ptr(ray_id), ptr(step_id),
+                                                        ptr(o_t), ptr(o_inner), ptr(TMA_STATS), st))
+                else:
+                    check(lib.ubn_march_feature_fwd(ptr(rays_o), ptr(rays_d), ptr(t_table), ptr(k0_grid), kdesc, cfg, c_i64(N),
+                                                    ptr(flags), ptr(offsets), ptr(dens), ptr(alpha), ptr(weight), ptr(feat),
+                                                    ptr(o_dens), ptr(o_alpha), ptr(o_weight), ptr(ray_id), ptr(step_id),
+                                                    ptr(o_t), ptr(o_inner), st))
         ctx.save_for_backward(rays_o, rays_d, t_table, dens, alpha, weight, T, flags, last, offsets)
         ctx.cfg, ctx.ddesc, ctx.kdesc = cfg, ddesc, kdesc
         ctx.dmeta = (density_grid.shape, density_grid.stride())
@@ -178,4 +194,4 @@ class March(torch.autograd.Function):
             ctx.dparam.grad, grad_d = buf_d, None
         if buf_k is not None:
             ctx.kparam.grad, grad_k = buf_k, None
-        return grad_d, grad_k, None, None, None, None, None, None, None, None
+        return grad_d, grad_k, None, None, None, None, None, None, None, None, None

@@ -114,7 +114,7 @@ class _ContractedBase(nn.Module):
         kg = self.k0.grid
         return kg.is_cuda and kg.shape[1] in (4, 8, 12, 16) and kg.shape[0] <= 16
 
-    def _march(self, rays_o, rays_d, stepsize):
+    def _march(self, rays_o, rays_d, stepsize, coherent=False):
         dev = rays_o.device
         t_table = march.t_schedule(self._world_len(), stepsize, self.bg_len, self.T_BOUNDARY, dev)
         interval = stepsize * float(self._voxel_size_ratio())
@@ -138,7 +138,7 @@ class _ContractedBase(nn.Module):
         kdesc = G.grid_desc(self.k0.grid, kmn, kmx, self.k0.num_freqs)
         dense_known = (self.fast_color_thres <= 0) and not self.USE_CUMDIST and not self.USE_MASKCACHE
         out = march.March.apply(self.density.grid, self.k0.grid, rays_o, rays_d, t_table, mask, cfg, ddesc, kdesc,
-                                dense_known)
+                                dense_known, coherent)
         return out, t_table
 
     def _shade(self, k0, viewdirs, ray_id):
@@ -522,8 +522,10 @@ class DirectContractedVoxGO(_ContractedBase):
         if not self._fused_ok():
             return self.forward_ops(rays_o, rays_d, viewdirs, global_step=global_step, is_train=is_train, **render_kwargs)
         N = len(rays_o)
+        # render_kwargs['coherent_rays'] (set by render.render_rays: a frame's image-ordered chunks) selects the TMA-staged
+        # feature read; it is a hint, never a requirement -- any rays give the same result
         (weights, alphainv_last, alpha, density, k0, ray_id, step_id, t, inner), t_table = self._march(
-            rays_o, rays_d, render_kwargs['stepsize'])
+            rays_o, rays_d, render_kwargs['stepsize'], coherent=bool(render_kwargs.get('coherent_rays', False)))
         rgb = self._shade(k0, viewdirs, ray_id)
         return self._finish(N, rays_o.device, weights, alphainv_last, density, alpha, rgb, ray_id, step_id, t, inner,
                             t_table.numel(), is_train, render_kwargs)
