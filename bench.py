@@ -19,8 +19,9 @@ thread count that is fastest for it.  `psnr_delta_vs_ref` = second half of the m
 `--impl reference-gpu` (informative, not part of the driver contract) = the reference's GPU path on this B200: its
 algorithm op by op with its own CUDA extension from oracle/_ref + ATen / cuBLAS.
 A/B switches (env): UBN_BENCH_TAIL=peer|pipelined|sequential (training-step tail), UBN_BENCH_LOSS=fused|torch,
-UBN_TV_IMPL=1|0 (streaming / element-per-thread TV), UBN_DENSITY_RED_PAIRS=1|0, UBN_FEATURE_IMPL, UBN_RGBNET_MODE,
-UBN_RGBNET_BWD_MODE, UBN_NCCL_HIGH_PRIORITY=1|0.
+UBN_TV_IMPL=1|0 (streaming / element-per-thread TV; scripts/check_tv_stream.py), UBN_RGBNET_MODE=tc3|tc1|simt,
+UBN_RGBNET_BWD_MODE=fused|tc3|simt (every mode is exercised by tests/test_gpu_models.py::test_fused_rgbnet_vs_torch),
+UBN_NCCL_HIGH_PRIORITY=1|0, UBN_PEER_MAP=auto|symm|ipc.
 """
 import argparse
 import json

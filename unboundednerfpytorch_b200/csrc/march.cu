@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(32 * kMarchWarps) k_march_density_bwd(
       const float cx = src_index(fourier_gamma(sl, nx), g.X);
       const float cy = src_index(fourier_gamma(sl, ny), g.Y);
       const float cz = src_index(fourier_gamma(sl, nz), g.Z);
-      if (g.sv == 1 && p.red_pairs) trilerp1_scatter_pairs(grad_grid + sl * g.sp, g.X, g.Y, g.Z, cx, cy, cz, gd);
+      if (g.sv == 1) trilerp1_scatter_pairs(grad_grid + sl * g.sp, g.X, g.Y, g.Z, cx, cy, cz, gd);
       else trilerp1_scatter(grad_grid + sl * g.sp, g.sv, g.X, g.Y, g.Z, cx, cy, cz, gd);
     }
   }

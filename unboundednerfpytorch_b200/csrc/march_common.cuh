@@ -1,6 +1,5 @@
 // march_common.cuh -- ray set-up and contracted sampling shared by the fused march kernels.
 #pragma once
-#include <cstdlib>
 #include "trilinear.cuh"
 
 namespace ubn {
@@ -16,7 +15,6 @@ struct MarchParams {
   int use_mask;
   int msz[3];
   float mscale[3], mshift[3];
-  int red_pairs;                  // density backward: paired-z vector reductions (UBN_DENSITY_RED_PAIRS=0 disables)
 };
 
 inline MarchParams make_params(const UbnMarchCfg* c) {
@@ -30,8 +28,6 @@ inline MarchParams make_params(const UbnMarchCfg* c) {
   p.use_cumdist = c->use_cumdist; p.cumdist_thres = c->cumdist_thres;
   p.use_mask = c->use_maskcache;
   for (int a = 0; a < 3; ++a) { p.msz[a] = c->mask_sz[a]; p.mscale[a] = c->mask_scale[a]; p.mshift[a] = c->mask_shift[a]; }
-  static const int red_pairs = [] { const char* e = getenv("UBN_DENSITY_RED_PAIRS"); return (e && e[0] == '0') ? 0 : 1; }();
-  p.red_pairs = red_pairs;
   return p;
 }
 

@@ -5,15 +5,13 @@
 // slabs before the next sample re-touched the same voxels) and one load in flight per warp.  Here:
 //   * no shared memory at all: the per-(sample, slab) cell (base voxel + 3 fractions) lives in the registers of the
 //     lane that owns the sample and is broadcast with warp shuffles -> the whole 228 KB stays L1;
-//   * samples are processed in groups of 8 with the slab loop OUTSIDE the sample loop, so the 8 corner records of
+//   * samples are processed in groups (2 forward, 4 backward) with the slab loop OUTSIDE the sample loop, so the corner records of
 //     consecutive samples (which share 4-8 corners at half-voxel steps) are re-read while still in L1;
 //   * the 8 loads of a group are issued back to back (independent) before their FMAs: 8x the memory-level parallelism;
 //   * cells are pre-clamped (base in [0, size-2], fraction in [0,1]) by the owning lane, so no per-corner bounds
 //     predicate is needed: contracted / Fourier-warped coordinates never leave [-1,1] (asserted by the host side).
 // Lane roles in the cooperative phase: corner = lane >> 2 (bit2 = x, bit1 = y, bit0 = z), quad = lane & 3 (channels
 // 4*quad .. 4*quad+3 of the C-channel voxel record); C in {4, 8, 12, 16}, channels-last grid.
-#include <cstdlib>
-
 #include "march_common.cuh"
 
 namespace ubn {
@@ -208,25 +206,14 @@ int march_feature_v2(bool backward, const float* rays_o, const float* rays_d, co
                      uint8_t* o_inner, cudaStream_t st) {
   if (g.X < 2 || g.Y < 2 || g.Z < 2) return -1;
   if ((int64_t)g.X * g.Y * g.Z * g.C >= (1ll << 31)) return -1;   // 32-bit voxel offsets inside a slab
-  static int impl = -1;   // UBN_FEATURE_IMPL: 0 = generic kernel (march.cu), 1 = groups of 8, 2 = groups of 4 (default)
-  if (impl < 0) {
-    const char* e = getenv("UBN_FEATURE_IMPL");
-    impl = e ? atoi(e) : 2;
-  }
-  if (impl == 0) return -1;
-  const bool g8 = impl == 1;
-  const bool g2 = impl == 3 || (impl == 2 && !backward);   // default: groups of 2 forward (occupancy), 4 backward
-  const bool g1 = impl == 4;
+  // forward: groups of 2 samples (80 registers, 6 CTAs/SM won the occupancy sweep); backward: groups of 4 (the vector reductions
+  // need no result, deeper batching costs nothing).  Round 1's other variants (groups of 1 / 8, the env switch) are gone.
 #define UBN_V2(P)                                                                                                       \
   case P:                                                                                                               \
-    return g1 ? launch_v2<P, 1>(backward, rays_o, rays_d, t_table, g, p, n_rays, flags, offsets, density, alpha, weight, \
-                                feat, grad_grid, o_density, o_alpha, o_weight, o_ray_id, o_step_id, o_t, o_inner, st)    \
-         : g2 ? launch_v2<P, 2>(backward, rays_o, rays_d, t_table, g, p, n_rays, flags, offsets, density, alpha, weight, \
-                                feat, grad_grid, o_density, o_alpha, o_weight, o_ray_id, o_step_id, o_t, o_inner, st)    \
-         : g8 ? launch_v2<P, 8>(backward, rays_o, rays_d, t_table, g, p, n_rays, flags, offsets, density, alpha, weight, \
-                                feat, grad_grid, o_density, o_alpha, o_weight, o_ray_id, o_step_id, o_t, o_inner, st)    \
-              : launch_v2<P, 4>(backward, rays_o, rays_d, t_table, g, p, n_rays, flags, offsets, density, alpha, weight, \
-                                feat, grad_grid, o_density, o_alpha, o_weight, o_ray_id, o_step_id, o_t, o_inner, st)
+    return backward ? launch_v2<P, 4>(backward, rays_o, rays_d, t_table, g, p, n_rays, flags, offsets, density, alpha, weight, \
+                                      feat, grad_grid, o_density, o_alpha, o_weight, o_ray_id, o_step_id, o_t, o_inner, st)    \
+                    : launch_v2<P, 2>(backward, rays_o, rays_d, t_table, g, p, n_rays, flags, offsets, density, alpha, weight, \
+                                      feat, grad_grid, o_density, o_alpha, o_weight, o_ray_id, o_step_id, o_t, o_inner, st)
   switch (g.P) {
     UBN_V2(1);
     UBN_V2(3);

@@ -25,15 +25,6 @@ def _t_schedule_cpu(world_len, stepsize, bg_len, t_boundary):
 
 
 _t_dev_cache = {}
-_side_streams = {}
-OVERLAP_BACKWARD = os.environ.get("UBN_OVERLAP_BACKWARD", "0") == "1"   # +1.5 % step speed, but blurs per-kernel timings
-
-
-def _side_stream(dev):
-    key = str(dev)
-    if key not in _side_streams:
-        _side_streams[key] = torch.cuda.Stream(device=dev)
-    return _side_streams[key]
 
 
 def t_schedule(world_len, stepsize, bg_len, t_boundary, device):
@@ -159,37 +150,24 @@ class March(torch.autograd.Function):
         g_weight, g_last, g_alpha, g_dens, g_feat = map(cont, (g_weight, g_last, g_alpha, g_dens, g_feat))
         grad_d = grad_k = None
         with ops._Guard(rays_o) as lib:
-            cur = torch.cuda.current_stream(dev)
             want_k = ctx.needs_input_grad[1] and g_feat is not None
             want_d = ctx.needs_input_grad[0]
-            # the two scatters touch different grids and are both latency-bound (ncu: DRAM < 20 % of peak, issue < 60 %), so
-            # the density scatter runs on a side stream concurrently with the feature scatter
-            side = _side_stream(dev) if (want_k and want_d and OVERLAP_BACKWARD) else None
             buf_d = getattr(ctx.dparam, '_ubn_grad_buffer', None) if want_d else None
             buf_k = getattr(ctx.kparam, '_ubn_grad_buffer', None) if want_k else None
             if want_d:
                 grad_d = buf_d if buf_d is not None else torch.empty_strided(*ctx.dmeta, dtype=torch.float32, device=dev).zero_()
             if want_k:
                 grad_k = buf_k if buf_k is not None else torch.empty_strided(*ctx.kmeta, dtype=torch.float32, device=dev).zero_()
-            if side is not None:
-                side.wait_stream(cur)
             if want_k:
                 with _cabi.timed('march_feature_bwd'):
                     check(lib.ubn_march_feature_bwd(ptr(rays_o), ptr(rays_d), ptr(t_table), ctx.kdesc, ctx.cfg, c_i64(N),
                                                     ptr(flags), ptr(offsets), ptr(g_feat), ptr(grad_k), stream_of(rays_o)))
             if want_d:
-                st_d = side if side is not None else cur
-                with torch.cuda.stream(st_d):
-                    with _cabi.timed('march_density_bwd'):
-                        check(lib.ubn_march_density_bwd(ptr(rays_o), ptr(rays_d), ptr(t_table), ctx.ddesc, ctx.cfg, c_i64(N),
-                                                        ptr(dens), ptr(alpha), ptr(weight), ptr(T), ptr(flags), ptr(last),
-                                                        ptr(offsets), ptr(g_weight), ptr(g_alpha), ptr(g_dens), ptr(g_last),
-                                                        ptr(grad_d), _cabi.c_p(st_d.cuda_stream)))
-                if side is not None:
-                    cur.wait_stream(side)
-                    for t in (dens, alpha, weight, T, flags, last, offsets, g_weight, g_alpha, g_dens, g_last, grad_d, rays_o, rays_d):
-                        if t is not None:
-                            t.record_stream(side)
+                with _cabi.timed('march_density_bwd'):
+                    check(lib.ubn_march_density_bwd(ptr(rays_o), ptr(rays_d), ptr(t_table), ctx.ddesc, ctx.cfg, c_i64(N),
+                                                    ptr(dens), ptr(alpha), ptr(weight), ptr(T), ptr(flags), ptr(last),
+                                                    ptr(offsets), ptr(g_weight), ptr(g_alpha), ptr(g_dens), ptr(g_last),
+                                                    ptr(grad_d), stream_of(rays_o)))
         if buf_d is not None:
             ctx.dparam.grad, grad_d = buf_d, None
         if buf_k is not None:
