@@ -221,7 +221,7 @@ def test_training_step_reduces_loss():
     assert all(torch.isfinite(p).all() for p in student.parameters())
 
 
-@pytest.mark.parametrize('mode', ['simt', 'tc3', 'tc1', 'tc3+tcbwd', 'tc3+fused'])
+@pytest.mark.parametrize('mode', ['simt', 'tc3', 'tc1', 'tc3+tcbwd', 'tc3+fused', 'tc1+fused'])
 def test_fused_rgbnet_vs_torch(mode, monkeypatch):
     """csrc/shade.cu (fp32 FFMA) and csrc/shade_tc.cu (tcgen05: 3xTF32 fp32-grade, single-pass TF32 preview) vs the torch
     nn.Sequential they replace: forward and every gradient."""
@@ -240,6 +240,17 @@ def test_fused_rgbnet_vs_torch(mode, monkeypatch):
         emb = torch.randn(n_rays, 27, generator=g).to(DEV)
         ray_id = torch.sort(torch.randint(0, n_rays, (M,), generator=g))[0].to(DEV)
         gr = torch.randn(M, 3, generator=g).to(DEV)
+        # ReLU' is discontinuous: a pre-activation within fp32 rounding of zero legitimately gets a different mask from two fp32
+        # implementations and changes that sample's gradient wholesale.  Keep the comparison about arithmetic: drop the (few)
+        # samples whose fp64 pre-activations come within 1e-5 of zero (1e-2 for the single-pass TF32 mode).
+        with torch.no_grad():
+            x64 = torch.cat([k0, emb[ray_id]], -1).double()
+            z1 = x64 @ net[0].weight.double().t() + net[0].bias.double()
+            z2 = torch.relu(z1) @ net[2][0].weight.double().t() + net[2][0].bias.double()
+            ok = (torch.minimum(z1.abs().amin(1), z2.abs().amin(1)) > (1e-2 if mode == 'tc1' else 1e-5))
+        if M > 1 and bool(ok.any()):
+            k0 = k0.detach()[ok].clone().requires_grad_(True)
+            ray_id, gr = ray_id[ok].contiguous(), gr[ok].contiguous()
         ref = torch.sigmoid(net(torch.cat([k0, emb[ray_id]], -1)))
         net.zero_grad(); k0.grad = None
         (ref * gr).sum().backward()
@@ -247,13 +258,16 @@ def test_fused_rgbnet_vs_torch(mode, monkeypatch):
         net.zero_grad(); k0.grad = None
         out = shade_mod.shade(net, k0, emb, ray_id)
         assert_close(out, ref, what=f'rgb M={M} {mode}', **fwd_tol)
-        if mode == 'tc1':
+        if mode == 'tc1' and shade_mod.BWD_MODE != 'fused':
             continue
         (out * gr).sum().backward()
         got = [k0.grad] + [p.grad for p in net.parameters()]
         for a, b, nm in zip(got, want, ['k0', 'W1', 'b1', 'W2', 'b2', 'W3', 'b3']):
             scale = b.abs().max().item() + 1e-12
-            assert_close(a, b, rtol=2e-5, atol=2e-6 * scale + 1e-9, what=f'grad {nm} M={M}')
+            if mode == 'tc1':            # single TF32 pass: ~1e-3 relative per product
+                assert_close(a, b, rtol=2e-2, atol=2e-2 * scale + 1e-9, what=f'grad {nm} M={M} tf32x1')
+            else:
+                assert_close(a, b, rtol=2e-5, atol=2e-6 * scale + 1e-9, what=f'grad {nm} M={M}')
 
 
 def test_progressive_growing_and_occupancy_utilities(oracle):

@@ -638,6 +638,7 @@ __device__ __forceinline__ void warp_stage_chunk(float* stg, const float4 (&q)[8
   __syncwarp();
 }
 
+template <bool kThree>
 __global__ void __launch_bounds__(kRows, 1) k_shade_bwd_fused(
     const float* __restrict__ feat, const int64_t* __restrict__ ray_id, const float* __restrict__ W1k,
     const float* __restrict__ W2, const float* __restrict__ W3, const float* __restrict__ rgb,
@@ -789,8 +790,10 @@ __global__ void __launch_bounds__(kRows, 1) k_shade_bwd_fused(
 #pragma unroll 4
       for (int ks = 0; ks < kHidden / 8; ++ks) {
         mma_ts(tmem + cDHf, tmem + cAhi + ks * 8, dWThi + ks * kStepK, ks > 0);
-        mma_ts(tmem + cDHf, tmem + cAlo + ks * 8, dWThi + ks * kStepK, 1);
-        mma_ts(tmem + cDHf, tmem + cAhi + ks * 8, dWTlo + ks * kStepK, 1);
+        if (kThree) {
+          mma_ts(tmem + cDHf, tmem + cAlo + ks * 8, dWThi + ks * kStepK, 1);
+          mma_ts(tmem + cDHf, tmem + cAhi + ks * 8, dWTlo + ks * kStepK, 1);
+        }
       }
       mma_commit(bar_addr);
     }
@@ -875,8 +878,10 @@ __global__ void __launch_bounds__(kRows, 1) k_shade_bwd_fused(
 #pragma unroll 4
       for (int ks = 0; ks < kHidden / 8; ++ks) {
         mma_ts_idesc(tmem + cDX, tmem + cAhi + ks * 8, dW1hi + ks * kStepK16, kIdescN16, ks > 0);
-        mma_ts_idesc(tmem + cDX, tmem + cAlo + ks * 8, dW1hi + ks * kStepK16, kIdescN16, 1);
-        mma_ts_idesc(tmem + cDX, tmem + cAhi + ks * 8, dW1lo + ks * kStepK16, kIdescN16, 1);
+        if (kThree) {
+          mma_ts_idesc(tmem + cDX, tmem + cAlo + ks * 8, dW1hi + ks * kStepK16, kIdescN16, 1);
+          mma_ts_idesc(tmem + cDX, tmem + cAhi + ks * 8, dW1lo + ks * kStepK16, kIdescN16, 1);
+        }
       }
       mma_commit(bar_addr);
     }
@@ -928,6 +933,7 @@ constexpr uint32_t kSmemBytesD = oBarD + 16;
 constexpr int kCtasPerSM = 3;
 }  // namespace dw
 
+template <bool kThree>
 __global__ void __launch_bounds__(dw::kThreadsDW, dw::kCtasPerSM) k_shade_dw2_tc(
     const float* __restrict__ W3, const float* __restrict__ rgb, const float* __restrict__ h1, const float* __restrict__ h2,
     const float* __restrict__ g_rgb, int64_t n_pts, float* __restrict__ gW2) {
@@ -1013,8 +1019,10 @@ __global__ void __launch_bounds__(dw::kThreadsDW, dw::kCtasPerSM) k_shade_dw2_tc
 #pragma unroll
       for (int ks = 0; ks < (int)(kK / 8); ++ks) {
         mma_ss(tmem, dAhi + ks * kStepK, dBhi + ks * kStepK, (rd > r_begin || ks > 0) ? 1u : 0u);
-        mma_ss(tmem, dAlo + ks * kStepK, dBhi + ks * kStepK, 1);
-        mma_ss(tmem, dAhi + ks * kStepK, dBlo + ks * kStepK, 1);
+        if (kThree) {
+          mma_ss(tmem, dAlo + ks * kStepK, dBhi + ks * kStepK, 1);
+          mma_ss(tmem, dAhi + ks * kStepK, dBlo + ks * kStepK, 1);
+        }
       }
       mma_commit(bar_addr);
     }
@@ -1088,11 +1096,11 @@ extern "C" int ubn_rgbnet_bwd_tc_data(const float* W2, const float* W3, const fl
   {   // dW2 (split-K GEMM over all samples)
     const int64_t n_rounds = (n_pts + tc::dw::kK - 1) / tc::dw::kK;
     const unsigned grid = (unsigned)std::min<int64_t>((int64_t)kNumSMs * tc::dw::kCtasPerSM, n_rounds);
-    cudaError_t e = cudaFuncSetAttribute(tc::k_shade_dw2_tc, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(tc::k_shade_dw2_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)tc::dw::kSmemBytesD);
     if (e != cudaSuccess) return finish(e);
-    tc::k_shade_dw2_tc<<<grid, tc::dw::kThreadsDW, tc::dw::kSmemBytesD, st>>>(W3, rgb, h1_save, h2_save, grad_rgb, n_pts,
-                                                                             grad_W2);
+    tc::k_shade_dw2_tc<true><<<grid, tc::dw::kThreadsDW, tc::dw::kSmemBytesD, st>>>(W3, rgb, h1_save, h2_save, grad_rgb, n_pts,
+                                                                                   grad_W2);
     UBN_LAUNCH_CHECK();
   }
   return 0;
@@ -1102,24 +1110,37 @@ extern "C" int ubn_rgbnet_bwd_tc_data(const float* W2, const float* W3, const fl
 extern "C" int ubn_rgbnet_bwd_tc_fused(const float* feat, const int64_t* ray_id, const float* W1k, const float* W2, const float* W3,
                                        const float* rgb, const float* h1_save, const float* h2_save, const float* grad_rgb,
                                        int64_t n_pts, float* grad_feat, float* grad_view_bias, float* grad_W1k, float* grad_W2,
-                                       float* grad_b2, float* grad_W3, float* grad_b3, void* stream) {
+                                       float* grad_b2, float* grad_W3, float* grad_b3, int single_pass, void* stream) {
   if (n_pts <= 0) return 0;
   cudaStream_t st = as_stream(stream);
   {   // dX + every sample reduction except dW2
     const int64_t n_tiles = (n_pts + tc::kRows - 1) / tc::kRows;
     const unsigned grid = (unsigned)std::min<int64_t>(kNumSMs, n_tiles);
-    cudaError_t e = cudaFuncSetAttribute(tc::k_shade_bwd_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::bf::kSmemBytesF);
-    if (e != cudaSuccess) return finish(e);
-    tc::k_shade_bwd_fused<<<grid, tc::kRows, tc::bf::kSmemBytesF, st>>>(feat, ray_id, W1k, W2, W3, rgb, h1_save, h2_save, grad_rgb, n_pts,
-                                                                        grad_feat, grad_view_bias, grad_W1k, grad_b2, grad_W3, grad_b3);
+#define UBN_BF(T)                                                                                                              \
+    do {                                                                                                                       \
+      cudaError_t e = cudaFuncSetAttribute(tc::k_shade_bwd_fused<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,              \
+                                           (int)tc::bf::kSmemBytesF);                                                          \
+      if (e != cudaSuccess) return finish(e);                                                                                  \
+      tc::k_shade_bwd_fused<T><<<grid, tc::kRows, tc::bf::kSmemBytesF, st>>>(feat, ray_id, W1k, W2, W3, rgb, h1_save, h2_save, grad_rgb, \
+                                                                             n_pts, grad_feat, grad_view_bias, grad_W1k, grad_b2,       \
+                                                                             grad_W3, grad_b3);                                         \
+    } while (0)
+    if (single_pass) UBN_BF(false); else UBN_BF(true);
+#undef UBN_BF
     UBN_LAUNCH_CHECK();
   }
   {   // dW2 (split-K GEMM over all samples)
     const int64_t n_rounds = (n_pts + tc::dw::kK - 1) / tc::dw::kK;
     const unsigned grid = (unsigned)std::min<int64_t>((int64_t)kNumSMs * tc::dw::kCtasPerSM, n_rounds);
-    cudaError_t e = cudaFuncSetAttribute(tc::k_shade_dw2_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::dw::kSmemBytesD);
-    if (e != cudaSuccess) return finish(e);
-    tc::k_shade_dw2_tc<<<grid, tc::dw::kThreadsDW, tc::dw::kSmemBytesD, st>>>(W3, rgb, h1_save, h2_save, grad_rgb, n_pts, grad_W2);
+#define UBN_DW(T)                                                                                                              \
+    do {                                                                                                                       \
+      cudaError_t e = cudaFuncSetAttribute(tc::k_shade_dw2_tc<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,                 \
+                                           (int)tc::dw::kSmemBytesD);                                                          \
+      if (e != cudaSuccess) return finish(e);                                                                                  \
+      tc::k_shade_dw2_tc<T><<<grid, tc::dw::kThreadsDW, tc::dw::kSmemBytesD, st>>>(W3, rgb, h1_save, h2_save, grad_rgb, n_pts, grad_W2); \
+    } while (0)
+    if (single_pass) UBN_DW(false); else UBN_DW(true);
+#undef UBN_DW
     UBN_LAUNCH_CHECK();
   }
   return 0;
