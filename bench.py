@@ -401,6 +401,8 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference', 'reference-gpu'])
     ap.add_argument('--workload', default='truck', choices=['truck', 'bicycle', 'garden', 'missionbay'])
     ap.add_argument('--cpu-rays', type=int, default=1024, help='upper bound of the ray sample of the CPU legs (shrunk to fit the time budget)')
+    ap.add_argument('--feature-kernel', type=int, default=None, choices=[0, 1, 2],
+                    help='A/B: pass-B kernel family (0 warp-cooperative, 1 lane-per-sample forward, 2 forward + backward); default = library default')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-reference-gpu', action='store_true', help='skip the reference-GPU baseline leg (oracle/_ref + ATen) of the N = 1 line')
     ap.add_argument('--only-timed', action='store_true', help='warm-up + timed region only (for ncu captures)')
@@ -478,6 +480,9 @@ def main():
     from unboundednerfpytorch_b200.functional import render_loss
     from unboundednerfpytorch_b200.masked_adam import create_optimizer_or_freeze_model
     _cabi.load()
+    if args.feature_kernel is not None:
+        from unboundednerfpytorch_b200 import ops as _ops
+        _ops.set_feature_kernel(args.feature_kernel)
     torch.manual_seed(SEED)
     cls = models.FourierGridModel if flavor == 'fouriergrid' else models.DirectContractedVoxGO
     model = cls(**kwargs).to(dev)

@@ -308,6 +308,13 @@ int ubn_march_density_fwd(const float* rays_o, const float* rays_d, const float*
 /* Exclusive scan of n_keep -> offsets[n_rays+1] (offsets[n_rays] = M). scratch >= n_rays/1024+2 int64. */
 int ubn_exclusive_scan_i32(const int32_t* in, int64_t n, int64_t* offsets, int64_t* scratch, void* stream);
 
+/* Which pass-B kernel family serves 12-channel channels-last feature grids: 0 = warp-cooperative (lane = corner x channel quad),
+ * 1 = lane-per-sample for the forward, 2 = lane-per-sample for forward and backward.  Same results to fp32 rounding (the
+ * lane-per-sample forward is bit-identical to F.grid_sample(...).mean(0)); process-wide, not thread-safe against concurrent
+ * launches.  Returns cudaErrorInvalidValue for other values. */
+int ubn_set_feature_kernel(int variant);
+int ubn_get_feature_kernel(void);
+
 /* Pass B: for every survivor (flags bit1), in (ray, step) order at offsets[ray]+rank: recompute the
  * contracted point, query the feature grid (k0), and emit the compacted per-survivor records. */
 int ubn_march_feature_fwd(const float* rays_o, const float* rays_d, const float* t_table,

@@ -413,3 +413,47 @@ def test_psnr_gate_of_the_single_pass_tf32_mode(monkeypatch):
         assert abs(r['delta_db']) <= 0.01
         assert r['psnr_cuda_vs_oracle'] > 45.0
 
+
+@pytest.mark.parametrize('flavor,F_,thres', [('fouriergrid', 4, 0.0), ('fouriergrid', 2, 1e-4), ('dcvgo', 0, 1e-4)])
+def test_feature_kernel_families_agree(flavor, F_, thres):
+    """Pass B in its three forms (ubn_set_feature_kernel 0 / 1 / 2: warp-cooperative, lane-per-sample forward, lane-per-sample
+    forward + backward): identical survivors and records, features / rgb equal to fp32 rounding, k0 gradients equal to the
+    atomics' summation order; and the lane-per-sample forward is BIT-identical to the stand-alone grid op (ATen corner order +
+    torch-CUDA slab-mean order), i.e. to what F.grid_sample(...).mean(0) returns in the reference."""
+    from unboundednerfpytorch_b200 import ops
+    m, _ = _fresh_model(flavor, 40, F_, thres, 11, dens_mean=5.0 if thres else 0.0, dens_std=3.0 if thres else 1.0)
+    m = m.to(DEV)
+    ro, rd, vd = seeded_rays(700, 12, DEV)
+    rk = dict(near=0., far=1e9, bg=1, rand_bkgd=False, stepsize=0.5, render_depth=True)
+    outs, grads = [], []
+    try:
+        for variant in (0, 1, 2):
+            ops.set_feature_kernel(variant)
+            assert ops.get_feature_kernel() == variant
+            m.zero_grad(set_to_none=True)
+            ret = m(ro, rd, vd, global_step=None, **rk)
+            (ret['rgb_marched'].sum() + 0.1 * ret['raw_rgb'].pow(2).sum()).backward()
+            outs.append(ret)
+            grads.append(m.k0.grid.grad.detach().clone())
+    finally:
+        ops.set_feature_kernel(0)
+    for ret in outs[1:]:
+        assert torch.equal(ret['ray_id'], outs[0]['ray_id']) and torch.equal(ret['step_id'], outs[0]['step_id'])
+        for k in ('weights', 'raw_density', 't'):
+            assert torch.equal(ret[k], outs[0][k]), k
+        assert_close(ret['raw_rgb'], outs[0]['raw_rgb'], rtol=1e-5, atol=1e-6, what='raw_rgb across kernel families')
+        assert_close(ret['rgb_marched'], outs[0]['rgb_marched'], rtol=1e-5, atol=1e-6, what='rgb_marched across kernel families')
+    for gk in grads[1:]:
+        scale = float(grads[0].abs().max())
+        assert_close(gk, grads[0], rtol=1e-4, atol=1e-5 * scale, what='k0 grad across kernel families')
+    # bit parity of the lane-per-sample forward with the stand-alone grid op on the same sample positions
+    with torch.no_grad():
+        ops.set_feature_kernel(1)
+        try:
+            (w, last, alpha, dens, k0, ray_id, step_id, t, inner), _ = m._march(ro, rd, 0.5)
+        finally:
+            ops.set_feature_kernel(0)
+        pts, _, _ = m._sample_dense(ro, rd, 0.5)
+        want = m.k0(pts[ray_id, step_id])
+    assert torch.equal(k0, want), f'{int((k0 != want).sum())} of {k0.numel()} feature values differ from the grid op'
+

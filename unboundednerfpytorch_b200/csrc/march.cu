@@ -320,6 +320,9 @@ int march_feature_v2(bool backward, const float* rays_o, const float* rays_d, co
                      float* o_density, float* o_alpha, float* o_weight, int64_t* o_ray_id, int64_t* o_step_id, float* o_t,
                      uint8_t* o_inner, cudaStream_t st);
 
+void set_feature_kernel(int v);
+int get_feature_kernel();
+
 static bool feature_grid_ok(const GridView& g) {
   return g.sc == 1 && g.sv == g.C && (g.C == 4 || g.C == 8 || g.C == 12 || g.C == 16) && g.P <= 16 &&
          ((uintptr_t)g.data & 15) == 0 && (g.sp % 4) == 0;
@@ -330,6 +333,13 @@ static bool feature_grid_ok(const GridView& g) {
 using namespace ubn;
 
 extern "C" {
+
+int ubn_set_feature_kernel(int variant) {
+  if (variant < 0 || variant > 2) return finish(cudaErrorInvalidValue);
+  set_feature_kernel(variant);
+  return 0;
+}
+int ubn_get_feature_kernel(void) { return get_feature_kernel(); }
 
 int ubn_march_density_fwd(const float* rays_o, const float* rays_d, const float* t_table, const float* density_grid,
                           const UbnGridDesc* density_desc, const uint8_t* mask_world, const UbnMarchCfg* cfg,

@@ -198,6 +198,172 @@ static int launch_v2(bool backward, const float* rays_o, const float* rays_d, co
   return 0;
 }
 
+// =====================================================================================================================
+// Third generation: LANE = SAMPLE.  The cooperative kernels above spend one warp instruction per (sample, slab) -- 24 of 32
+// lanes fetch the 8 x 48-byte corner records of ONE sample, then 12 shuffles reduce the corners: ~17 issue slots and 4 broadcast
+// shuffles per sample-slab, few independent loads in flight per warp (ncu, round 1: issue 46 % busy, DRAM 19 %, 29 % of the
+// warps resident, long-scoreboard bound).  Here every lane owns one surviving sample of the chunk and walks its own 8 corners:
+//   * 24 independent 128-bit loads per lane and slab (8 corners x 3 channel quads), no shuffles, no cross-lane reduction:
+//     ~4.7 issue slots per sample-slab, and 8-24 loads in flight per LANE instead of per warp;
+//   * adjacent lanes are adjacent samples of a ray (half a voxel apart), so the same-corner loads of a warp instruction
+//     fall into a handful of neighbouring records and coalesce in the LSU;
+//   * per slab the 8 products are accumulated in ATen's corner order (FMA chain tnw .. bse) and the slabs are combined in
+//     torch-CUDA's mean order (four interleaved accumulators, trilinear.cuh::SlabMean): the features are bit-identical to
+//     F.grid_sample(...).mean(0), i.e. to the reference's GPU path;
+//   * survivors of a 32-sample chunk are compacted to the low lanes (3 shuffles per chunk) so output rows are written
+//     coalesced in (ray, step) order.
+// C = 12 channels-last grids (every shipped config); other channel counts keep the cooperative kernels.
+// =====================================================================================================================
+template <int kP>
+__device__ __forceinline__ void slab_cell(const GridView& g, int sl, float nx, float ny, float nz, CellR& c) {
+  c = make_cell(src_index(fourier_gamma(sl, nx), g.X), src_index(fourier_gamma(sl, ny), g.Y), src_index(fourier_gamma(sl, nz), g.Z),
+                g.X, g.Y, g.Z);
+}
+
+template <int kP, bool kBackward>
+__global__ void __launch_bounds__(32 * kMarchWarps, 4) k_march_feature_v3(
+    const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float* __restrict__ t_table,
+    GridView g, MarchParams p, int64_t n_rays, const uint8_t* __restrict__ flags,
+    const int64_t* __restrict__ offsets, const float* __restrict__ density, const float* __restrict__ alpha,
+    const float* __restrict__ weight, float* __restrict__ feat /* out (fwd) or grad in (bwd) */,
+    float* __restrict__ grad_grid, float* __restrict__ o_density, float* __restrict__ o_alpha,
+    float* __restrict__ o_weight, int64_t* __restrict__ o_ray_id, int64_t* __restrict__ o_step_id,
+    float* __restrict__ o_t, uint8_t* __restrict__ o_inner) {
+  constexpr int kC = 12;
+  const int lane = threadIdx.x & 31;
+  const int64_t ray = (int64_t)blockIdx.x * kMarchWarps + (threadIdx.x >> 5);
+  if (ray >= n_rays) return;
+  int64_t out_base = offsets[ray];
+  const int64_t out_end = offsets[ray + 1];
+  if (out_base == out_end) return;
+  const Ray r = load_ray(rays_o + 3 * ray, rays_d + 3 * ray, p);
+  const int S = p.S;
+  const int dY = g.Z * kC, dX = g.Y * g.Z * kC;        // record strides (floats) of +1 in y / x; +1 in z is kC
+
+  for (int base = 0; base < S && out_base < out_end; base += 32) {
+    const int s = base + lane;
+    const uint8_t f = (s < S) ? flags[ray * S + s] : 0;
+    const bool keep = (f & UBN_FLAG_KEEP) != 0;
+    const unsigned km = __ballot_sync(0xffffffffu, keep);
+    if (km == 0) continue;
+    const int n_here = __popc(km);
+    const int rank = __popc(km & ((1u << lane) - 1));
+    float nx = 0.f, ny = 0.f, nz = 0.f;
+    if (keep) {
+      float x, y, z;
+      const float t = t_table[s];
+      sample_point(r, t, p, x, y, z);
+      nx = norm_coord(x, g.mn[0], g.len[0]);
+      ny = norm_coord(y, g.mn[1], g.len[1]);
+      nz = norm_coord(z, g.mn[2], g.len[2]);
+      if (!kBackward) {
+        const int64_t o = out_base + rank;
+        const int64_t i = ray * S + s;
+        o_density[o] = density[i];
+        o_alpha[o] = alpha[i];
+        o_weight[o] = weight[i];
+        o_ray_id[o] = ray;
+        o_step_id[o] = s;
+        o_t[o] = t;
+        o_inner[o] = (f & UBN_FLAG_INNER) ? 1 : 0;
+      }
+    }
+    if (km != 0xffffffffu) {            // compact: lane i takes the i-th survivor of the chunk
+      const int src = __fns(km, 0, lane + 1) & 31;
+      nx = __shfl_sync(0xffffffffu, nx, src);
+      ny = __shfl_sync(0xffffffffu, ny, src);
+      nz = __shfl_sync(0xffffffffu, nz, src);
+    }
+    const bool act = lane < n_here;
+    const int64_t row = out_base + lane;
+    if (!kBackward) {
+      // slabs visited in torch's mean order: accumulator a = slab & 3, i.e. 0,4,8 | 1,5,9 | 2,6 | 3,7 ...; `tot` = ((a0 + a1) + a2) + a3
+      float tot[kC], grp[kC];
+#pragma unroll
+      for (int a = 0; a < 4 && a < kP; ++a) {
+#pragma unroll
+        for (int sl = a; sl < kP; sl += 4) {
+          float val[kC];
+#pragma unroll
+          for (int c = 0; c < kC; ++c) val[c] = 0.f;
+          if (act) {
+            CellR cell;
+            slab_cell<kP>(g, sl, nx, ny, nz, cell);
+            const float* rec = g.data + sl * g.sp + (int64_t)cell.v * kC;
+#pragma unroll
+            for (int corner = 0; corner < 8; ++corner) {          // tnw, tne, tsw, tse, bnw, bne, bsw, bse (z fastest)
+              const int bx = corner >> 2, by = (corner >> 1) & 1, bz = corner & 1;
+              const float wgt = ((bz ? cell.fz : 1.f - cell.fz) * (by ? cell.fy : 1.f - cell.fy)) * (bx ? cell.fx : 1.f - cell.fx);
+              const float4* q = reinterpret_cast<const float4*>(rec + bx * dX + by * dY + bz * kC);
+              const float4 v0 = __ldg(q), v1 = __ldg(q + 1), v2 = __ldg(q + 2);
+              val[0] = fmaf(v0.x, wgt, val[0]); val[1] = fmaf(v0.y, wgt, val[1]); val[2] = fmaf(v0.z, wgt, val[2]); val[3] = fmaf(v0.w, wgt, val[3]);
+              val[4] = fmaf(v1.x, wgt, val[4]); val[5] = fmaf(v1.y, wgt, val[5]); val[6] = fmaf(v1.z, wgt, val[6]); val[7] = fmaf(v1.w, wgt, val[7]);
+              val[8] = fmaf(v2.x, wgt, val[8]); val[9] = fmaf(v2.y, wgt, val[9]); val[10] = fmaf(v2.z, wgt, val[10]); val[11] = fmaf(v2.w, wgt, val[11]);
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < kC; ++c) grp[c] = (sl == a) ? __fadd_rn(0.f, val[c]) : __fadd_rn(grp[c], val[c]);
+        }
+#pragma unroll
+        for (int c = 0; c < kC; ++c) tot[c] = (a == 0) ? grp[c] : __fadd_rn(tot[c], grp[c]);
+      }
+      if (act) {
+        float4* o = reinterpret_cast<float4*>(feat + row * kC);
+        o[0] = make_float4(slab_mean_scale(tot[0], kP), slab_mean_scale(tot[1], kP), slab_mean_scale(tot[2], kP), slab_mean_scale(tot[3], kP));
+        o[1] = make_float4(slab_mean_scale(tot[4], kP), slab_mean_scale(tot[5], kP), slab_mean_scale(tot[6], kP), slab_mean_scale(tot[7], kP));
+        o[2] = make_float4(slab_mean_scale(tot[8], kP), slab_mean_scale(tot[9], kP), slab_mean_scale(tot[10], kP), slab_mean_scale(tot[11], kP));
+      }
+    } else if (act) {
+      const float4* gi = reinterpret_cast<const float4*>(feat + row * kC);
+      float4 g0 = gi[0], g1 = gi[1], g2 = gi[2];
+      g0.x = slab_mean_scale(g0.x, kP); g0.y = slab_mean_scale(g0.y, kP); g0.z = slab_mean_scale(g0.z, kP); g0.w = slab_mean_scale(g0.w, kP);
+      g1.x = slab_mean_scale(g1.x, kP); g1.y = slab_mean_scale(g1.y, kP); g1.z = slab_mean_scale(g1.z, kP); g1.w = slab_mean_scale(g1.w, kP);
+      g2.x = slab_mean_scale(g2.x, kP); g2.y = slab_mean_scale(g2.y, kP); g2.z = slab_mean_scale(g2.z, kP); g2.w = slab_mean_scale(g2.w, kP);
+#pragma unroll
+      for (int sl = 0; sl < kP; ++sl) {
+        CellR cell;
+        slab_cell<kP>(g, sl, nx, ny, nz, cell);
+        float* rec = grad_grid + sl * g.sp + (int64_t)cell.v * kC;
+#pragma unroll
+        for (int corner = 0; corner < 8; ++corner) {
+          const int bx = corner >> 2, by = (corner >> 1) & 1, bz = corner & 1;
+          const float wgt = ((bz ? cell.fz : 1.f - cell.fz) * (by ? cell.fy : 1.f - cell.fy)) * (bx ? cell.fx : 1.f - cell.fx);
+          float* q = rec + bx * dX + by * dY + bz * kC;
+          red_add_v4(q, make_float4(wgt * g0.x, wgt * g0.y, wgt * g0.z, wgt * g0.w));
+          red_add_v4(q + 4, make_float4(wgt * g1.x, wgt * g1.y, wgt * g1.z, wgt * g1.w));
+          red_add_v4(q + 8, make_float4(wgt * g2.x, wgt * g2.y, wgt * g2.z, wgt * g2.w));
+        }
+      }
+    }
+    out_base += n_here;
+  }
+}
+
+template <int kP>
+static int launch_v3(bool backward, const float* rays_o, const float* rays_d, const float* t_table, const GridView& g,
+                     const MarchParams& p, int64_t n_rays, const uint8_t* flags, const int64_t* offsets,
+                     const float* density, const float* alpha, const float* weight, float* feat, float* grad_grid,
+                     float* o_density, float* o_alpha, float* o_weight, int64_t* o_ray_id, int64_t* o_step_id, float* o_t,
+                     uint8_t* o_inner, cudaStream_t st) {
+  const unsigned nb = blocks_for(n_rays, kMarchWarps);
+  if (backward)
+    k_march_feature_v3<kP, true><<<nb, 32 * kMarchWarps, 0, st>>>(rays_o, rays_d, t_table, g, p, n_rays, flags, offsets, density, alpha,
+                                                                  weight, feat, grad_grid, o_density, o_alpha, o_weight, o_ray_id,
+                                                                  o_step_id, o_t, o_inner);
+  else
+    k_march_feature_v3<kP, false><<<nb, 32 * kMarchWarps, 0, st>>>(rays_o, rays_d, t_table, g, p, n_rays, flags, offsets, density, alpha,
+                                                                   weight, feat, grad_grid, o_density, o_alpha, o_weight, o_ray_id,
+                                                                   o_step_id, o_t, o_inner);
+  UBN_LAUNCH_CHECK();
+  return 0;
+}
+
+// 0 = warp-cooperative kernels (v2), 1 = lane-per-sample (v3) for the forward, 2 = for forward and backward.  Set through
+// ubn_set_feature_kernel (tests exercise every value); the default is chosen from the measurements in profiles/.
+static int g_feature_kernel = 0;
+void set_feature_kernel(int v) { g_feature_kernel = v; }
+int get_feature_kernel() { return g_feature_kernel; }
+
 // returns -1 when this configuration is not covered (caller falls back to the generic kernel)
 int march_feature_v2(bool backward, const float* rays_o, const float* rays_d, const float* t_table, const GridView& g,
                      const MarchParams& p, int64_t n_rays, const uint8_t* flags, const int64_t* offsets,
@@ -206,6 +372,21 @@ int march_feature_v2(bool backward, const float* rays_o, const float* rays_d, co
                      uint8_t* o_inner, cudaStream_t st) {
   if (g.X < 2 || g.Y < 2 || g.Z < 2) return -1;
   if ((int64_t)g.X * g.Y * g.Z * g.C >= (1ll << 31)) return -1;   // 32-bit voxel offsets inside a slab
+  if (g.C == 12 && (g_feature_kernel == 2 || (g_feature_kernel == 1 && !backward))) {
+#define UBN_V3(P)                                                                                                               \
+  case P:                                                                                                                       \
+    return launch_v3<P>(backward, rays_o, rays_d, t_table, g, p, n_rays, flags, offsets, density, alpha, weight, feat, grad_grid, \
+                        o_density, o_alpha, o_weight, o_ray_id, o_step_id, o_t, o_inner, st)
+    switch (g.P) {
+      UBN_V3(1);
+      UBN_V3(3);
+      UBN_V3(5);
+      UBN_V3(7);
+      UBN_V3(9);
+      default: break;
+    }
+#undef UBN_V3
+  }
   // forward: groups of 2 samples (80 registers, 6 CTAs/SM won the occupancy sweep); backward: groups of 4 (the vector reductions
   // need no result, deeper batching costs nothing).  Round 1's other variants (groups of 1 / 8, the env switch) are gone.
 #define UBN_V2(P)                                                                                                       \

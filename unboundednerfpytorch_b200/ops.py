@@ -429,6 +429,18 @@ def maskout_near_cam_(slab, cams, near_clip, fill=-100.0):
     return slab
 
 
+def set_feature_kernel(variant):
+    """Pass-B kernel family for 12-channel channels-last feature grids: 0 = warp-cooperative, 1 = lane-per-sample forward,
+    2 = lane-per-sample forward + backward (ubn_set_feature_kernel).  Process-wide."""
+    from ._cabi import load
+    check(load().ubn_set_feature_kernel(c_int(int(variant))))
+
+
+def get_feature_kernel():
+    from ._cabi import load
+    return int(load().ubn_get_feature_kernel())
+
+
 def cumdist_thres(dist, thres):
     _chk(dist, 'dist')
     mask = torch.empty(dist.shape, dtype=torch.bool, device=dist.device)
