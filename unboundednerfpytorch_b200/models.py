@@ -305,7 +305,9 @@ class FourierGridModel(_ContractedBase):
         freqs = 2 ** torch.linspace(0, F_ - 1, F_, device=dev)
         emb = [ind_norm] + [f(fr * ind_norm) for fr in freqs for f in (torch.sin, torch.cos)]      # gamma_i of FourierGrid_grid.py:32-36
         for i, cam in enumerate(emb):
-            ops.maskout_near_cam_(self.density.grid.data[0][i], cam.reshape(-1, 3), near_clip, -100.0)   # same indexing as :388
+            # the reference writes `self.density.grid[0][i][...] = -100` (:388), which for its own [P,1,X,Y,Z] density grid raises an
+            # IndexError at i = 1; the evident intent -- slab i, masked in slab i's embedded coordinates -- is grid[i][0]
+            ops.maskout_near_cam_(self.density.grid.data[i][0], cam.reshape(-1, 3), near_clip, -100.0)
 
     def voxel_count_views(self, rays_o_tr, rays_d_tr, imsz, near, far, stepsize, downrate=1, irregular_shape=False):
         """FourierGrid_model.py:390-420: per-voxel number of training views that see it.  The reference materialises the sample
