@@ -389,7 +389,8 @@ int ubn_rgbnet_bwd_small(const float* feat, const int64_t* ray_id, const float* 
  *            reduction over samples except dW2 (grad_view_bias per ray, grad_W1k, grad_b2, grad_W3, grad_b3) from warp-transposed
  *            32 x 32 chunks of H2 / dZ1 held in shared memory;   launch 2: grad_W2 += dZ2^T.H1 (split-K tcgen05 GEMM).
  * Replaces ubn_rgbnet_bwd_tc_data + ubn_rgbnet_bwd_small (which round-tripped dZ1 [n_pts,128] through HBM and re-read H2).
- * single_pass != 0: one TF32 pass per product instead of the 3-pass split (the opt-in reduced-precision training mode). */
+ * single_pass bit 0: one TF32 pass per product instead of the 3-pass split (the opt-in reduced-precision training mode);
+ * bit 1: launch 1 without warp specialisation (4 warps do the tensor-core chain AND the sample reductions; A/B). */
 int ubn_rgbnet_bwd_tc_fused(const float* feat, const int64_t* ray_id, const float* W1k, const float* W2, const float* W3,
                             const float* rgb, const float* h1_save, const float* h2_save, const float* grad_rgb, int64_t n_pts,
                             float* grad_feat, float* grad_view_bias, float* grad_W1k, float* grad_W2, float* grad_b2,

@@ -221,12 +221,12 @@ def test_training_step_reduces_loss():
     assert all(torch.isfinite(p).all() for p in student.parameters())
 
 
-@pytest.mark.parametrize('mode', ['simt', 'tc3', 'tc1', 'tc3+tcbwd', 'tc3+fused', 'tc1+fused'])
+@pytest.mark.parametrize('mode', ['simt', 'tc3', 'tc1', 'tc3+tcbwd', 'tc3+fused', 'tc3+fused4', 'tc1+fused'])
 def test_fused_rgbnet_vs_torch(mode, monkeypatch):
     """csrc/shade.cu (fp32 FFMA) and csrc/shade_tc.cu (tcgen05: 3xTF32 fp32-grade, single-pass TF32 preview) vs the torch
     nn.Sequential they replace: forward and every gradient."""
     from unboundednerfpytorch_b200 import models, shade as shade_mod
-    monkeypatch.setattr(shade_mod, 'BWD_MODE', 'tc3' if mode.endswith('tcbwd') else ('fused' if mode.endswith('fused') else 'simt'))
+    monkeypatch.setattr(shade_mod, 'BWD_MODE', {'tcbwd': 'tc3', 'fused': 'fused', 'fused4': 'fused4'}.get(mode.split('+')[-1], 'simt'))
     mode = mode.split('+')[0]
     monkeypatch.setattr(shade_mod, 'MODE', mode)
     fwd_tol = dict(rtol=1e-5, atol=1e-6) if mode != 'tc1' else dict(rtol=5e-3, atol=5e-3)
@@ -258,7 +258,7 @@ def test_fused_rgbnet_vs_torch(mode, monkeypatch):
         net.zero_grad(); k0.grad = None
         out = shade_mod.shade(net, k0, emb, ray_id)
         assert_close(out, ref, what=f'rgb M={M} {mode}', **fwd_tol)
-        if mode == 'tc1' and shade_mod.BWD_MODE != 'fused':
+        if mode == 'tc1' and shade_mod.BWD_MODE not in ('fused', 'fused4'):
             continue
         (out * gr).sum().backward()
         got = [k0.grad] + [p.grad for p in net.parameters()]

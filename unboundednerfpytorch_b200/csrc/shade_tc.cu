@@ -917,6 +917,351 @@ __global__ void __launch_bounds__(kRows, 1) k_shade_bwd_fused(
 }
 
 
+// =====================================================================================================================
+// k_shade_bwd_fused, warp-specialised: the sample reductions of the kernel above cost as much as its tensor-core chain when the
+// same four warps do both (measured: 18.5 us per 128-sample tile against 9.5 us for the chain alone -- one warp per scheduler
+// cannot hide the shared-memory latency of the column loops).  Here the CTA has EIGHT warps:
+//   warps 0-3 (row warps, thread = sample row): dZ2 -> TMEM, dH1 MMA, dZ1 -> TMEM, dX MMA, dX store -- and after computing a
+//       32 x 32 chunk of H2 / dZ1 they only STAGE it in shared memory (double-buffered per warp) and signal an mbarrier;
+//   warps 4-7 (column warps, lane = hidden unit): consume the staged chunks of "their" row warp: db2 / dW3 from H2 chunks, dvb
+//       (per ray) / dW1k from dZ1 chunks, releasing each buffer through a second mbarrier.
+// The two halves run concurrently on the four schedulers (two warps each).  Per-tile row tables (dz3, ray id, X) are
+// double-buffered by tile parity; the producer can run at most two chunks ahead, so a table is never overwritten while in use.
+// =====================================================================================================================
+namespace bf2 {
+constexpr uint32_t oVThi = 0;
+constexpr uint32_t oVTlo = oVThi + (kHidden / 4) * kPanelBytes;
+constexpr uint32_t oV1hi = oVTlo + (kHidden / 4) * kPanelBytes;
+constexpr uint32_t oV1lo = oV1hi + (kHidden / 4) * bf::kPanelN16;
+constexpr uint32_t oStg2 = oV1lo + (kHidden / 4) * bf::kPanelN16;   // [4 row warps][2][32 x 36 floats]
+constexpr uint32_t oX2 = oStg2 + 8 * kStgBytesPerWarp;              // [2][128][12]
+constexpr uint32_t oDz32 = oX2 + 2 * kRows * kFeat * 4;             // [2][128] float4
+constexpr uint32_t oRay2 = oDz32 + 2 * kRows * 16;                  // [2][128] int
+constexpr uint32_t oW32 = oRay2 + 2 * kRows * 4;                    // [3][128]
+constexpr uint32_t oAccW1b = oW32 + 3 * kHidden * 4;
+constexpr uint32_t oAccW3b = oAccW1b + kHidden * kFeat * 4;
+constexpr uint32_t oAccB2b = oAccW3b + 3 * kHidden * 4;
+constexpr uint32_t oAccB3b = oAccB2b + kHidden * 4;
+constexpr uint32_t oFull = oAccB3b + 16;                             // [4][2] mbarriers
+constexpr uint32_t oEmpty = oFull + 64;                              // [4][2]
+constexpr uint32_t oBar2 = oEmpty + 64;                              // MMA mbarrier + TMEM slot
+constexpr uint32_t kSmemBytesF2 = oBar2 + 16;
+}  // namespace bf2
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar_smem) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_smem) : "memory");
+}
+__device__ __forceinline__ void row_warps_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+template <bool kThree>
+__global__ void __launch_bounds__(2 * kRows, 1) k_shade_bwd_fused_ws(
+    const float* __restrict__ feat, const int64_t* __restrict__ ray_id, const float* __restrict__ W1k,
+    const float* __restrict__ W2, const float* __restrict__ W3, const float* __restrict__ rgb,
+    const float* __restrict__ h1, const float* __restrict__ h2, const float* __restrict__ g_rgb, int64_t n_pts,
+    float* __restrict__ g_feat, float* __restrict__ g_vb, float* __restrict__ gW1k, float* __restrict__ gb2,
+    float* __restrict__ gW3, float* __restrict__ gb3) {
+  using namespace bf2;
+  using bf::cAhi; using bf::cAlo; using bf::cDHf; using bf::cDX; using bf::kIdescN16; using bf::kPanelN16;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool is_row = warp < 4;
+  const int rw = warp & 3;                                  // the row warp this warp is / serves
+  float* sW3 = reinterpret_cast<float*>(smem + oW32);
+  float* sAccW1 = reinterpret_cast<float*>(smem + oAccW1b);
+  float* sAccW3 = reinterpret_cast<float*>(smem + oAccW3b);
+  float* sAccB2 = reinterpret_cast<float*>(smem + oAccB2b);
+  float* sAccB3 = reinterpret_cast<float*>(smem + oAccB3b);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + oBar2);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + oBar2 + 8);
+  const uint32_t bar_addr = smem_u32(bar);
+  const uint32_t full0 = smem_u32(smem + oFull + rw * 16), empty0 = smem_u32(smem + oEmpty + rw * 16);   // + 8 * buffer
+
+  for (int i = tid; i < kHidden * kHidden; i += 2 * kRows) {
+    const int j = i / kHidden, k = i % kHidden;
+    const float w = W2[i];
+    const uint32_t hb = tf32_hi_bits(w);
+    const uint32_t off = (uint32_t)(j >> 2) * kPanelBytes + (uint32_t)k * 16 + (uint32_t)(j & 3) * 4;
+    *reinterpret_cast<uint32_t*>(smem + oVThi + off) = hb;
+    *reinterpret_cast<float*>(smem + oVTlo + off) = w - __uint_as_float(hb);
+  }
+  for (int i = tid; i < kHidden * 16; i += 2 * kRows) {
+    const int j = i >> 4, c = i & 15;
+    const float w = (c < kFeat) ? W1k[j * kFeat + c] : 0.f;
+    const uint32_t hb = tf32_hi_bits(w);
+    const uint32_t off = (uint32_t)(j >> 2) * kPanelN16 + (uint32_t)c * 16 + (uint32_t)(j & 3) * 4;
+    *reinterpret_cast<uint32_t*>(smem + oV1hi + off) = hb;
+    *reinterpret_cast<float*>(smem + oV1lo + off) = w - __uint_as_float(hb);
+  }
+  for (int i = tid; i < 3 * kHidden; i += 2 * kRows) { sW3[i] = W3[i]; sAccW3[i] = 0.f; }
+  for (int i = tid; i < kHidden * kFeat; i += 2 * kRows) sAccW1[i] = 0.f;
+  if (tid < kHidden) sAccB2[tid] = 0.f;
+  if (tid < 4) sAccB3[tid] = 0.f;
+  if (tid == 0) {
+    mbar_init(bar_addr, 1);
+    for (int q = 0; q < 8; ++q) {
+      mbar_init(smem_u32(smem + oFull + q * 8), 1);
+      mbar_init(smem_u32(smem + oEmpty + q * 8), 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  const int64_t n_tiles = (n_pts + kRows - 1) / kRows;
+  const int64_t per_cta = (n_tiles + gridDim.x - 1) / gridDim.x;
+  const int64_t tile_begin = (int64_t)blockIdx.x * per_cta, tile_end = min(n_tiles, tile_begin + per_cta);
+  uint32_t seq = 0;                                         // chunk-phase counter of this (row warp, column warp) pair
+
+  if (is_row) {
+    // ================================================= row warps =================================================
+    const int rtid = tid;                                   // 0..127 = row within the tile
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    uint32_t phase = 0;
+    const uint64_t dWThi = make_desc(smem_u32(smem + oVThi)), dWTlo = make_desc(smem_u32(smem + oVTlo));
+    const uint64_t dW1hi = make_desc_lbo(smem_u32(smem + oV1hi), kPanelN16), dW1lo = make_desc_lbo(smem_u32(smem + oV1lo), kPanelN16);
+    constexpr uint64_t kStepK = (uint64_t)((2 * kPanelBytes) >> 4);
+    constexpr uint64_t kStepK16 = (uint64_t)((2 * kPanelN16) >> 4);
+    float b3a = 0.f, b3b = 0.f, b3c = 0.f;
+    auto publish = [&](const float4 (&q8)[8]) {            // stage one 32 x 32 chunk for the column warp
+      const uint32_t b = seq & 1, use = seq >> 1;
+      if (use > 0) mbar_wait(empty0 + 8 * b, (use - 1) & 1);
+      float* stg = reinterpret_cast<float*>(smem + oStg2 + (rw * 2 + b) * kStgBytesPerWarp);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(stg + lane * kStgStride + i * 4) = q8[i];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full0 + 8 * b);
+      ++seq;
+    };
+    for (int64_t tile = tile_begin; tile < tile_end; ++tile) {
+      const int tp = (int)((tile - tile_begin) & 1);
+      float* sX = reinterpret_cast<float*>(smem + oX2) + tp * kRows * kFeat;
+      float4* sDz3 = reinterpret_cast<float4*>(smem + oDz32) + tp * kRows;
+      int* sRay = reinterpret_cast<int*>(smem + oRay2) + tp * kRows;
+      const int64_t row = tile * kRows + rtid;
+      const bool live = row < n_pts;
+      float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+      {
+        int my_ray = -1;
+        float4 x0 = make_float4(0, 0, 0, 0), x1 = x0, x2 = x0;
+        if (live) {
+          const float* o = rgb + row * 3;
+          const float* g = g_rgb + row * 3;
+          d0 = g[0] * (o[0] * (1.f - o[0]));
+          d1 = g[1] * (o[1] * (1.f - o[1]));
+          d2 = g[2] * (o[2] * (1.f - o[2]));
+          my_ray = (int)ray_id[row];
+          const float4* xr = reinterpret_cast<const float4*>(feat + row * kFeat);
+          x0 = __ldg(xr); x1 = __ldg(xr + 1); x2 = __ldg(xr + 2);
+        }
+        sDz3[rtid] = make_float4(d0, d1, d2, 0.f);
+        sRay[rtid] = my_ray;
+        float4* xs = reinterpret_cast<float4*>(sX + rtid * kFeat);
+        xs[0] = x0; xs[1] = x1; xs[2] = x2;
+        b3a += d0; b3b += d1; b3c += d2;
+      }
+      float4 hrow[kHidden / 4];
+#pragma unroll
+      for (int q = 0; q < kHidden / 4; ++q) {
+        hrow[q] = make_float4(0, 0, 0, 0);
+        if (live) hrow[q] = __ldg(reinterpret_cast<const float4*>(h2 + row * kHidden + q * 4));
+      }
+#pragma unroll
+      for (int c = 0; c < kHidden / 32; ++c) {
+        uint32_t hi[32], lo[32];
+        float4 q8[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 hv = hrow[c * 8 + q];
+          q8[q] = hv;
+          const float4 wa = *reinterpret_cast<const float4*>(sW3 + c * 32 + q * 4);
+          const float4 wb = *reinterpret_cast<const float4*>(sW3 + kHidden + c * 32 + q * 4);
+          const float4 wc = *reinterpret_cast<const float4*>(sW3 + 2 * kHidden + c * 32 + q * 4);
+          const float z[4] = {hv.x > 0.f ? fmaf(d2, wc.x, fmaf(d1, wb.x, d0 * wa.x)) : 0.f,
+                              hv.y > 0.f ? fmaf(d2, wc.y, fmaf(d1, wb.y, d0 * wa.y)) : 0.f,
+                              hv.z > 0.f ? fmaf(d2, wc.z, fmaf(d1, wb.z, d0 * wa.z)) : 0.f,
+                              hv.w > 0.f ? fmaf(d2, wc.w, fmaf(d1, wb.w, d0 * wa.w)) : 0.f};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const uint32_t hb = tf32_hi_bits(z[e]);
+            hi[q * 4 + e] = hb;
+            lo[q * 4 + e] = __float_as_uint(z[e] - __uint_as_float(hb));
+          }
+        }
+        tmem_st32(tmem + lane_base + cAhi + c * 32, hi);
+        if (kThree) tmem_st32(tmem + lane_base + cAlo + c * 32, lo);
+        publish(q8);                                        // H2 chunk -> db2 / dW3 on the column warp
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      row_warps_sync();
+      if (tid == 0) {
+        tc_fence_after();
+#pragma unroll 4
+        for (int ks = 0; ks < kHidden / 8; ++ks) {
+          mma_ts(tmem + cDHf, tmem + cAhi + ks * 8, dWThi + ks * kStepK, ks > 0);
+          if (kThree) {
+            mma_ts(tmem + cDHf, tmem + cAlo + ks * 8, dWThi + ks * kStepK, 1);
+            mma_ts(tmem + cDHf, tmem + cAhi + ks * 8, dWTlo + ks * kStepK, 1);
+          }
+        }
+        mma_commit(bar_addr);
+      }
+#pragma unroll
+      for (int q = 0; q < kHidden / 4; ++q) {
+        hrow[q] = make_float4(0, 0, 0, 0);
+        if (live) hrow[q] = __ldg(reinterpret_cast<const float4*>(h1 + row * kHidden + q * 4));
+      }
+      mbar_wait(bar_addr, phase);
+      phase ^= 1;
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < kHidden / 32; ++c) {
+        float v[32];
+        tmem_ld32(tmem + lane_base + cDHf + c * 32, v);
+        uint32_t hi[32], lo[32];
+        float4 q8[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 hv = hrow[c * 8 + q];
+          q8[q].x = hv.x > 0.f ? v[q * 4] : 0.f; q8[q].y = hv.y > 0.f ? v[q * 4 + 1] : 0.f;
+          q8[q].z = hv.z > 0.f ? v[q * 4 + 2] : 0.f; q8[q].w = hv.w > 0.f ? v[q * 4 + 3] : 0.f;
+          const float zs[4] = {q8[q].x, q8[q].y, q8[q].z, q8[q].w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const uint32_t hb = tf32_hi_bits(zs[e]);
+            hi[q * 4 + e] = hb;
+            lo[q * 4 + e] = __float_as_uint(zs[e] - __uint_as_float(hb));
+          }
+        }
+        tmem_st32(tmem + lane_base + cAhi + c * 32, hi);
+        if (kThree) tmem_st32(tmem + lane_base + cAlo + c * 32, lo);
+        publish(q8);                                        // dZ1 chunk -> dvb / dW1k on the column warp
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      row_warps_sync();
+      if (tid == 0) {
+        tc_fence_after();
+#pragma unroll 4
+        for (int ks = 0; ks < kHidden / 8; ++ks) {
+          mma_ts_idesc(tmem + cDX, tmem + cAhi + ks * 8, dW1hi + ks * kStepK16, kIdescN16, ks > 0);
+          if (kThree) {
+            mma_ts_idesc(tmem + cDX, tmem + cAlo + ks * 8, dW1hi + ks * kStepK16, kIdescN16, 1);
+            mma_ts_idesc(tmem + cDX, tmem + cAhi + ks * 8, dW1lo + ks * kStepK16, kIdescN16, 1);
+          }
+        }
+        mma_commit(bar_addr);
+      }
+      mbar_wait(bar_addr, phase);
+      phase ^= 1;
+      tc_fence_after();
+      {
+        float v[16];
+        tmem_ld16(tmem + lane_base + cDX, v);
+        if (live) {
+          float4* o = reinterpret_cast<float4*>(g_feat + row * kFeat);
+          o[0] = make_float4(v[0], v[1], v[2], v[3]);
+          o[1] = make_float4(v[4], v[5], v[6], v[7]);
+          o[2] = make_float4(v[8], v[9], v[10], v[11]);
+        }
+      }
+      tc_fence_before();
+      row_warps_sync();                                     // TMEM reads done before the next tile's stores
+    }
+    atomicAdd(sAccB3 + 0, b3a); atomicAdd(sAccB3 + 1, b3b); atomicAdd(sAccB3 + 2, b3c);
+  } else {
+    // ================================================ column warps ================================================
+    auto acquire = [&]() -> const float* {
+      const uint32_t b = seq & 1, use = seq >> 1;
+      mbar_wait(full0 + 8 * b, use & 1);
+      return reinterpret_cast<const float*>(smem + oStg2 + (rw * 2 + b) * kStgBytesPerWarp);
+    };
+    auto release = [&]() {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty0 + 8 * (seq & 1));
+      ++seq;
+    };
+    for (int64_t tile = tile_begin; tile < tile_end; ++tile) {
+      const int tp = (int)((tile - tile_begin) & 1);
+      const float* sX = reinterpret_cast<const float*>(smem + oX2) + tp * kRows * kFeat;
+      const float4* sDz3 = reinterpret_cast<const float4*>(smem + oDz32) + tp * kRows;
+      const int* sRay = reinterpret_cast<const int*>(smem + oRay2) + tp * kRows;
+      // ---- H2 chunks: db2[j] += sum_s dZ2[s][j],  dW3[c][j] += sum_s dz3[s][c] H2[s][j] ----
+      for (int c = 0; c < kHidden / 32; ++c) {
+        const float* stg = acquire();
+        const int j = c * 32 + lane;
+        const float w3a = sW3[j], w3b = sW3[kHidden + j], w3c = sW3[2 * kHidden + j];
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, ab = 0.f;
+#pragma unroll 8
+        for (int sidx = 0; sidx < 32; ++sidx) {
+          const float h = stg[sidx * kStgStride + lane];
+          const float4 dz = sDz3[rw * 32 + sidx];
+          a0 = fmaf(dz.x, h, a0); a1 = fmaf(dz.y, h, a1); a2 = fmaf(dz.z, h, a2);
+          ab += h > 0.f ? fmaf(dz.z, w3c, fmaf(dz.y, w3b, dz.x * w3a)) : 0.f;
+        }
+        release();
+        atomicAdd(sAccW3 + j, a0); atomicAdd(sAccW3 + kHidden + j, a1); atomicAdd(sAccW3 + 2 * kHidden + j, a2);
+        atomicAdd(sAccB2 + j, ab);
+      }
+      // ---- dZ1 chunks: dvb[ray][j] += sum_{s in ray} dZ1[s][j],  dW1k[j][0..11] += sum_s dZ1[s][j] X[s][0..11] ----
+      for (int c = 0; c < kHidden / 32; ++c) {
+        const float* stg = acquire();                       // acquire first: the tile's tables are visible from here on
+        const int my_ray = sRay[rw * 32 + lane];
+        const int ray0 = __shfl_sync(0xffffffffu, my_ray, 0);
+        const bool one_ray = __all_sync(0xffffffffu, my_ray == ray0) && ray0 >= 0;
+        const int j = c * 32 + lane;
+        float acc[kFeat];
+#pragma unroll
+        for (int k = 0; k < kFeat; ++k) acc[k] = 0.f;
+        float run = 0.f;
+        int run_ray = one_ray ? ray0 : -1;
+#pragma unroll 4
+        for (int sidx = 0; sidx < 32; ++sidx) {
+          const float d = stg[sidx * kStgStride + lane];
+          if (!one_ray) {                                   // warp-uniform branch
+            const int r = sRay[rw * 32 + sidx];
+            if (r != run_ray) {
+              if (run_ray >= 0) atomicAdd(g_vb + (int64_t)run_ray * kHidden + j, run);
+              run_ray = r;
+              run = 0.f;
+            }
+          }
+          run += d;
+          const float4* xs = reinterpret_cast<const float4*>(sX + (rw * 32 + sidx) * kFeat);
+          const float4 xa = xs[0], xb = xs[1], xc = xs[2];
+          acc[0] = fmaf(d, xa.x, acc[0]); acc[1] = fmaf(d, xa.y, acc[1]); acc[2] = fmaf(d, xa.z, acc[2]); acc[3] = fmaf(d, xa.w, acc[3]);
+          acc[4] = fmaf(d, xb.x, acc[4]); acc[5] = fmaf(d, xb.y, acc[5]); acc[6] = fmaf(d, xb.z, acc[6]); acc[7] = fmaf(d, xb.w, acc[7]);
+          acc[8] = fmaf(d, xc.x, acc[8]); acc[9] = fmaf(d, xc.y, acc[9]); acc[10] = fmaf(d, xc.z, acc[10]); acc[11] = fmaf(d, xc.w, acc[11]);
+        }
+        release();
+        if (run_ray >= 0) atomicAdd(g_vb + (int64_t)run_ray * kHidden + j, run);
+#pragma unroll
+        for (int k = 0; k < kFeat; ++k) atomicAdd(sAccW1 + j * kFeat + k, acc[k]);
+      }
+    }
+  }
+
+  // ---- flush the CTA partials ----
+  __syncthreads();
+  for (int i = tid; i < kHidden * kFeat; i += 2 * kRows) atomicAdd(gW1k + i, sAccW1[i]);
+  for (int i = tid; i < 3 * kHidden; i += 2 * kRows) atomicAdd(gW3 + i, sAccW3[i]);
+  if (tid < kHidden) atomicAdd(gb2 + tid, sAccB2[tid]);
+  if (tid < 3) atomicAdd(gb3 + tid, sAccB3[tid]);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+  }
+}
+
+
 // ---- dW2 += dZ2^T . H1 as its own split-K GEMM ----------------------------------------------------------------------
 // Round = 32 consecutive samples.  Warp w stages rows 4w..4w+3; lane l serves row (l & 3) and hidden units j = 8*jj + (l >> 2)
 // (jj < 16): for one store instruction the 32 lanes hit 32 distinct banks of one K-major panel (conflict free).
@@ -1125,7 +1470,19 @@ extern "C" int ubn_rgbnet_bwd_tc_fused(const float* feat, const int64_t* ray_id,
                                                                              n_pts, grad_feat, grad_view_bias, grad_W1k, grad_b2,       \
                                                                              grad_W3, grad_b3);                                         \
     } while (0)
-    if (single_pass) UBN_BF(false); else UBN_BF(true);
+#define UBN_BFW(T)                                                                                                             \
+    do {                                                                                                                       \
+      cudaError_t e = cudaFuncSetAttribute(tc::k_shade_bwd_fused_ws<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,           \
+                                           (int)tc::bf2::kSmemBytesF2);                                                        \
+      if (e != cudaSuccess) return finish(e);                                                                                  \
+      tc::k_shade_bwd_fused_ws<T><<<grid, 2 * tc::kRows, tc::bf2::kSmemBytesF2, st>>>(feat, ray_id, W1k, W2, W3, rgb, h1_save, h2_save, \
+                                                                                      grad_rgb, n_pts, grad_feat, grad_view_bias,        \
+                                                                                      grad_W1k, grad_b2, grad_W3, grad_b3);              \
+    } while (0)
+    const bool one_pass = (single_pass & 1) != 0, plain = (single_pass & 2) != 0;
+    if (plain) { if (one_pass) UBN_BF(false); else UBN_BF(true); }
+    else       { if (one_pass) UBN_BFW(false); else UBN_BFW(true); }
+#undef UBN_BFW
 #undef UBN_BF
     UBN_LAUNCH_CHECK();
   }
@@ -1139,7 +1496,7 @@ extern "C" int ubn_rgbnet_bwd_tc_fused(const float* feat, const int64_t* ray_id,
       if (e != cudaSuccess) return finish(e);                                                                                  \
       tc::k_shade_dw2_tc<T><<<grid, tc::dw::kThreadsDW, tc::dw::kSmemBytesD, st>>>(W3, rgb, h1_save, h2_save, grad_rgb, n_pts, grad_W2); \
     } while (0)
-    if (single_pass) UBN_DW(false); else UBN_DW(true);
+    if (single_pass & 1) UBN_DW(false); else UBN_DW(true);
 #undef UBN_DW
     UBN_LAUNCH_CHECK();
   }

@@ -18,7 +18,8 @@ from ._cabi import c_i64, c_int, check, ptr, stream_of
 # mode, ~1e-3 relative error, gated by the PSNR test in tests/test_gpu_models.py --, 'simt' = fp32 FFMA
 MODE = os.environ.get('UBN_RGBNET_MODE', 'tc3')
 # backward engine: 'fused' = tcgen05 3xTF32, dZ2 -> dH1 -> dZ1 -> dX chained through tensor memory + all sample reductions in one
-# kernel, dW2 in a second (no intermediate in HBM); 'tc3' = the previous three-launch form (dZ1 round trip + CUDA-core kernel for
+# warp-specialised kernel (4 row warps drive the tensor cores, 4 column warps reduce over samples), dW2 in a second launch; no
+# intermediate in HBM; 'fused4' = the same without warp specialisation (A/B); 'tc3' = the previous three-launch form (dZ1 round trip + CUDA-core kernel for
 # the small gradients; kept for A/B); 'simt' = fp32 FFMA
 BWD_MODE = os.environ.get('UBN_RGBNET_BWD_MODE', 'fused')
 
@@ -62,11 +63,12 @@ class _ShadeFn(torch.autograd.Function):
         z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
         g_vb, gW1k, gW2, gb2, gW3, gb3 = z(ctx.n_rays, 128), z(128, 12), z(128, 128), z(128), z(3, 128), z(3)
         with ops._Guard(feat) as lib:
-            if BWD_MODE == 'fused':
+            if BWD_MODE in ('fused', 'fused4'):          # 'fused4': the same kernel without warp specialisation (A/B)
                 with _cabi.timed('rgbnet_bwd'):
                     check(lib.ubn_rgbnet_bwd_tc_fused(ptr(feat), ptr(ray_id), ptr(W1k), ptr(W2), ptr(W3), ptr(rgb), ptr(h1), ptr(h2),
                                                       ptr(g_rgb), c_i64(M), ptr(g_feat), ptr(g_vb), ptr(gW1k), ptr(gW2), ptr(gb2),
-                                                      ptr(gW3), ptr(gb3), c_int(1 if MODE == 'tc1' else 0), stream_of(feat)))
+                                                      ptr(gW3), ptr(gb3), c_int((1 if MODE == 'tc1' else 0) | (2 if BWD_MODE == 'fused4' else 0)),
+                                                      stream_of(feat)))
                 return g_feat, g_vb, None, gW1k, gW2, gb2, gW3, gb3, None
             if BWD_MODE == 'tc3':
                 dz1 = torch.empty(M, 128, dtype=torch.float32, device=dev)
