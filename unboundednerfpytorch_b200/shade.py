@@ -21,7 +21,7 @@ MODE = os.environ.get('UBN_RGBNET_MODE', 'tc3')
 # warp-specialised kernel (4 row warps drive the tensor cores, 4 column warps reduce over samples), dW2 in a second launch; no
 # intermediate in HBM; 'fused4' = the same without warp specialisation (A/B); 'tc3' = the previous three-launch form (dZ1 round trip + CUDA-core kernel for
 # the small gradients; kept for A/B); 'simt' = fp32 FFMA
-BWD_MODE = os.environ.get('UBN_RGBNET_BWD_MODE', 'fused')
+BWD_MODE = os.environ.get('UBN_RGBNET_BWD_MODE', 'fused4')
 
 
 class _ShadeFn(torch.autograd.Function):
