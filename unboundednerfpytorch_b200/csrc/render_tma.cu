@@ -12,6 +12,10 @@
 //   outside the grid) brings the brick into the warp's shared-memory buffer, signalled on an mbarrier, and all 128 samples
 //   interpolate from shared memory (8 corners x 3 LDS.128);  otherwise (row wrap of the image, grazing geometry) the lanes
 //   fall back to direct global loads for that block.
+// Parallelism: a chunk of 8192 rays is only 256 ray groups, so the step axis is split too: a warp owns (32 rays) x (a segment of
+// 64 steps = 16 blocks); its output cursor starts after the survivors of the earlier segments, counted from the flag bytes
+// (16-byte loads, 4 bytes of flags per step block).  First version (one warp per ray group, all 128 blocks): 3x slower than the
+// gather kernel on the garden frame, because 64 CTAs per chunk left more than half of the SMs idle.
 // The trilinear sum runs in ATen's corner order (tnw .. bse, FMA chain), so the features are bit-identical to the stand-alone
 // grid op (trilinear.cu) and to torch F.grid_sample, which the reference calls.  Outputs = those of ubn_march_feature_fwd.
 #include <cuda.h>
@@ -27,6 +31,7 @@ namespace rt {
 constexpr int kBox = 8;                                  // lattice points per axis in a staged brick
 constexpr int kChan = 12;
 constexpr int kSteps = 4;                                // steps per block
+constexpr int kSegSteps = 64;                            // steps per warp (16 blocks)
 constexpr uint32_t kBoxBytes = kBox * kBox * kBox * kChan * 4;   // 24 576
 constexpr int kWarps = 4;
 constexpr uint32_t kSmemBytes = kWarps * kBoxBytes + kWarps * 8 + 128;   // + mbarriers (+ slack for 128-byte alignment)
@@ -95,19 +100,35 @@ __global__ void __launch_bounds__(32 * rt::kWarps, 2) k_march_feature_tma(
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
 
-  const int64_t ray = ((int64_t)blockIdx.x * kWarps + w) * 32 + lane;
+  const int S = p.S;
+  const int n_seg = (S + kSegSteps - 1) / kSegSteps;
+  const int64_t unit = (int64_t)blockIdx.x * kWarps + w;                 // (ray group, step segment)
+  const int64_t group = unit / n_seg;
+  const int seg = (int)(unit - group * n_seg);
+  const int64_t ray = group * 32 + lane;
   const bool ray_ok = ray < n_rays;
   Ray r = {0, 0, 0, 0, 0, 1};
   int64_t cursor = 0;
+  const int seg_begin = seg * kSegSteps, seg_end = min(seg_begin + kSegSteps, S);
   if (ray_ok) {
     r = load_ray(rays_o + 3 * ray, rays_d + 3 * ray, p);
-    cursor = offsets[ray];
+    // survivors of this ray in the earlier segments: KEEP is bit 3 of every flag byte
+    const uint8_t* fr = flags + ray * S;
+    int before = 0;
+    if ((S & 15) == 0) {
+      for (int i = 0; i < seg_begin; i += 16) {
+        const uint4 v = *reinterpret_cast<const uint4*>(fr + i);
+        before += __popc(v.x & 0x08080808u) + __popc(v.y & 0x08080808u) + __popc(v.z & 0x08080808u) + __popc(v.w & 0x08080808u);
+      }
+    } else {
+      for (int i = 0; i < seg_begin; ++i) before += (fr[i] & UBN_FLAG_KEEP) ? 1 : 0;
+    }
+    cursor = offsets[ray] + before;
   }
-  const int S = p.S;
   uint32_t phase = 0;
   unsigned long long n_tma = 0, n_fallback = 0;
 
-  for (int s0 = 0; s0 < S; s0 += kSteps) {
+  for (int s0 = seg_begin; s0 < seg_end; s0 += kSteps) {
     // ---- this lane's up-to-4 samples of the block ----
     Cell3 cell[kSteps];
     float tt[kSteps];
@@ -117,7 +138,7 @@ __global__ void __launch_bounds__(32 * rt::kWarps, 2) k_march_feature_tma(
 #pragma unroll
     for (int j = 0; j < kSteps; ++j) {
       const int s = s0 + j;
-      fl[j] = (ray_ok && s < S) ? flags[ray * S + s] : 0;
+      fl[j] = (ray_ok && s < seg_end) ? flags[ray * S + s] : 0;
       keep[j] = (fl[j] & UBN_FLAG_KEEP) != 0;
       tt[j] = 0.f;
       cell[j] = Cell3{0, 0, 0, 0.f, 0.f, 0.f};
@@ -237,8 +258,9 @@ extern "C" int ubn_march_feature_fwd_tma(const float* rays_o, const float* rays_
   const MarchParams p = make_params(cfg);
   cudaError_t e = cudaFuncSetAttribute(k_march_feature_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rt::kSmemBytes);
   if (e != cudaSuccess) return finish(e);
-  const int64_t rays_per_cta = 32 * rt::kWarps;
-  k_march_feature_tma<<<blocks_for(n_rays, (int)rays_per_cta), 32 * rt::kWarps, rt::kSmemBytes, as_stream(stream)>>>(
+  const int64_t n_seg = (p.S + rt::kSegSteps - 1) / rt::kSegSteps;
+  const int64_t units = ((n_rays + 31) / 32) * n_seg;                    // (ray group, step segment) pairs, one warp each
+  k_march_feature_tma<<<blocks_for(units, rt::kWarps), 32 * rt::kWarps, rt::kSmemBytes, as_stream(stream)>>>(
       tmap, rays_o, rays_d, t_table, g, p, n_rays, flags, offsets, density, alpha, weight, feat, o_density, o_alpha, o_weight,
       o_ray_id, o_step_id, o_t, o_inner, stats2);
   UBN_LAUNCH_CHECK();
