@@ -501,7 +501,22 @@ def main():
     n_global = N_RAYS * world
     tv_terms = model.tv_terms(1e-6 / n_global, 1e-7 / n_global, True)
     tail_mode = os.environ.get('UBN_BENCH_TAIL', 'peer')
-    peer_tail = ubdist.PeerTail(opt) if tail_mode == 'peer' else None
+    peer_tail = None
+    if tail_mode == 'peer':
+        try:
+            peer_tail = ubdist.PeerTail(opt)
+        except Exception as e:        # peer mapping unavailable on this box (no P2P / IPC): fall back to the NCCL-pipelined tail on ALL ranks
+            sys.stderr.write(f'[bench] PeerTail unavailable on rank {rank} ({e!r}); using the pipelined NCCL tail\n')
+            peer_tail = None
+        if world > 1:                 # every rank must take the same route
+            ok = torch.tensor([1 if peer_tail is not None else 0], device=dev)
+            torch.distributed.all_reduce(ok, op=torch.distributed.ReduceOp.MIN)
+            if int(ok.item()) == 0:
+                if peer_tail is not None:
+                    raise SystemExit('PeerTail came up on some ranks only; set UBN_BENCH_TAIL=pipelined')
+                tail_mode = 'pipelined'
+        elif peer_tail is None:
+            tail_mode = 'pipelined'
 
     # every rank gets its own 8192-ray batch (weak scaling); host copies are pinned for the e2e leg
     host = [t.pin_memory() for t in synth_batch(N_RAYS, SEED + rank)]

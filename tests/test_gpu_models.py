@@ -221,7 +221,7 @@ def test_training_step_reduces_loss():
     assert all(torch.isfinite(p).all() for p in student.parameters())
 
 
-@pytest.mark.parametrize('mode', ['simt', 'tc3', 'tc1', 'tc3+tcbwd', 'tc3+fused', 'tc3+fused4', 'tc1+fused'])
+@pytest.mark.parametrize('mode', ['simt', 'tc3', 'tc3w4', 'tc1', 'tc3+tcbwd', 'tc3+fused', 'tc3+fused4', 'tc1+fused'])
 def test_fused_rgbnet_vs_torch(mode, monkeypatch):
     """csrc/shade.cu (fp32 FFMA) and csrc/shade_tc.cu (tcgen05: 3xTF32 fp32-grade, single-pass TF32 preview) vs the torch
     nn.Sequential they replace: forward and every gradient."""

@@ -45,8 +45,9 @@ constexpr uint32_t oA1lo = oA1hi + (kK1 / 4) * kPanelBytes;
 constexpr uint32_t oW3 = oA1lo + (kK1 / 4) * kPanelBytes;           // [3][128] fp32
 constexpr uint32_t oB2 = oW3 + 3 * kHidden * 4;
 constexpr uint32_t oBar = oB2 + kHidden * 4;                        // mbarrier (8 B) + tmem base (4 B)
-constexpr uint32_t oStg = oBar + 16;                                // 4 warps x 4.5 KB store-transpose tiles
-constexpr uint32_t kSmemBytes = oStg + 4 * 32 * 36 * 4;
+constexpr uint32_t oPart = oBar + 16;                               // [128][4] layer-3 partial sums (8-warp forward)
+constexpr uint32_t oStg = oPart + kRows * 16;                       // up to 8 warps x 4.5 KB store-transpose tiles
+constexpr uint32_t kSmemBytes = oStg + 8 * 32 * 36 * 4;
 
 // TMEM column plan (512 columns x 128 lanes x 32 bit)
 constexpr uint32_t cD1 = 0, cA2hi = 128, cA2lo = 256, cD2 = 384;
@@ -169,25 +170,33 @@ __device__ void stage_weights(const float* __restrict__ W, int K, int Kpad, uint
   }
 }
 
-template <bool kSave, bool kThreePass>
-__global__ void __launch_bounds__(kRows, 1) k_shade_fwd_tc(
+// kHalves = 2: EIGHT warps per CTA.  Warps w and w + 4 address the same quarter of the TMEM lanes (a warp may touch lanes
+// 32 (w % 4) .. + 31), so they split every sample row of the tile by COLUMNS: half 0 owns hidden units 0..63, half 1 owns 64..127
+// in both epilogues; the three layer-3 dot products are combined through 1.5 KB of shared memory.  With four warps each scheduler
+// has a single warp and every TMEM / shared-memory latency of the epilogues is exposed; eight warps halve the epilogue time.
+template <bool kSave, bool kThreePass, int kHalves>
+__global__ void __launch_bounds__(kRows * kHalves, 1) k_shade_fwd_tc(
     const float* __restrict__ feat, const float* __restrict__ vb, const int64_t* __restrict__ ray_id,
     const float* __restrict__ W1k, const float* __restrict__ W2, const float* __restrict__ b2,
     const float* __restrict__ W3, const float* __restrict__ b3, int64_t n_pts, float* __restrict__ rgb,
     float* __restrict__ h1_out, float* __restrict__ h2_out) {
+  constexpr int kThreads = kRows * kHalves;
+  constexpr int kChunksPerHalf = (kHidden / 32) / kHalves;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int rtid = tid & (kRows - 1), half = tid >> 7;          // row within the tile, column half
   float* sW3 = reinterpret_cast<float*>(smem + oW3);
   float* sB2 = reinterpret_cast<float*>(smem + oB2);
+  float* sPart = reinterpret_cast<float*>(smem + oPart);        // [128][4] layer-3 partials of half 1
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + oBar);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + oBar + 8);
   const uint32_t bar_addr = smem_u32(bar);
 
   // ---- one-time setup: weights (split hi/lo, K-major panels), barrier, TMEM ----
-  stage_weights(W2, kHidden, kHidden, smem + oW2hi, smem + oW2lo, tid, kRows);
-  stage_weights(W1k, kFeat, kK1, smem + oW1hi, smem + oW1lo, tid, kRows);
-  for (int i = tid; i < 3 * kHidden; i += kRows) sW3[i] = W3[i];
-  sB2[tid] = b2[tid];
+  stage_weights(W2, kHidden, kHidden, smem + oW2hi, smem + oW2lo, tid, kThreads);
+  stage_weights(W1k, kFeat, kK1, smem + oW1hi, smem + oW1lo, tid, kThreads);
+  for (int i = tid; i < 3 * kHidden; i += kThreads) sW3[i] = W3[i];
+  if (tid < kHidden) sB2[tid] = b2[tid];
   if (tid == 0) {
     mbar_init(bar_addr, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -201,7 +210,7 @@ __global__ void __launch_bounds__(kRows, 1) k_shade_fwd_tc(
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t lane_base = (uint32_t)(warp * 32) << 16;      // this warp's TMEM lane quarter
+  const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;      // this warp's TMEM lane quarter
   const float b3x = b3[0], b3y = b3[1], b3z = b3[2];
   uint32_t phase = 0;
 
@@ -212,27 +221,23 @@ __global__ void __launch_bounds__(kRows, 1) k_shade_fwd_tc(
 
   const int64_t n_tiles = (n_pts + kRows - 1) / kRows;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int64_t row = tile * kRows + tid;
+    const int64_t row = tile * kRows + rtid;
     const bool live = row < n_pts;
-    // ---- stage the X tile: row `tid`, 12 features (+4 zero pad), split hi / lo ----
+    // ---- stage the X tile: row `rtid`, 12 features (+4 zero pad), split hi / lo; with two halves each stages two panels ----
     {
-      float x[kK1];
+      constexpr int kPanelsPerHalf = (kK1 / 4) / kHalves;
 #pragma unroll
-      for (int q = 0; q < 3; ++q) {
+      for (int pp = 0; pp < kPanelsPerHalf; ++pp) {
+        const int pnl = half * kPanelsPerHalf + pp;
         float4 v = make_float4(0, 0, 0, 0);
-        if (live) v = *reinterpret_cast<const float4*>(feat + row * kFeat + q * 4);
-        x[q * 4] = v.x; x[q * 4 + 1] = v.y; x[q * 4 + 2] = v.z; x[q * 4 + 3] = v.w;
-      }
-      x[12] = x[13] = x[14] = x[15] = 0.f;
-#pragma unroll
-      for (int p = 0; p < kK1 / 4; ++p) {
+        if (live && pnl < 3) v = *reinterpret_cast<const float4*>(feat + row * kFeat + pnl * 4);
         uint4 hi;
         float4 lo;
-        hi.x = tf32_hi_bits(x[p * 4]); hi.y = tf32_hi_bits(x[p * 4 + 1]); hi.z = tf32_hi_bits(x[p * 4 + 2]); hi.w = tf32_hi_bits(x[p * 4 + 3]);
-        lo.x = x[p * 4] - __uint_as_float(hi.x); lo.y = x[p * 4 + 1] - __uint_as_float(hi.y);
-        lo.z = x[p * 4 + 2] - __uint_as_float(hi.z); lo.w = x[p * 4 + 3] - __uint_as_float(hi.w);
-        *reinterpret_cast<uint4*>(smem + oA1hi + p * kPanelBytes + tid * 16) = hi;
-        *reinterpret_cast<float4*>(smem + oA1lo + p * kPanelBytes + tid * 16) = lo;
+        hi.x = tf32_hi_bits(v.x); hi.y = tf32_hi_bits(v.y); hi.z = tf32_hi_bits(v.z); hi.w = tf32_hi_bits(v.w);
+        lo.x = v.x - __uint_as_float(hi.x); lo.y = v.y - __uint_as_float(hi.y);
+        lo.z = v.z - __uint_as_float(hi.z); lo.w = v.w - __uint_as_float(hi.w);
+        *reinterpret_cast<uint4*>(smem + oA1hi + pnl * kPanelBytes + rtid * 16) = hi;
+        *reinterpret_cast<float4*>(smem + oA1lo + pnl * kPanelBytes + rtid * 16) = lo;
       }
     }
     const int64_t my_ray = live ? ray_id[row] : 0;
@@ -255,9 +260,10 @@ __global__ void __launch_bounds__(kRows, 1) k_shade_fwd_tc(
     mbar_wait(bar_addr, phase);
     phase ^= 1;
     tc_fence_after();
-    // ---- epilogue 1: + vb[ray], ReLU, split, back into TMEM as the layer-2 A operand ----
+    // ---- epilogue 1: + vb[ray], ReLU, split, back into TMEM as the layer-2 A operand (this half's columns) ----
 #pragma unroll 1
-    for (int c = 0; c < kHidden / 32; ++c) {
+    for (int cc = 0; cc < kChunksPerHalf; ++cc) {
+      const int c = half * kChunksPerHalf + cc;
       float v[32];
       tmem_ld32(tmem + lane_base + cD1 + c * 32, v);
       uint32_t hi[32], lo[32];
@@ -280,7 +286,7 @@ __global__ void __launch_bounds__(kRows, 1) k_shade_fwd_tc(
       if (kThreePass) tmem_st32(tmem + lane_base + cA2lo + c * 32, lo);
       if (kSave)
         warp_store_chunk(reinterpret_cast<float*>(smem + oStg + warp * kStgBytesPerWarp), v,
-                         h1_out + (tile * kRows + warp * 32) * kHidden, c * 32, n_pts - (tile * kRows + warp * 32), tid & 31);
+                         h1_out + (tile * kRows + (warp & 3) * 32) * kHidden, c * 32, n_pts - (tile * kRows + (warp & 3) * 32), tid & 31);
     }
     tmem_st_wait();
     tc_fence_before();
@@ -301,10 +307,11 @@ __global__ void __launch_bounds__(kRows, 1) k_shade_fwd_tc(
     mbar_wait(bar_addr, phase);
     phase ^= 1;
     tc_fence_after();
-    // ---- epilogue 2: + b2, ReLU, layer 3 on CUDA cores, sigmoid ----
+    // ---- epilogue 2: + b2, ReLU, layer 3 on CUDA cores (this half's columns), sigmoid ----
     float p0 = 0.f, p1 = 0.f, p2 = 0.f;
 #pragma unroll 1
-    for (int c = 0; c < kHidden / 32; ++c) {
+    for (int cc = 0; cc < kChunksPerHalf; ++cc) {
+      const int c = half * kChunksPerHalf + cc;
       float v[32];
       tmem_ld32(tmem + lane_base + cD2 + c * 32, v);
 #pragma unroll
@@ -322,9 +329,20 @@ __global__ void __launch_bounds__(kRows, 1) k_shade_fwd_tc(
       }
       if (kSave)
         warp_store_chunk(reinterpret_cast<float*>(smem + oStg + warp * kStgBytesPerWarp), v,
-                         h2_out + (tile * kRows + warp * 32) * kHidden, c * 32, n_pts - (tile * kRows + warp * 32), tid & 31);
+                         h2_out + (tile * kRows + (warp & 3) * 32) * kHidden, c * 32, n_pts - (tile * kRows + (warp & 3) * 32), tid & 31);
     }
-    if (live) {
+    if (kHalves == 2) {
+      // the fp32 sum order of the 4-warp kernel is (columns 0..127 in one FMA chain); here it is chain(0..63) + chain(64..127):
+      // same terms, one extra rounding -- inside the 1e-5 parity tolerance like every other re-association of this dot product
+      if (half == 1) *reinterpret_cast<float4*>(sPart + rtid * 4) = make_float4(p0, p1, p2, 0.f);
+      tc_fence_before();
+      __syncthreads();
+      if (half == 0) {
+        const float4 o = *reinterpret_cast<const float4*>(sPart + rtid * 4);
+        p0 += o.x; p1 += o.y; p2 += o.z;
+      }
+    }
+    if (live && half == 0) {
       float* o = rgb + row * 3;
       o[0] = 1.f / (1.f + expf(-(p0 + b3x)));
       o[1] = 1.f / (1.f + expf(-(p1 + b3y)));
@@ -1404,20 +1422,29 @@ extern "C" int ubn_rgbnet_fwd_tc(const float* feat, const float* view_bias, cons
   const int64_t n_tiles = (n_pts + tc::kRows - 1) / tc::kRows;
   const unsigned grid = (unsigned)std::min<int64_t>(kNumSMs, n_tiles);
   cudaStream_t st = as_stream(stream);
-#define UBN_TC_LAUNCH(SAVE, THREE)                                                                                   \
-  do {                                                                                                               \
-    cudaError_t e = cudaFuncSetAttribute(tc::k_shade_fwd_tc<SAVE, THREE>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                         (int)tc::kSmemBytes);                                                       \
-    if (e != cudaSuccess) return finish(e);                                                                          \
-    tc::k_shade_fwd_tc<SAVE, THREE><<<grid, tc::kRows, tc::kSmemBytes, st>>>(feat, view_bias, ray_id, W1k, W2, b2, W3, b3, \
-                                                                              n_pts, rgb, h1_save, h2_save);          \
+  // single_pass bit 0: one TF32 pass per product; bit 1: the 4-warp form (A/B; default = 8 warps, two column halves per row)
+#define UBN_TC_LAUNCH_H(SAVE, THREE, H)                                                                                 \
+  do {                                                                                                                  \
+    cudaError_t e = cudaFuncSetAttribute(tc::k_shade_fwd_tc<SAVE, THREE, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                         (int)tc::kSmemBytes);                                                          \
+    if (e != cudaSuccess) return finish(e);                                                                             \
+    tc::k_shade_fwd_tc<SAVE, THREE, H><<<grid, tc::kRows * H, tc::kSmemBytes, st>>>(feat, view_bias, ray_id, W1k, W2, b2, W3, \
+                                                                                     b3, n_pts, rgb, h1_save, h2_save);      \
   } while (0)
+#define UBN_TC_LAUNCH(SAVE, THREE)                                   \
+  do {                                                               \
+    if (four_warps) UBN_TC_LAUNCH_H(SAVE, THREE, 1);                 \
+    else UBN_TC_LAUNCH_H(SAVE, THREE, 2);                            \
+  } while (0)
+  const bool four_warps = (single_pass & 2) != 0;
+  single_pass &= 1;
   if (save) {
     if (single_pass) UBN_TC_LAUNCH(true, false); else UBN_TC_LAUNCH(true, true);
   } else {
     if (single_pass) UBN_TC_LAUNCH(false, false); else UBN_TC_LAUNCH(false, true);
   }
 #undef UBN_TC_LAUNCH
+#undef UBN_TC_LAUNCH_H
   UBN_LAUNCH_CHECK();
   return 0;
 }

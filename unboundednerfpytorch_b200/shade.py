@@ -40,9 +40,10 @@ class _ShadeFn(torch.autograd.Function):
         h2 = torch.empty(M, 128, dtype=torch.float32, device=dev) if need_grad else None
         with ops._Guard(feat) as lib:
             with _cabi.timed('rgbnet_fwd'):
-                if MODE in ('tc3', 'tc1'):
+                if MODE in ('tc3', 'tc1', 'tc3w4'):      # 'tc3w4': the 4-warp form of the forward kernel (A/B of the 8-warp default)
                     check(lib.ubn_rgbnet_fwd_tc(ptr(feat), ptr(vb), ptr(ray_id), ptr(W1k), ptr(W2), ptr(b2), ptr(W3), ptr(b3),
-                                                c_i64(M), ptr(rgb), ptr(h1), ptr(h2), c_int(1 if MODE == 'tc1' else 0),
+                                                c_i64(M), ptr(rgb), ptr(h1), ptr(h2),
+                                                c_int((1 if MODE == 'tc1' else 0) | (2 if MODE == 'tc3w4' else 0)),
                                                 stream_of(feat)))
                 else:
                     check(lib.ubn_rgbnet_fwd(ptr(feat), ptr(vb), ptr(ray_id), ptr(W1k), ptr(W2), ptr(b2), ptr(W3), ptr(b3),
