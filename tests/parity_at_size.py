@@ -177,6 +177,11 @@ def compare(name, dev, n_rays=8192, backward=True, ext=None, truth=True):
         pairs += [('rgbnet.' + k, v.grad, p['rgbnet'][k].grad) for k, v in names.items()]
         for nm, a, b in pairs:
             out['grad ' + nm] = _stat(a, b)
+        if truth:
+            grads64, out['n_relu_ambiguous'] = colour_branch_fp64(flavor, p, ref, vd, target, n_rays)
+            for nm, a, b in pairs:
+                if nm in grads64:
+                    out['truth ' + nm] = _vs_truth(a, b, grads64[nm])
         # the reference against ITSELF: its grid scatters are fp32 atomicAdds (ATen grid_sampler_3d_backward), so two runs of the
         # reference differ by the summation order alone -- the floor any other implementation can be asked to reach
         first = {nm: b.detach().clone() for nm, a, b in pairs[:2]}
@@ -187,9 +192,4 @@ def compare(name, dev, n_rays=8192, backward=True, ext=None, truth=True):
         out['refself density.grid'] = _stat(p['density_grid'].grad, first['density.grid'])
         out['refself k0.grid'] = _stat(p['k0_grid'].grad, first['k0.grid'])
         del ref2, first
-        if truth:
-            grads64, out['n_relu_ambiguous'] = colour_branch_fp64(flavor, p, ref, vd, target, n_rays)
-            for nm, a, b in pairs:
-                if nm in grads64:
-                    out['truth ' + nm] = _vs_truth(a, b, grads64[nm])
     return out, ours, p
