@@ -313,7 +313,7 @@ def render_workload(args, emit):
     H, W = FRAME_HW
     ro, rd, vd = frame_rays(dev, H, W)
     n_rays = ro.shape[0]
-    rk = dict(near=0., far=1e9, bg=1, rand_bkgd=False, stepsize=1.045, coherent_rays=not args.no_tma)
+    rk = dict(near=0., far=1e9, bg=1, rand_bkgd=False, stepsize=1.045, coherent_rays=args.tma)
     if args.workload == 'garden':
         model, _ = block_model(SEED, dev)
         fn = lambda: RD.render_frame_sharded(model, ro, rd, vd, rk)
@@ -387,7 +387,7 @@ def render_workload(args, emit):
                          'parallelism': (f'rays sharded contiguously over {world} GPUs, grids replicated' if args.workload == 'garden'
                                          else f'{world} block models, one per GPU'),
                          'l2_policy': 'inputs larger than L2 (1.7 GB of grids)'},
-              'ray_samples_per_s': rays_total * N_SAMPLES / (ms_frame * 1e-3), 'tma_feature_read': not args.no_tma,
+              'ray_samples_per_s': rays_total * N_SAMPLES / (ms_frame * 1e-3), 'tma_feature_read': args.tma,
               'clocks': clk, 'check': check})
     if world > 1:
         torch.distributed.destroy_process_group()
@@ -404,7 +404,8 @@ def main():
     ap.add_argument('--cpu-rays', type=int, default=1024, help='upper bound of the ray sample of the CPU legs (shrunk to fit the time budget)')
     ap.add_argument('--feature-kernel', type=int, default=None, choices=[0, 1, 2],
                     help='A/B: pass-B kernel family (0 warp-cooperative, 1 lane-per-sample forward, 2 forward + backward); default = library default')
-    ap.add_argument('--no-tma', action='store_true', help='A/B (render workloads): gather kernel instead of the TMA-staged feature read')
+    ap.add_argument('--tma', action='store_true', help='A/B (render workloads): TMA-staged brick feature read instead of the gather kernel')
+    ap.add_argument('--no-tma', action='store_true', help='(default; kept for old scripts)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-reference-gpu', action='store_true', help='skip the reference-GPU baseline leg (oracle/_ref + ATen) of the N = 1 line')
     ap.add_argument('--only-timed', action='store_true', help='warm-up + timed region only (for ncu captures)')

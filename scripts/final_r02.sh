@@ -7,8 +7,8 @@ timeout 600 python bench.py > $O/bench_truck.json 2> $O/bench_truck.err; cut -c1
 timeout 400 python bench.py --workload bicycle --no-cpu-baseline > $O/bench_bicycle.json 2> $O/bench_bicycle.err; cut -c1-200 $O/bench_bicycle.json
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > $O/bench_ref.json 2> $O/bench_ref.err; cut -c1-200 $O/bench_ref.json
 timeout 300 python bench.py --workload garden --steps 3 --warmup 3 > $O/bench_garden.json 2> $O/bench_garden.err; cut -c1-200 $O/bench_garden.json
-timeout 300 python bench.py --workload garden --steps 3 --warmup 3 --no-tma > $O/bench_garden_notma.json 2> $O/bench_garden_notma.err; cut -c1-200 $O/bench_garden_notma.json
+timeout 300 python bench.py --workload garden --steps 3 --warmup 3 --tma > $O/bench_garden_tma.json 2> $O/bench_garden_tma.err; cut -c1-200 $O/bench_garden_tma.json
 timeout 900 python scripts/parity_at_size_report.py > $O/parity_at_size.jsonl 2> $O/parity_at_size.err; wc -l $O/parity_at_size.jsonl
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/launches.csv python bench.py --only-timed --steps 1 --warmup 3 --no-reference-gpu > $O/ncu_launch.log 2>&1; wc -l $O/launches.csv
 timeout 900 ncu --set full --clock-control none --import-source on -k "regex:k_march_feature_v3|k_shade_bwd_fused|k_shade_fwd_tc|k_tv_adam_peer|k_shade_dw2_tc|k_march_feature_v2" -s 18 -c 7 -o $O/new_kernels -f python bench.py --only-timed --steps 1 --warmup 3 --no-reference-gpu > $O/ncu_full.log 2>&1; ls -la $O/*.ncu-rep
-timeout 600 ncu --set full --clock-control none --import-source on -k "regex:k_march_feature_tma" -s 20 -c 2 -o $O/tma_kernel -f python bench.py --workload garden --steps 1 --warmup 3 > $O/ncu_tma.log 2>&1; ls -la $O/*.ncu-rep
+timeout 600 ncu --set full --clock-control none --import-source on -k "regex:k_march_feature_tma" -s 20 -c 2 -o $O/tma_kernel -f python bench.py --workload garden --tma --steps 1 --warmup 3 > $O/ncu_tma.log 2>&1; ls -la $O/*.ncu-rep

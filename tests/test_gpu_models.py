@@ -268,7 +268,9 @@ def test_fused_rgbnet_vs_torch(mode, monkeypatch):
                 rel = float((a - b).norm() / (b.norm() + 1e-30))
                 assert rel <= 8e-2, f'grad {nm} M={M} tf32x1: relative Frobenius error {rel:.2e}'
             else:
-                assert_close(a, b, rtol=2e-5, atol=2e-6 * scale + 1e-9, what=f'grad {nm} M={M}')
+                # parameter gradients are fp32 sums over M samples whose partial sums reach `scale`: two summation orders differ
+                # by a few ulp(scale) * sqrt(#adds) -- judged at the north-star 1e-5 of the largest element; k0 is per sample
+                assert_close(a, b, rtol=2e-5, atol=(2e-6 if nm == 'k0' else 1e-5) * scale + 1e-9, what=f'grad {nm} M={M}')
 
 
 def test_progressive_growing_and_occupancy_utilities(oracle):

@@ -1206,17 +1206,30 @@ __global__ void __launch_bounds__(2 * kRows, 1) k_shade_bwd_fused_ws(
       if (lane == 0) mbar_arrive(empty0 + 8 * (seq & 1));
       ++seq;
     };
+    // Every column warp owns the same (32 rows of its row warp) x (all 128 hidden units) strip in every tile, so the
+    // per-hidden-unit sums of lane j live in REGISTERS for the whole kernel (64 per lane) and reach shared memory once, at the
+    // end.  (They used to be shared-memory atomics after every chunk: ncu attributed 24 % of the kernel's stall samples and
+    // 60 % of its shared-memory wavefronts to those 16 four-way-conflicting ATOMS per chunk.)
+    float accW1[kHidden / 32][kFeat], accW3[kHidden / 32][3], accB2[kHidden / 32];
+#pragma unroll
+    for (int c = 0; c < kHidden / 32; ++c) {
+#pragma unroll
+      for (int k = 0; k < kFeat; ++k) accW1[c][k] = 0.f;
+      accW3[c][0] = accW3[c][1] = accW3[c][2] = 0.f;
+      accB2[c] = 0.f;
+    }
     for (int64_t tile = tile_begin; tile < tile_end; ++tile) {
       const int tp = (int)((tile - tile_begin) & 1);
       const float* sX = reinterpret_cast<const float*>(smem + oX2) + tp * kRows * kFeat;
       const float4* sDz3 = reinterpret_cast<const float4*>(smem + oDz32) + tp * kRows;
       const int* sRay = reinterpret_cast<const int*>(smem + oRay2) + tp * kRows;
       // ---- H2 chunks: db2[j] += sum_s dZ2[s][j],  dW3[c][j] += sum_s dz3[s][c] H2[s][j] ----
+#pragma unroll
       for (int c = 0; c < kHidden / 32; ++c) {
         const float* stg = acquire();
         const int j = c * 32 + lane;
         const float w3a = sW3[j], w3b = sW3[kHidden + j], w3c = sW3[2 * kHidden + j];
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, ab = 0.f;
+        float a0 = accW3[c][0], a1 = accW3[c][1], a2 = accW3[c][2], ab = accB2[c];
 #pragma unroll 8
         for (int sidx = 0; sidx < 32; ++sidx) {
           const float h = stg[sidx * kStgStride + lane];
@@ -1225,19 +1238,16 @@ __global__ void __launch_bounds__(2 * kRows, 1) k_shade_bwd_fused_ws(
           ab += h > 0.f ? fmaf(dz.z, w3c, fmaf(dz.y, w3b, dz.x * w3a)) : 0.f;
         }
         release();
-        atomicAdd(sAccW3 + j, a0); atomicAdd(sAccW3 + kHidden + j, a1); atomicAdd(sAccW3 + 2 * kHidden + j, a2);
-        atomicAdd(sAccB2 + j, ab);
+        accW3[c][0] = a0; accW3[c][1] = a1; accW3[c][2] = a2; accB2[c] = ab;
       }
       // ---- dZ1 chunks: dvb[ray][j] += sum_{s in ray} dZ1[s][j],  dW1k[j][0..11] += sum_s dZ1[s][j] X[s][0..11] ----
+#pragma unroll
       for (int c = 0; c < kHidden / 32; ++c) {
         const float* stg = acquire();                       // acquire first: the tile's tables are visible from here on
         const int my_ray = sRay[rw * 32 + lane];
         const int ray0 = __shfl_sync(0xffffffffu, my_ray, 0);
         const bool one_ray = __all_sync(0xffffffffu, my_ray == ray0) && ray0 >= 0;
         const int j = c * 32 + lane;
-        float acc[kFeat];
-#pragma unroll
-        for (int k = 0; k < kFeat; ++k) acc[k] = 0.f;
         float run = 0.f;
         int run_ray = one_ray ? ray0 : -1;
 #pragma unroll 4
@@ -1254,21 +1264,34 @@ __global__ void __launch_bounds__(2 * kRows, 1) k_shade_bwd_fused_ws(
           run += d;
           const float4* xs = reinterpret_cast<const float4*>(sX + (rw * 32 + sidx) * kFeat);
           const float4 xa = xs[0], xb = xs[1], xc = xs[2];
-          acc[0] = fmaf(d, xa.x, acc[0]); acc[1] = fmaf(d, xa.y, acc[1]); acc[2] = fmaf(d, xa.z, acc[2]); acc[3] = fmaf(d, xa.w, acc[3]);
-          acc[4] = fmaf(d, xb.x, acc[4]); acc[5] = fmaf(d, xb.y, acc[5]); acc[6] = fmaf(d, xb.z, acc[6]); acc[7] = fmaf(d, xb.w, acc[7]);
-          acc[8] = fmaf(d, xc.x, acc[8]); acc[9] = fmaf(d, xc.y, acc[9]); acc[10] = fmaf(d, xc.z, acc[10]); acc[11] = fmaf(d, xc.w, acc[11]);
+          accW1[c][0] = fmaf(d, xa.x, accW1[c][0]); accW1[c][1] = fmaf(d, xa.y, accW1[c][1]);
+          accW1[c][2] = fmaf(d, xa.z, accW1[c][2]); accW1[c][3] = fmaf(d, xa.w, accW1[c][3]);
+          accW1[c][4] = fmaf(d, xb.x, accW1[c][4]); accW1[c][5] = fmaf(d, xb.y, accW1[c][5]);
+          accW1[c][6] = fmaf(d, xb.z, accW1[c][6]); accW1[c][7] = fmaf(d, xb.w, accW1[c][7]);
+          accW1[c][8] = fmaf(d, xc.x, accW1[c][8]); accW1[c][9] = fmaf(d, xc.y, accW1[c][9]);
+          accW1[c][10] = fmaf(d, xc.z, accW1[c][10]); accW1[c][11] = fmaf(d, xc.w, accW1[c][11]);
         }
         release();
         if (run_ray >= 0) atomicAdd(g_vb + (int64_t)run_ray * kHidden + j, run);
-#pragma unroll
-        for (int k = 0; k < kFeat; ++k) atomicAdd(sAccW1 + j * kFeat + k, acc[k]);
       }
+    }
+    // the four column warps hold partials of the SAME hidden units (different rows): combine them in shared memory, [k][j]
+    // layout so that the 32 lanes of one atomic hit 32 banks
+#pragma unroll
+    for (int c = 0; c < kHidden / 32; ++c) {
+      const int j = c * 32 + lane;
+#pragma unroll
+      for (int k = 0; k < kFeat; ++k) atomicAdd(sAccW1 + k * kHidden + j, accW1[c][k]);
+      atomicAdd(sAccW3 + j, accW3[c][0]); atomicAdd(sAccW3 + kHidden + j, accW3[c][1]);
+      atomicAdd(sAccW3 + 2 * kHidden + j, accW3[c][2]);
+      atomicAdd(sAccB2 + j, accB2[c]);
     }
   }
 
   // ---- flush the CTA partials ----
   __syncthreads();
-  for (int i = tid; i < kHidden * kFeat; i += 2 * kRows) atomicAdd(gW1k + i, sAccW1[i]);
+  for (int i = tid; i < kHidden * kFeat; i += 2 * kRows)      // sAccW1 is [k][j]; gW1k is [j][k]
+    atomicAdd(gW1k + i, sAccW1[(i % kFeat) * kHidden + i / kFeat]);
   for (int i = tid; i < 3 * kHidden; i += 2 * kRows) atomicAdd(gW3 + i, sAccW3[i]);
   if (tid < kHidden) atomicAdd(gb2 + tid, sAccB2[tid]);
   if (tid < 3) atomicAdd(gb3 + tid, sAccB3[tid]);

@@ -27,7 +27,10 @@ def render_rays(model, rays_o, rays_d, viewdirs, render_kwargs, chunk=8192, keys
     """[n,3] ray arrays -> {key: [n, K]} (K = 3 for rgb_marched, 1 otherwise), in ``chunk``-ray calls like run_render.py:56-63."""
     rk = dict(render_kwargs)
     rk.setdefault('render_depth', True)
-    rk.setdefault('coherent_rays', True)      # image-ordered chunks: DenseGrid models read the feature grid through TMA-staged bricks
+    # render_kwargs['coherent_rays']=True routes DenseGrid feature reads of image-ordered chunks through the TMA-staged brick
+    # kernel (csrc/render_tma.cu).  Opt-in: on the garden frame it measured 311.6 ms/frame against 271.7 ms for the
+    # lane-per-sample gather (profiles/README.md, round 2), so the gather stays the default.
+    rk.setdefault('coherent_rays', False)
     outs = {k: [] for k in keys}
     for ro, rd, vd in zip(rays_o.split(chunk, 0), rays_d.split(chunk, 0), viewdirs.split(chunk, 0)):
         ret = model(ro, rd, vd, **rk)
