@@ -363,7 +363,10 @@ int ubn_rgbnet_fwd(const float* feat, const float* view_bias, const int64_t* ray
                    float* h2_save, void* stream);
 /* Same contract on the tensor cores: the two 128-wide layers run as tcgen05.mma (kind::tf32, M=128 sample tiles,
  * accumulators and the layer-2 A operand in tensor memory).  single_pass = 0: 3xTF32 split accumulation (fp32-grade,
- * meets the 1e-5 parity gate); single_pass = 1: one TF32 pass (~1e-3 relative; fast preview only). */
+ * meets the 1e-5 parity gate); single_pass bit 0: one TF32 pass (~1e-3 relative); bit 1: the 4-warp form of the kernel (A/B);
+ * bit 2: h1_save / h2_save are written in the PANEL layout [ceil(n_pts/128)][32 column quads][128 rows][4 floats] -- coalesced
+ * for the row-per-thread kernels on both sides -- and must hold ceil(n_pts/128)*128 rows; only ubn_rgbnet_bwd_tc_fused called
+ * with the same bit reads that layout. */
 int ubn_rgbnet_fwd_tc(const float* feat, const float* view_bias, const int64_t* ray_id, const float* W1k, const float* W2,
                       const float* b2, const float* W3, const float* b3, int64_t n_pts, float* rgb, float* h1_save,
                       float* h2_save, int single_pass, void* stream);
@@ -390,7 +393,8 @@ int ubn_rgbnet_bwd_small(const float* feat, const int64_t* ray_id, const float* 
  *            32 x 32 chunks of H2 / dZ1 held in shared memory;   launch 2: grad_W2 += dZ2^T.H1 (split-K tcgen05 GEMM).
  * Replaces ubn_rgbnet_bwd_tc_data + ubn_rgbnet_bwd_small (which round-tripped dZ1 [n_pts,128] through HBM and re-read H2).
  * single_pass bit 0: one TF32 pass per product instead of the 3-pass split (the opt-in reduced-precision training mode);
- * bit 1: launch 1 without warp specialisation (4 warps do the tensor-core chain AND the sample reductions; A/B). */
+ * bit 1: launch 1 without warp specialisation (4 warps do the tensor-core chain AND the sample reductions; A/B);
+ * bit 2: h1_save / h2_save are in the panel layout of ubn_rgbnet_fwd_tc (not combinable with bit 1: cudaErrorInvalidValue). */
 int ubn_rgbnet_bwd_tc_fused(const float* feat, const int64_t* ray_id, const float* W1k, const float* W2, const float* W3,
                             const float* rgb, const float* h1_save, const float* h2_save, const float* grad_rgb, int64_t n_pts,
                             float* grad_feat, float* grad_view_bias, float* grad_W1k, float* grad_W2, float* grad_b2,

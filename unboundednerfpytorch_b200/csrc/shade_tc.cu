@@ -63,6 +63,21 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
 // instruction descriptor: D = fp32 (c_format 1 @4), A = B = TF32 (format 2 @7, @10), K-major both, N>>3 @17, M>>4 @24
 constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kHidden >> 3) << 17) | ((uint32_t)(kRows >> 4) << 24);
 
+// The MMA-issuing thread is picked with elect.sync inside a warp-uniform branch.  With `if (threadIdx.x == 0)` the compiler cannot
+// prove the instruction's uniform-register operands warp-uniform and wraps EVERY tcgen05.mma in an ELECT / BRA.U.ANY waterfall
+// loop (SASS); a phase trace of the backward kernel (scripts/trace_ws.cu) showed 143 cycles per 128x128x8 MMA issued that way
+// against the tensor pipe's 64-cycle floor, and 55 cycles per N = 16 MMA (floor 8).  With elect.sync the UTCHMMAs issue back to back.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred px;\n\telect.sync _|px, 0xffffffff;\n\tselp.u32 %0, 1, 0, px;\n\t}\n" : "=r"(pred));
+  return pred != 0;
+}
+
+// ask L2 for `bytes` (a multiple of 16, 16-byte aligned address) of global memory; no destination, no completion to wait for
+__device__ __forceinline__ void l2_prefetch(const void* gptr, uint32_t bytes) {
+  if (bytes) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+}
+
 __device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -174,7 +189,13 @@ __device__ void stage_weights(const float* __restrict__ W, int K, int Kpad, uint
 // 32 (w % 4) .. + 31), so they split every sample row of the tile by COLUMNS: half 0 owns hidden units 0..63, half 1 owns 64..127
 // in both epilogues; the three layer-3 dot products are combined through 1.5 KB of shared memory.  With four warps each scheduler
 // has a single warp and every TMEM / shared-memory latency of the epilogues is exposed; eight warps halve the epilogue time.
-template <bool kSave, bool kThreePass, int kHalves>
+// kPanel: the two [n,128] activation saves are written in the PANEL layout  [tile][32 column quads][128 rows][4]  (the K-major
+// panel order of the tensor-core operands) instead of row-major: the thread that owns a sample row stores its 16-byte quads
+// directly (a warp instruction covers 32 consecutive rows of one quad = 512 contiguous bytes), and the backward kernels' row-per-
+// thread loads are coalesced the same way.  Row-major saves cost the backward 32 x 32 L1 wavefronts per thread row (one 128-byte
+// line per lane and instruction: 8 k L1 cycles per 128-sample tile, phase trace in scripts/trace_ws.cu) and the forward a
+// shared-memory transpose per chunk.  The buffers must then hold ceil(n / 128) * 128 rows.
+template <bool kSave, bool kThreePass, int kHalves, bool kPanel>
 __global__ void __launch_bounds__(kRows * kHalves, 1) k_shade_fwd_tc(
     const float* __restrict__ feat, const float* __restrict__ vb, const int64_t* __restrict__ ray_id,
     const float* __restrict__ W1k, const float* __restrict__ W2, const float* __restrict__ b2,
@@ -220,32 +241,45 @@ __global__ void __launch_bounds__(kRows * kHalves, 1) k_shade_fwd_tc(
   constexpr uint64_t kStep = (uint64_t)((2 * kPanelBytes) >> 4);   // one K=8 step = two 16-byte panels
 
   const int64_t n_tiles = (n_pts + kRows - 1) / kRows;
+  // The X rows and ray ids of a tile are fetched ONE TILE AHEAD into registers (right after the previous tile's layer-1 MMA is
+  // issued), so the HBM latency of these loads is off the critical path of the serial  stage -> MMA -> epilogue  chain.
+  constexpr int kPanelsPerHalf = (kK1 / 4) / kHalves;
+  float4 xnext[kPanelsPerHalf];
+  int64_t ray_next = 0;
+  auto fetch_x = [&](int64_t t) {
+    const int64_t r = t * kRows + rtid;
+    const bool ok = t < n_tiles && r < n_pts;
+#pragma unroll
+    for (int pp = 0; pp < kPanelsPerHalf; ++pp) {
+      const int pnl = half * kPanelsPerHalf + pp;
+      xnext[pp] = make_float4(0, 0, 0, 0);
+      if (ok && pnl < 3) xnext[pp] = __ldg(reinterpret_cast<const float4*>(feat + r * kFeat + pnl * 4));
+    }
+    ray_next = ok ? ray_id[r] : 0;
+  };
+  fetch_x(blockIdx.x);
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t row = tile * kRows + rtid;
     const bool live = row < n_pts;
     // ---- stage the X tile: row `rtid`, 12 features (+4 zero pad), split hi / lo; with two halves each stages two panels ----
-    {
-      constexpr int kPanelsPerHalf = (kK1 / 4) / kHalves;
 #pragma unroll
-      for (int pp = 0; pp < kPanelsPerHalf; ++pp) {
-        const int pnl = half * kPanelsPerHalf + pp;
-        float4 v = make_float4(0, 0, 0, 0);
-        if (live && pnl < 3) v = *reinterpret_cast<const float4*>(feat + row * kFeat + pnl * 4);
-        uint4 hi;
-        float4 lo;
-        hi.x = tf32_hi_bits(v.x); hi.y = tf32_hi_bits(v.y); hi.z = tf32_hi_bits(v.z); hi.w = tf32_hi_bits(v.w);
-        lo.x = v.x - __uint_as_float(hi.x); lo.y = v.y - __uint_as_float(hi.y);
-        lo.z = v.z - __uint_as_float(hi.z); lo.w = v.w - __uint_as_float(hi.w);
-        *reinterpret_cast<uint4*>(smem + oA1hi + pnl * kPanelBytes + rtid * 16) = hi;
-        *reinterpret_cast<float4*>(smem + oA1lo + pnl * kPanelBytes + rtid * 16) = lo;
-      }
+    for (int pp = 0; pp < kPanelsPerHalf; ++pp) {
+      const int pnl = half * kPanelsPerHalf + pp;
+      const float4 v = xnext[pp];
+      uint4 hi;
+      float4 lo;
+      hi.x = tf32_hi_bits(v.x); hi.y = tf32_hi_bits(v.y); hi.z = tf32_hi_bits(v.z); hi.w = tf32_hi_bits(v.w);
+      lo.x = v.x - __uint_as_float(hi.x); lo.y = v.y - __uint_as_float(hi.y);
+      lo.z = v.z - __uint_as_float(hi.z); lo.w = v.w - __uint_as_float(hi.w);
+      *reinterpret_cast<uint4*>(smem + oA1hi + pnl * kPanelBytes + rtid * 16) = hi;
+      *reinterpret_cast<float4*>(smem + oA1lo + pnl * kPanelBytes + rtid * 16) = lo;
     }
-    const int64_t my_ray = live ? ray_id[row] : 0;
+    const int64_t my_ray = ray_next;
     fence_async_smem();        // generic-proxy smem writes -> visible to the tensor core (async proxy)
     tc_fence_before();
     __syncthreads();
     // ---- layer 1 MMA (one thread issues) ----
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {   // one elected lane of a CONVERGED warp: plain UTCHMMA issue (see elect_one)
       tc_fence_after();
 #pragma unroll
       for (int ks = 0; ks < kK1 / 8; ++ks) {
@@ -257,6 +291,7 @@ __global__ void __launch_bounds__(kRows * kHalves, 1) k_shade_fwd_tc(
       }
       mma_commit(bar_addr);
     }
+    fetch_x(tile + gridDim.x);
     mbar_wait(bar_addr, phase);
     phase ^= 1;
     tc_fence_after();
@@ -284,15 +319,22 @@ __global__ void __launch_bounds__(kRows * kHalves, 1) k_shade_fwd_tc(
       }
       tmem_st32(tmem + lane_base + cA2hi + c * 32, hi);
       if (kThreePass) tmem_st32(tmem + lane_base + cA2lo + c * 32, lo);
-      if (kSave)
-        warp_store_chunk(reinterpret_cast<float*>(smem + oStg + warp * kStgBytesPerWarp), v,
-                         h1_out + (tile * kRows + (warp & 3) * 32) * kHidden, c * 32, n_pts - (tile * kRows + (warp & 3) * 32), tid & 31);
+      if (kSave) {
+        if (kPanel) {
+          float4* dst = reinterpret_cast<float4*>(h1_out + tile * (kRows * kHidden) + (int64_t)(c * 8) * (kRows * 4) + rtid * 4);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) dst[q * kRows] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+        } else {
+          warp_store_chunk(reinterpret_cast<float*>(smem + oStg + warp * kStgBytesPerWarp), v,
+                           h1_out + (tile * kRows + (warp & 3) * 32) * kHidden, c * 32, n_pts - (tile * kRows + (warp & 3) * 32), tid & 31);
+        }
+      }
     }
     tmem_st_wait();
     tc_fence_before();
     __syncthreads();
     // ---- layer 2 MMA: A from TMEM ----
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {   // one elected lane of a CONVERGED warp: plain UTCHMMA issue (see elect_one)
       tc_fence_after();
 #pragma unroll 4
       for (int ks = 0; ks < kHidden / 8; ++ks) {
@@ -327,9 +369,16 @@ __global__ void __launch_bounds__(kRows * kHalves, 1) k_shade_fwd_tc(
         p1 = fmaf(h3, wb.w, fmaf(h2v, wb.z, fmaf(h1v, wb.y, fmaf(h0, wb.x, p1))));
         p2 = fmaf(h3, wc.w, fmaf(h2v, wc.z, fmaf(h1v, wc.y, fmaf(h0, wc.x, p2))));
       }
-      if (kSave)
-        warp_store_chunk(reinterpret_cast<float*>(smem + oStg + warp * kStgBytesPerWarp), v,
-                         h2_out + (tile * kRows + (warp & 3) * 32) * kHidden, c * 32, n_pts - (tile * kRows + (warp & 3) * 32), tid & 31);
+      if (kSave) {
+        if (kPanel) {
+          float4* dst = reinterpret_cast<float4*>(h2_out + tile * (kRows * kHidden) + (int64_t)(c * 8) * (kRows * 4) + rtid * 4);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) dst[q * kRows] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+        } else {
+          warp_store_chunk(reinterpret_cast<float*>(smem + oStg + warp * kStgBytesPerWarp), v,
+                           h2_out + (tile * kRows + (warp & 3) * 32) * kHidden, c * 32, n_pts - (tile * kRows + (warp & 3) * 32), tid & 31);
+        }
+      }
     }
     if (kHalves == 2) {
       // the fp32 sum order of the 4-warp kernel is (columns 0..127 in one FMA chain); here it is chain(0..63) + chain(64..127):
@@ -484,7 +533,7 @@ __global__ void __launch_bounds__(kRows, 1) k_shade_bwd_tc(
     tc_fence_before();
     __syncthreads();
     // ---- dH1 = dZ2 . W2 ----
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {   // one elected lane of a CONVERGED warp: plain UTCHMMA issue (see elect_one)
       tc_fence_after();
 #pragma unroll 4
       for (int ks = 0; ks < kHidden / 8; ++ks) {
@@ -550,7 +599,7 @@ __global__ void __launch_bounds__(kRows, 1) k_shade_bwd_tc(
       fence_async_smem();
       tc_fence_before();
       __syncthreads();
-      if (tid == 0) {
+      if (warp == 0 && elect_one()) {   // one elected lane of a CONVERGED warp: plain UTCHMMA issue (see elect_one)
         tc_fence_after();
 #pragma unroll
         for (int ks = 0; ks < (int)(kChunkK / 8); ++ks) {
@@ -803,7 +852,7 @@ __global__ void __launch_bounds__(kRows, 1) k_shade_bwd_fused(
     tc_fence_before();
     __syncthreads();
     // ---- dH1 = dZ2 . W2 ----
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {   // one elected lane of a CONVERGED warp: plain UTCHMMA issue (see elect_one)
       tc_fence_after();
 #pragma unroll 4
       for (int ks = 0; ks < kHidden / 8; ++ks) {
@@ -891,7 +940,7 @@ __global__ void __launch_bounds__(kRows, 1) k_shade_bwd_fused(
     tc_fence_before();
     __syncthreads();
     // ---- dX = dZ1 . W1k  (N = 16) ----
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {   // one elected lane of a CONVERGED warp: plain UTCHMMA issue (see elect_one)
       tc_fence_after();
 #pragma unroll 4
       for (int ks = 0; ks < kHidden / 8; ++ks) {
@@ -966,12 +1015,24 @@ constexpr uint32_t oBar2 = oEmpty + 64;                              // MMA mbar
 constexpr uint32_t kSmemBytesF2 = oBar2 + 16;
 }  // namespace bf2
 
+// Phase timestamps of CTA 0 (tiles 4..7 of its range) for scripts/trace_ws.cu; compiled out of the library.
+#ifdef UBN_WS_TRACE
+__device__ long long g_ws_trace[4 * 8 * 64];
+#define WS_T(slot)                                                                                                   \
+  do {                                                                                                               \
+    const int64_t tt_ = tile - tile_begin - 4;                                                                       \
+    if (blockIdx.x == 0 && lane == 0 && tt_ >= 0 && tt_ < 4) g_ws_trace[(tt_ * 8 + warp) * 64 + (slot)] = clock64(); \
+  } while (0)
+#else
+#define WS_T(slot)
+#endif
+
 __device__ __forceinline__ void mbar_arrive(uint32_t bar_smem) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_smem) : "memory");
 }
 __device__ __forceinline__ void row_warps_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
-template <bool kThree>
+template <bool kThree, bool kPanel>      // kPanel: h1 / h2 in the panel layout of k_shade_fwd_tc<.., kPanel = true>
 __global__ void __launch_bounds__(2 * kRows, 1) k_shade_bwd_fused_ws(
     const float* __restrict__ feat, const int64_t* __restrict__ ray_id, const float* __restrict__ W1k,
     const float* __restrict__ W2, const float* __restrict__ W3, const float* __restrict__ rgb,
@@ -1065,6 +1126,27 @@ __global__ void __launch_bounds__(2 * kRows, 1) k_shade_bwd_fused_ws(
       const int64_t row = tile * kRows + rtid;
       const bool live = row < n_pts;
       float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+      WS_T(0);
+      // the next tile's operands are contiguous (128 consecutive rows): one lane asks L2 for them now, a whole tile ahead of
+      // their use, so that the row loads below (32 LDG.128 per thread, the serial head of every tile) hit L2 instead of HBM
+      if (warp == 1 && tile + 1 < tile_end && elect_one()) {
+        const int64_t r0 = (tile + 1) * kRows;
+        const uint32_t nr = (uint32_t)min((int64_t)kRows, n_pts - r0);
+        l2_prefetch(h2 + r0 * kHidden, (kPanel ? (uint32_t)kRows : nr) * kHidden * 4);   // panel layout: rows interleaved, buffer padded
+        l2_prefetch(h1 + r0 * kHidden, (kPanel ? (uint32_t)kRows : nr) * kHidden * 4);
+        l2_prefetch(feat + r0 * kFeat, nr * kFeat * 4);
+        l2_prefetch(rgb + r0 * 3, (nr * 12) & ~15u);
+        l2_prefetch(g_rgb + r0 * 3, (nr * 12) & ~15u);
+        l2_prefetch(ray_id + r0, nr * 8);
+      }
+      float4 hrow[kHidden / 4];                              // H2 row first: the longest wait of the tile starts at once
+#pragma unroll
+      for (int q = 0; q < kHidden / 4; ++q) {
+        hrow[q] = make_float4(0, 0, 0, 0);
+        if (live)
+          hrow[q] = __ldg(reinterpret_cast<const float4*>(kPanel ? h2 + tile * (kRows * kHidden) + (int64_t)q * (kRows * 4) + rtid * 4
+                                                                 : h2 + row * kHidden + q * 4));
+      }
       {
         int my_ray = -1;
         float4 x0 = make_float4(0, 0, 0, 0), x1 = x0, x2 = x0;
@@ -1084,12 +1166,7 @@ __global__ void __launch_bounds__(2 * kRows, 1) k_shade_bwd_fused_ws(
         xs[0] = x0; xs[1] = x1; xs[2] = x2;
         b3a += d0; b3b += d1; b3c += d2;
       }
-      float4 hrow[kHidden / 4];
-#pragma unroll
-      for (int q = 0; q < kHidden / 4; ++q) {
-        hrow[q] = make_float4(0, 0, 0, 0);
-        if (live) hrow[q] = __ldg(reinterpret_cast<const float4*>(h2 + row * kHidden + q * 4));
-      }
+      WS_T(1);
 #pragma unroll
       for (int c = 0; c < kHidden / 32; ++c) {
         uint32_t hi[32], lo[32];
@@ -1115,11 +1192,13 @@ __global__ void __launch_bounds__(2 * kRows, 1) k_shade_bwd_fused_ws(
         tmem_st32(tmem + lane_base + cAhi + c * 32, hi);
         if (kThree) tmem_st32(tmem + lane_base + cAlo + c * 32, lo);
         publish(q8);                                        // H2 chunk -> db2 / dW3 on the column warp
+        WS_T(2 + c);
       }
       tmem_st_wait();
       tc_fence_before();
       row_warps_sync();
-      if (tid == 0) {
+      WS_T(6);
+      if (warp == 0 && elect_one()) {   // one elected lane of a CONVERGED warp: plain UTCHMMA issue (see elect_one)
         tc_fence_after();
 #pragma unroll 4
         for (int ks = 0; ks < kHidden / 8; ++ks) {
@@ -1134,11 +1213,15 @@ __global__ void __launch_bounds__(2 * kRows, 1) k_shade_bwd_fused_ws(
 #pragma unroll
       for (int q = 0; q < kHidden / 4; ++q) {
         hrow[q] = make_float4(0, 0, 0, 0);
-        if (live) hrow[q] = __ldg(reinterpret_cast<const float4*>(h1 + row * kHidden + q * 4));
+        if (live)
+          hrow[q] = __ldg(reinterpret_cast<const float4*>(kPanel ? h1 + tile * (kRows * kHidden) + (int64_t)q * (kRows * 4) + rtid * 4
+                                                                 : h1 + row * kHidden + q * 4));
       }
+      WS_T(7);
       mbar_wait(bar_addr, phase);
       phase ^= 1;
       tc_fence_after();
+      WS_T(8);
 #pragma unroll
       for (int c = 0; c < kHidden / 32; ++c) {
         float v[32];
@@ -1161,11 +1244,13 @@ __global__ void __launch_bounds__(2 * kRows, 1) k_shade_bwd_fused_ws(
         tmem_st32(tmem + lane_base + cAhi + c * 32, hi);
         if (kThree) tmem_st32(tmem + lane_base + cAlo + c * 32, lo);
         publish(q8);                                        // dZ1 chunk -> dvb / dW1k on the column warp
+        WS_T(9 + c);
       }
       tmem_st_wait();
       tc_fence_before();
       row_warps_sync();
-      if (tid == 0) {
+      WS_T(13);
+      if (warp == 0 && elect_one()) {   // one elected lane of a CONVERGED warp: plain UTCHMMA issue (see elect_one)
         tc_fence_after();
 #pragma unroll 4
         for (int ks = 0; ks < kHidden / 8; ++ks) {
@@ -1177,9 +1262,11 @@ __global__ void __launch_bounds__(2 * kRows, 1) k_shade_bwd_fused_ws(
         }
         mma_commit(bar_addr);
       }
+      WS_T(14);
       mbar_wait(bar_addr, phase);
       phase ^= 1;
       tc_fence_after();
+      WS_T(15);
       {
         float v[16];
         tmem_ld16(tmem + lane_base + cDX, v);
@@ -1192,6 +1279,7 @@ __global__ void __launch_bounds__(2 * kRows, 1) k_shade_bwd_fused_ws(
       }
       tc_fence_before();
       row_warps_sync();                                     // TMEM reads done before the next tile's stores
+      WS_T(16);
     }
     atomicAdd(sAccB3 + 0, b3a); atomicAdd(sAccB3 + 1, b3b); atomicAdd(sAccB3 + 2, b3c);
   } else {
@@ -1226,7 +1314,9 @@ __global__ void __launch_bounds__(2 * kRows, 1) k_shade_bwd_fused_ws(
       // ---- H2 chunks: db2[j] += sum_s dZ2[s][j],  dW3[c][j] += sum_s dz3[s][c] H2[s][j] ----
 #pragma unroll
       for (int c = 0; c < kHidden / 32; ++c) {
+        WS_T(c);
         const float* stg = acquire();
+        WS_T(8 + c);
         const int j = c * 32 + lane;
         const float w3a = sW3[j], w3b = sW3[kHidden + j], w3c = sW3[2 * kHidden + j];
         float a0 = accW3[c][0], a1 = accW3[c][1], a2 = accW3[c][2], ab = accB2[c];
@@ -1238,40 +1328,58 @@ __global__ void __launch_bounds__(2 * kRows, 1) k_shade_bwd_fused_ws(
           ab += h > 0.f ? fmaf(dz.z, w3c, fmaf(dz.y, w3b, dz.x * w3a)) : 0.f;
         }
         release();
+        WS_T(16 + c);
         accW3[c][0] = a0; accW3[c][1] = a1; accW3[c][2] = a2; accB2[c] = ab;
       }
       // ---- dZ1 chunks: dvb[ray][j] += sum_{s in ray} dZ1[s][j],  dW1k[j][0..11] += sum_s dZ1[s][j] X[s][0..11] ----
 #pragma unroll
       for (int c = 0; c < kHidden / 32; ++c) {
+        WS_T(4 + c);
         const float* stg = acquire();                       // acquire first: the tile's tables are visible from here on
+        WS_T(12 + c);
         const int my_ray = sRay[rw * 32 + lane];
         const int ray0 = __shfl_sync(0xffffffffu, my_ray, 0);
         const bool one_ray = __all_sync(0xffffffffu, my_ray == ray0) && ray0 >= 0;
         const int j = c * 32 + lane;
         float run = 0.f;
         int run_ray = one_ray ? ray0 : -1;
-#pragma unroll 4
-        for (int sidx = 0; sidx < 32; ++sidx) {
-          const float d = stg[sidx * kStgStride + lane];
-          if (!one_ray) {                                   // warp-uniform branch
+#define UBN_DW1K_FMA()                                                                                     \
+        do {                                                                                               \
+          const float4* xs = reinterpret_cast<const float4*>(sX + (rw * 32 + sidx) * kFeat);               \
+          const float4 xa = xs[0], xb = xs[1], xc = xs[2];                                                 \
+          accW1[c][0] = fmaf(d, xa.x, accW1[c][0]); accW1[c][1] = fmaf(d, xa.y, accW1[c][1]);              \
+          accW1[c][2] = fmaf(d, xa.z, accW1[c][2]); accW1[c][3] = fmaf(d, xa.w, accW1[c][3]);              \
+          accW1[c][4] = fmaf(d, xb.x, accW1[c][4]); accW1[c][5] = fmaf(d, xb.y, accW1[c][5]);              \
+          accW1[c][6] = fmaf(d, xb.z, accW1[c][6]); accW1[c][7] = fmaf(d, xb.w, accW1[c][7]);              \
+          accW1[c][8] = fmaf(d, xc.x, accW1[c][8]); accW1[c][9] = fmaf(d, xc.y, accW1[c][9]);              \
+          accW1[c][10] = fmaf(d, xc.z, accW1[c][10]); accW1[c][11] = fmaf(d, xc.w, accW1[c][11]);          \
+        } while (0)
+        if (one_ray) {
+          // the common case (S samples per ray >> 32): straight-line body, so the unrolled iterations' LDS are hoisted above the
+          // FMAs (with the ray-change test in the loop every iteration waited for its own loads: 94 cycles per sample)
+#pragma unroll 8
+          for (int sidx = 0; sidx < 32; ++sidx) {
+            const float d = stg[sidx * kStgStride + lane];
+            run += d;
+            UBN_DW1K_FMA();
+          }
+        } else {
+#pragma unroll 2
+          for (int sidx = 0; sidx < 32; ++sidx) {
+            const float d = stg[sidx * kStgStride + lane];
             const int r = sRay[rw * 32 + sidx];
-            if (r != run_ray) {
+            if (r != run_ray) {                             // warp-uniform branch
               if (run_ray >= 0) atomicAdd(g_vb + (int64_t)run_ray * kHidden + j, run);
               run_ray = r;
               run = 0.f;
             }
+            run += d;
+            UBN_DW1K_FMA();
           }
-          run += d;
-          const float4* xs = reinterpret_cast<const float4*>(sX + (rw * 32 + sidx) * kFeat);
-          const float4 xa = xs[0], xb = xs[1], xc = xs[2];
-          accW1[c][0] = fmaf(d, xa.x, accW1[c][0]); accW1[c][1] = fmaf(d, xa.y, accW1[c][1]);
-          accW1[c][2] = fmaf(d, xa.z, accW1[c][2]); accW1[c][3] = fmaf(d, xa.w, accW1[c][3]);
-          accW1[c][4] = fmaf(d, xb.x, accW1[c][4]); accW1[c][5] = fmaf(d, xb.y, accW1[c][5]);
-          accW1[c][6] = fmaf(d, xb.z, accW1[c][6]); accW1[c][7] = fmaf(d, xb.w, accW1[c][7]);
-          accW1[c][8] = fmaf(d, xc.x, accW1[c][8]); accW1[c][9] = fmaf(d, xc.y, accW1[c][9]);
-          accW1[c][10] = fmaf(d, xc.z, accW1[c][10]); accW1[c][11] = fmaf(d, xc.w, accW1[c][11]);
         }
+#undef UBN_DW1K_FMA
         release();
+        WS_T(20 + c);
         if (run_ray >= 0) atomicAdd(g_vb + (int64_t)run_ray * kHidden + j, run);
       }
     }
@@ -1319,7 +1427,7 @@ constexpr uint32_t kSmemBytesD = oBarD + 16;
 constexpr int kCtasPerSM = 3;
 }  // namespace dw
 
-template <bool kThree>
+template <bool kThree, bool kPanel>
 __global__ void __launch_bounds__(dw::kThreadsDW, dw::kCtasPerSM) k_shade_dw2_tc(
     const float* __restrict__ W3, const float* __restrict__ rgb, const float* __restrict__ h1, const float* __restrict__ h2,
     const float* __restrict__ g_rgb, int64_t n_pts, float* __restrict__ gW2) {
@@ -1370,8 +1478,11 @@ __global__ void __launch_bounds__(dw::kThreadsDW, dw::kCtasPerSM) k_shade_dw2_tc
     }
 #pragma unroll
     for (int jj = 0; jj < kHidden / 8; ++jj) {
-      p2[jj] = live ? __ldg(h2 + row * kHidden + jj * 8 + q) : 0.f;
-      p1[jj] = live ? __ldg(h1 + row * kHidden + jj * 8 + q) : 0.f;
+      const int j = jj * 8 + q;
+      const int64_t idx = kPanel ? (row >> 7) * (int64_t)(kRows * kHidden) + (int64_t)(j >> 2) * (kRows * 4) + (row & 127) * 4 + (j & 3)
+                                 : row * kHidden + j;
+      p2[jj] = live ? __ldg(h2 + idx) : 0.f;
+      p1[jj] = live ? __ldg(h1 + idx) : 0.f;
     }
   };
   if (r_begin < r_end) prefetch(r_begin);
@@ -1400,7 +1511,7 @@ __global__ void __launch_bounds__(dw::kThreadsDW, dw::kCtasPerSM) k_shade_dw2_tc
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {   // one elected lane of a CONVERGED warp: plain UTCHMMA issue (see elect_one)
       tc_fence_after();
 #pragma unroll
       for (int ks = 0; ks < (int)(kK / 8); ++ks) {
@@ -1446,25 +1557,27 @@ extern "C" int ubn_rgbnet_fwd_tc(const float* feat, const float* view_bias, cons
   const unsigned grid = (unsigned)std::min<int64_t>(kNumSMs, n_tiles);
   cudaStream_t st = as_stream(stream);
   // single_pass bit 0: one TF32 pass per product; bit 1: the 4-warp form (A/B; default = 8 warps, two column halves per row)
-#define UBN_TC_LAUNCH_H(SAVE, THREE, H)                                                                                 \
+#define UBN_TC_LAUNCH_H(SAVE, THREE, H, P)                                                                                \
   do {                                                                                                                  \
-    cudaError_t e = cudaFuncSetAttribute(tc::k_shade_fwd_tc<SAVE, THREE, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+    cudaError_t e = cudaFuncSetAttribute(tc::k_shade_fwd_tc<SAVE, THREE, H, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                          (int)tc::kSmemBytes);                                                          \
     if (e != cudaSuccess) return finish(e);                                                                             \
-    tc::k_shade_fwd_tc<SAVE, THREE, H><<<grid, tc::kRows * H, tc::kSmemBytes, st>>>(feat, view_bias, ray_id, W1k, W2, b2, W3, \
-                                                                                     b3, n_pts, rgb, h1_save, h2_save);      \
+    tc::k_shade_fwd_tc<SAVE, THREE, H, P><<<grid, tc::kRows * H, tc::kSmemBytes, st>>>(feat, view_bias, ray_id, W1k, W2, b2, W3, \
+                                                                                        b3, n_pts, rgb, h1_save, h2_save);   \
   } while (0)
-#define UBN_TC_LAUNCH(SAVE, THREE)                                   \
+#define UBN_TC_LAUNCH(SAVE, THREE, P)                                \
   do {                                                               \
-    if (four_warps) UBN_TC_LAUNCH_H(SAVE, THREE, 1);                 \
-    else UBN_TC_LAUNCH_H(SAVE, THREE, 2);                            \
+    if (four_warps) UBN_TC_LAUNCH_H(SAVE, THREE, 1, P);              \
+    else UBN_TC_LAUNCH_H(SAVE, THREE, 2, P);                         \
   } while (0)
-  const bool four_warps = (single_pass & 2) != 0;
+  const bool four_warps = (single_pass & 2) != 0, panel = (single_pass & 4) != 0;   // bit 2: panel-layout saves (see the kernel)
   single_pass &= 1;
-  if (save) {
-    if (single_pass) UBN_TC_LAUNCH(true, false); else UBN_TC_LAUNCH(true, true);
+  if (save && panel) {
+    if (single_pass) UBN_TC_LAUNCH(true, false, true); else UBN_TC_LAUNCH(true, true, true);
+  } else if (save) {
+    if (single_pass) UBN_TC_LAUNCH(true, false, false); else UBN_TC_LAUNCH(true, true, false);
   } else {
-    if (single_pass) UBN_TC_LAUNCH(false, false); else UBN_TC_LAUNCH(false, true);
+    if (single_pass) UBN_TC_LAUNCH(false, false, false); else UBN_TC_LAUNCH(false, true, false);
   }
 #undef UBN_TC_LAUNCH
 #undef UBN_TC_LAUNCH_H
@@ -1491,10 +1604,10 @@ extern "C" int ubn_rgbnet_bwd_tc_data(const float* W2, const float* W3, const fl
   {   // dW2 (split-K GEMM over all samples)
     const int64_t n_rounds = (n_pts + tc::dw::kK - 1) / tc::dw::kK;
     const unsigned grid = (unsigned)std::min<int64_t>((int64_t)kNumSMs * tc::dw::kCtasPerSM, n_rounds);
-    cudaError_t e = cudaFuncSetAttribute(tc::k_shade_dw2_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(tc::k_shade_dw2_tc<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)tc::dw::kSmemBytesD);
     if (e != cudaSuccess) return finish(e);
-    tc::k_shade_dw2_tc<true><<<grid, tc::dw::kThreadsDW, tc::dw::kSmemBytesD, st>>>(W3, rgb, h1_save, h2_save, grad_rgb, n_pts,
+    tc::k_shade_dw2_tc<true, false><<<grid, tc::dw::kThreadsDW, tc::dw::kSmemBytesD, st>>>(W3, rgb, h1_save, h2_save, grad_rgb, n_pts,
                                                                                    grad_W2);
     UBN_LAUNCH_CHECK();
   }
@@ -1520,18 +1633,20 @@ extern "C" int ubn_rgbnet_bwd_tc_fused(const float* feat, const int64_t* ray_id,
                                                                              n_pts, grad_feat, grad_view_bias, grad_W1k, grad_b2,       \
                                                                              grad_W3, grad_b3);                                         \
     } while (0)
-#define UBN_BFW(T)                                                                                                             \
+#define UBN_BFW(T, P)                                                                                                          \
     do {                                                                                                                       \
-      cudaError_t e = cudaFuncSetAttribute(tc::k_shade_bwd_fused_ws<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,           \
+      cudaError_t e = cudaFuncSetAttribute(tc::k_shade_bwd_fused_ws<T, P>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
                                            (int)tc::bf2::kSmemBytesF2);                                                        \
       if (e != cudaSuccess) return finish(e);                                                                                  \
-      tc::k_shade_bwd_fused_ws<T><<<grid, 2 * tc::kRows, tc::bf2::kSmemBytesF2, st>>>(feat, ray_id, W1k, W2, W3, rgb, h1_save, h2_save, \
+      tc::k_shade_bwd_fused_ws<T, P><<<grid, 2 * tc::kRows, tc::bf2::kSmemBytesF2, st>>>(feat, ray_id, W1k, W2, W3, rgb, h1_save, h2_save, \
                                                                                       grad_rgb, n_pts, grad_feat, grad_view_bias,        \
                                                                                       grad_W1k, grad_b2, grad_W3, grad_b3);              \
     } while (0)
-    const bool one_pass = (single_pass & 1) != 0, plain = (single_pass & 2) != 0;
-    if (plain) { if (one_pass) UBN_BF(false); else UBN_BF(true); }
-    else       { if (one_pass) UBN_BFW(false); else UBN_BFW(true); }
+    const bool one_pass = (single_pass & 1) != 0, plain = (single_pass & 2) != 0, panel = (single_pass & 4) != 0;
+    if (plain && panel) return finish(cudaErrorInvalidValue);       // the 4-warp A/B kernel reads row-major saves only
+    if (plain)      { if (one_pass) UBN_BF(false); else UBN_BF(true); }
+    else if (panel) { if (one_pass) UBN_BFW(false, true); else UBN_BFW(true, true); }
+    else            { if (one_pass) UBN_BFW(false, false); else UBN_BFW(true, false); }
 #undef UBN_BFW
 #undef UBN_BF
     UBN_LAUNCH_CHECK();
@@ -1539,14 +1654,15 @@ extern "C" int ubn_rgbnet_bwd_tc_fused(const float* feat, const int64_t* ray_id,
   {   // dW2 (split-K GEMM over all samples)
     const int64_t n_rounds = (n_pts + tc::dw::kK - 1) / tc::dw::kK;
     const unsigned grid = (unsigned)std::min<int64_t>((int64_t)kNumSMs * tc::dw::kCtasPerSM, n_rounds);
-#define UBN_DW(T)                                                                                                              \
+#define UBN_DW(T, P)                                                                                                           \
     do {                                                                                                                       \
-      cudaError_t e = cudaFuncSetAttribute(tc::k_shade_dw2_tc<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,                 \
+      cudaError_t e = cudaFuncSetAttribute(tc::k_shade_dw2_tc<T, P>, cudaFuncAttributeMaxDynamicSharedMemorySize,              \
                                            (int)tc::dw::kSmemBytesD);                                                          \
       if (e != cudaSuccess) return finish(e);                                                                                  \
-      tc::k_shade_dw2_tc<T><<<grid, tc::dw::kThreadsDW, tc::dw::kSmemBytesD, st>>>(W3, rgb, h1_save, h2_save, grad_rgb, n_pts, grad_W2); \
+      tc::k_shade_dw2_tc<T, P><<<grid, tc::dw::kThreadsDW, tc::dw::kSmemBytesD, st>>>(W3, rgb, h1_save, h2_save, grad_rgb, n_pts, grad_W2); \
     } while (0)
-    if (single_pass & 1) UBN_DW(false); else UBN_DW(true);
+    if (single_pass & 4) { if (single_pass & 1) UBN_DW(false, true); else UBN_DW(true, true); }
+    else                 { if (single_pass & 1) UBN_DW(false, false); else UBN_DW(true, false); }
 #undef UBN_DW
     UBN_LAUNCH_CHECK();
   }

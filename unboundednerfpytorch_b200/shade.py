@@ -21,7 +21,7 @@ MODE = os.environ.get('UBN_RGBNET_MODE', 'tc3')
 # warp-specialised kernel (4 row warps drive the tensor cores, 4 column warps reduce over samples), dW2 in a second launch; no
 # intermediate in HBM; 'fused4' = the same without warp specialisation (A/B); 'tc3' = the previous three-launch form (dZ1 round trip + CUDA-core kernel for
 # the small gradients; kept for A/B); 'simt' = fp32 FFMA
-BWD_MODE = os.environ.get('UBN_RGBNET_BWD_MODE', 'fused4')
+BWD_MODE = os.environ.get('UBN_RGBNET_BWD_MODE', 'fused')
 
 
 class _ShadeFn(torch.autograd.Function):
@@ -36,14 +36,18 @@ class _ShadeFn(torch.autograd.Function):
         # mirrors requires_grad of the inputs even under torch.no_grad() -- render / eval forwards must not allocate and stream
         # the two [M,128] activation saves
         need_grad = bool(need_grad) and any(ctx.needs_input_grad)
-        h1 = torch.empty(M, 128, dtype=torch.float32, device=dev) if need_grad else None
-        h2 = torch.empty(M, 128, dtype=torch.float32, device=dev) if need_grad else None
+        # panel-layout saves ([tile][32 column quads][128 rows][4], ceil(M/128)*128 rows): coalesced for the row-per-thread kernels
+        # on both sides; only the tcgen05 forward writes it and only the warp-specialised backward (+ dW2) reads it
+        panel = need_grad and MODE in ('tc3', 'tc1', 'tc3w4') and BWD_MODE == 'fused'
+        rows = -(-M // 128) * 128 if panel else M
+        h1 = torch.empty(rows, 128, dtype=torch.float32, device=dev) if need_grad else None
+        h2 = torch.empty(rows, 128, dtype=torch.float32, device=dev) if need_grad else None
         with ops._Guard(feat) as lib:
             with _cabi.timed('rgbnet_fwd'):
                 if MODE in ('tc3', 'tc1', 'tc3w4'):      # 'tc3w4': the 4-warp form of the forward kernel (A/B of the 8-warp default)
                     check(lib.ubn_rgbnet_fwd_tc(ptr(feat), ptr(vb), ptr(ray_id), ptr(W1k), ptr(W2), ptr(b2), ptr(W3), ptr(b3),
                                                 c_i64(M), ptr(rgb), ptr(h1), ptr(h2),
-                                                c_int((1 if MODE == 'tc1' else 0) | (2 if MODE == 'tc3w4' else 0)),
+                                                c_int((1 if MODE == 'tc1' else 0) | (2 if MODE == 'tc3w4' else 0) | (4 if panel else 0)),
                                                 stream_of(feat)))
                 else:
                     check(lib.ubn_rgbnet_fwd(ptr(feat), ptr(vb), ptr(ray_id), ptr(W1k), ptr(W2), ptr(b2), ptr(W3), ptr(b3),
@@ -51,6 +55,8 @@ class _ShadeFn(torch.autograd.Function):
         if need_grad:
             ctx.save_for_backward(feat, ray_id, W1k, W2, W3, rgb, h1, h2)
             ctx.n_rays = vb.shape[0]
+            ctx.panel = panel
+            ctx.bwd_mode = BWD_MODE
         return rgb
 
     @staticmethod
@@ -64,14 +70,15 @@ class _ShadeFn(torch.autograd.Function):
         z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
         g_vb, gW1k, gW2, gb2, gW3, gb3 = z(ctx.n_rays, 128), z(128, 12), z(128, 128), z(128), z(3, 128), z(3)
         with ops._Guard(feat) as lib:
-            if BWD_MODE in ('fused', 'fused4'):          # 'fused4': the same kernel without warp specialisation (A/B)
+            bwd_mode = ctx.bwd_mode                      # as chosen in forward (the save layout depends on it)
+            if bwd_mode in ('fused', 'fused4'):          # 'fused4': the same kernel without warp specialisation (A/B)
                 with _cabi.timed('rgbnet_bwd'):
                     check(lib.ubn_rgbnet_bwd_tc_fused(ptr(feat), ptr(ray_id), ptr(W1k), ptr(W2), ptr(W3), ptr(rgb), ptr(h1), ptr(h2),
                                                       ptr(g_rgb), c_i64(M), ptr(g_feat), ptr(g_vb), ptr(gW1k), ptr(gW2), ptr(gb2),
-                                                      ptr(gW3), ptr(gb3), c_int((1 if MODE == 'tc1' else 0) | (2 if BWD_MODE == 'fused4' else 0)),
+                                                      ptr(gW3), ptr(gb3), c_int((1 if MODE == 'tc1' else 0) | (2 if bwd_mode == 'fused4' else 0) | (4 if ctx.panel else 0)),
                                                       stream_of(feat)))
                 return g_feat, g_vb, None, gW1k, gW2, gb2, gW3, gb3, None
-            if BWD_MODE == 'tc3':
+            if bwd_mode == 'tc3':
                 dz1 = torch.empty(M, 128, dtype=torch.float32, device=dev)
                 with _cabi.timed('rgbnet_bwd'):
                     check(lib.ubn_rgbnet_bwd_tc_data(ptr(W2), ptr(W3), ptr(rgb), ptr(h1), ptr(h2), ptr(g_rgb), c_i64(M),
