@@ -419,8 +419,8 @@ def test_psnr_gate_of_the_single_pass_tf32_mode(monkeypatch):
 
 @pytest.mark.parametrize('flavor,F_,thres', [('fouriergrid', 4, 0.0), ('fouriergrid', 2, 1e-4), ('dcvgo', 0, 1e-4)])
 def test_feature_kernel_families_agree(flavor, F_, thres):
-    """Pass B in its three forms (ubn_set_feature_kernel 0 / 1 / 2: warp-cooperative, lane-per-sample forward, lane-per-sample
-    forward + backward): identical survivors and records, features / rgb equal to fp32 rounding, k0 gradients equal to the
+    """Pass B in its four forms (ubn_set_feature_kernel 0 / 1 / 2 / 3: warp-cooperative, lane-per-sample forward, lane-per-sample
+    forward + backward, lane-per-sample forward + slab-major scatter): identical survivors and records, features / rgb equal to fp32 rounding, k0 gradients equal to the
     atomics' summation order; and the lane-per-sample forward is BIT-identical to the stand-alone grid op (ATen corner order +
     torch-CUDA slab-mean order), i.e. to what F.grid_sample(...).mean(0) returns in the reference."""
     from unboundednerfpytorch_b200 import ops
@@ -430,7 +430,7 @@ def test_feature_kernel_families_agree(flavor, F_, thres):
     rk = dict(near=0., far=1e9, bg=1, rand_bkgd=False, stepsize=0.5, render_depth=True)
     outs, grads = [], []
     try:
-        for variant in (0, 1, 2):
+        for variant in (0, 1, 2, 3):
             ops.set_feature_kernel(variant)
             assert ops.get_feature_kernel() == variant
             m.zero_grad(set_to_none=True)

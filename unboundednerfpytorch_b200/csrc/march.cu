@@ -335,7 +335,7 @@ using namespace ubn;
 extern "C" {
 
 int ubn_set_feature_kernel(int variant) {
-  if (variant < 0 || variant > 2) return finish(cudaErrorInvalidValue);
+  if (variant < 0 || variant > 3) return finish(cudaErrorInvalidValue);
   set_feature_kernel(variant);
   return 0;
 }

@@ -358,7 +358,99 @@ static int launch_v3(bool backward, const float* rays_o, const float* rays_d, co
   return 0;
 }
 
-// 0 = warp-cooperative kernels (v2), 1 = lane-per-sample (v3) for the forward (default), 2 = for forward and backward.  Set
+// =====================================================================================================================
+// Slab-major scatter (variant 3).  The k0 gradient of the truck workload is 9 slabs x 172 MB: with the slab loop inside the
+// kernel every resident warp spreads its reductions over all 1.55 GB, so the 126 MB L2 holds 8 % of the live footprint and
+// nearly every vector reduction costs a DRAM sector fetch + write-back at random addresses (ncu, round 1: 8.9 GB of DRAM
+// traffic, L2 hit 51 %).  Here the SLAB is the slow grid dimension (blockIdx.y): the CTAs of slab s are scheduled before the
+// CTAs of slab s + 1, the live gradient footprint at any moment is ONE slab (73 % of it L2-resident), and every sector of a
+// slab goes to DRAM about once.  Cost: the chunk preamble (flags, sample point, compaction) runs once per slab instead of
+// once, and the 48-byte gradient rows are re-read 9 times (coalesced, L2 hits after the first slab).  Same lane roles and
+// the same addends as k_march_feature_v2<.., true, ..>: the gradients differ only by the atomics' summation order.
+// =====================================================================================================================
+template <int kP, int kGroup>
+__global__ void __launch_bounds__(32 * kMarchWarps, 6) k_march_feature_bwd_slab(
+    const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float* __restrict__ t_table,
+    GridView g, MarchParams p, int64_t n_rays, const uint8_t* __restrict__ flags,
+    const int64_t* __restrict__ offsets, const float* __restrict__ gfeat, float* __restrict__ grad_grid) {
+  const int lane = threadIdx.x & 31;
+  const int sl = blockIdx.y;
+  const int64_t ray = (int64_t)blockIdx.x * kMarchWarps + (threadIdx.x >> 5);
+  if (ray >= n_rays) return;
+  int64_t out_base = offsets[ray];
+  const int64_t out_end = offsets[ray + 1];
+  if (out_base == out_end) return;
+  const int corner = lane >> 2, quad = lane & 3;
+  const bool bx = corner & 4, by = corner & 2, bz = corner & 1;
+  const bool quad_on = quad < (g.C >> 2);
+  const int lane_off = (((bx ? 1 : 0) * g.Y + (by ? 1 : 0)) * g.Z + (bz ? 1 : 0)) * g.C + quad * 4;
+  float* slab = grad_grid + sl * g.sp + lane_off;
+  const Ray r = load_ray(rays_o + 3 * ray, rays_d + 3 * ray, p);
+  const int S = p.S;
+
+  for (int base = 0; base < S && out_base < out_end; base += 32) {
+    const int s = base + lane;
+    const uint8_t f = (s < S) ? flags[ray * S + s] : 0;
+    const bool keep = (f & UBN_FLAG_KEEP) != 0;
+    const unsigned km = __ballot_sync(0xffffffffu, keep);
+    if (km == 0) continue;
+    const int n_here = __popc(km);
+    CellR cell;
+    {
+      float x = 0, y = 0, z = 0;
+      if (keep) sample_point(r, t_table[s], p, x, y, z);
+      const float nx = norm_coord(x, g.mn[0], g.len[0]);
+      const float ny = norm_coord(y, g.mn[1], g.len[1]);
+      const float nz = norm_coord(z, g.mn[2], g.len[2]);
+      cell = make_cell(src_index(fourier_gamma(sl, nx), g.X), src_index(fourier_gamma(sl, ny), g.Y),
+                       src_index(fourier_gamma(sl, nz), g.Z), g.X, g.Y, g.Z);
+    }
+    if (km != 0xffffffffu) {
+      const int src = __fns(km, 0, lane + 1) & 31;
+      cell.v = __shfl_sync(0xffffffffu, cell.v, src);
+      cell.fx = __shfl_sync(0xffffffffu, cell.fx, src);
+      cell.fy = __shfl_sync(0xffffffffu, cell.fy, src);
+      cell.fz = __shfl_sync(0xffffffffu, cell.fz, src);
+    }
+    for (int g0 = 0; g0 < n_here; g0 += kGroup) {
+      float4 gin[kGroup];
+#pragma unroll
+      for (int j = 0; j < kGroup; ++j) {
+        gin[j] = make_float4(0, 0, 0, 0);
+        if (quad_on && g0 + j < n_here) gin[j] = __ldg(reinterpret_cast<const float4*>(gfeat + (out_base + g0 + j) * g.C + quad * 4));
+      }
+#pragma unroll
+      for (int j = 0; j < kGroup; ++j) {
+        const int src = (g0 + j) & 31;
+        const int v = __shfl_sync(0xffffffffu, cell.v, src);
+        const float fx = __shfl_sync(0xffffffffu, cell.fx, src);
+        const float fy = __shfl_sync(0xffffffffu, cell.fy, src);
+        const float fz = __shfl_sync(0xffffffffu, cell.fz, src);
+        const float wgt = ((bz ? fz : 1.f - fz) * (by ? fy : 1.f - fy)) * (bx ? fx : 1.f - fx);
+        if (quad_on && g0 + j < n_here) {
+          const float4 q = gin[j];
+          red_add_v4(slab + (int64_t)v * g.C,
+                     make_float4(wgt * slab_mean_scale(q.x, kP), wgt * slab_mean_scale(q.y, kP), wgt * slab_mean_scale(q.z, kP),
+                                 wgt * slab_mean_scale(q.w, kP)));
+        }
+      }
+    }
+    out_base += n_here;
+  }
+}
+
+template <int kP>
+static int launch_bwd_slab(const float* rays_o, const float* rays_d, const float* t_table, const GridView& g, const MarchParams& p,
+                           int64_t n_rays, const uint8_t* flags, const int64_t* offsets, const float* gfeat, float* grad_grid,
+                           cudaStream_t st) {
+  const dim3 grid(blocks_for(n_rays, kMarchWarps), kP);
+  k_march_feature_bwd_slab<kP, 4><<<grid, 32 * kMarchWarps, 0, st>>>(rays_o, rays_d, t_table, g, p, n_rays, flags, offsets, gfeat, grad_grid);
+  UBN_LAUNCH_CHECK();
+  return 0;
+}
+
+// 0 = warp-cooperative kernels (v2), 1 = lane-per-sample (v3) for the forward (default), 2 = for forward and backward, 3 = lane-per-sample forward + SLAB-MAJOR cooperative
+// scatter (k_march_feature_bwd_slab).  Set
 // through ubn_set_feature_kernel (tests exercise every value).  The scatter stays cooperative: one warp instruction issues the 24
 // vector reductions of a sample into 8 x 48 contiguous bytes, whereas lane-per-sample reductions hit 32 unrelated records per
 // instruction and serialise in the L2 atomic units.
@@ -374,7 +466,16 @@ int march_feature_v2(bool backward, const float* rays_o, const float* rays_d, co
                      uint8_t* o_inner, cudaStream_t st) {
   if (g.X < 2 || g.Y < 2 || g.Z < 2) return -1;
   if ((int64_t)g.X * g.Y * g.Z * g.C >= (1ll << 31)) return -1;   // 32-bit voxel offsets inside a slab
-  if (g.C == 12 && (g_feature_kernel == 2 || (g_feature_kernel == 1 && !backward))) {
+  if (backward && g_feature_kernel == 3 && g.P > 1) {
+    switch (g.P) {
+      case 3: return launch_bwd_slab<3>(rays_o, rays_d, t_table, g, p, n_rays, flags, offsets, feat, grad_grid, st);
+      case 5: return launch_bwd_slab<5>(rays_o, rays_d, t_table, g, p, n_rays, flags, offsets, feat, grad_grid, st);
+      case 7: return launch_bwd_slab<7>(rays_o, rays_d, t_table, g, p, n_rays, flags, offsets, feat, grad_grid, st);
+      case 9: return launch_bwd_slab<9>(rays_o, rays_d, t_table, g, p, n_rays, flags, offsets, feat, grad_grid, st);
+      default: break;
+    }
+  }
+  if (g.C == 12 && (g_feature_kernel == 2 || ((g_feature_kernel == 1 || g_feature_kernel == 3) && !backward))) {
 #define UBN_V3(P)                                                                                                               \
   case P:                                                                                                                       \
     return launch_v3<P>(backward, rays_o, rays_d, t_table, g, p, n_rays, flags, offsets, density, alpha, weight, feat, grad_grid, \
