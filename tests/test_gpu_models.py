@@ -273,6 +273,48 @@ def test_fused_rgbnet_vs_torch(mode, monkeypatch):
                 assert_close(a, b, rtol=2e-5, atol=(2e-6 if nm == 'k0' else 1e-5) * scale + 1e-9, what=f'grad {nm} M={M}')
 
 
+def test_rgbnet_dw2_long_sample_sum_vs_fp64():
+    """dW2 = sum over ALL samples of dZ2^T H1 is a split-K tensor-core GEMM.  tcgen05 adds into its fp32 accumulator with
+    truncation, so one accumulator chain per CTA over hundreds of 32-sample rounds carries a bias that grows linearly with the
+    chain (measured at size in round 2: 1.4e-4 of scale at 295 rounds per CTA, 4.5e-5 at 91, against 2.6e-6 for cuBLAS).
+    k_shade_dw2_tc therefore restarts the MMA accumulator every 4 rounds and keeps an fp32 round-to-nearest running sum in a
+    second block of tensor memory.  This test makes the chains long (1.2 M samples, ~130 rounds per CTA) and judges dW2 -- and
+    the other sample sums -- against an fp64 evaluation at 1e-5 of the tensor scale."""
+    from unboundednerfpytorch_b200 import models, shade as shade_mod
+    assert shade_mod.MODE == 'tc3' and shade_mod.BWD_MODE == 'fused'
+    torch.manual_seed(5)
+    net = models._make_rgbnet(39, 128, 3).to(DEV)
+    M, n_rays = 1_200_007, 2048
+    g = torch.Generator().manual_seed(M)
+    k0 = torch.randn(M, 12, generator=g).to(DEV)
+    emb = torch.randn(n_rays, 27, generator=g).to(DEV)
+    ray_id = torch.sort(torch.randint(0, n_rays, (M,), generator=g))[0].to(DEV)
+    gr = (torch.rand(M, 3, generator=g) + 0.25).to(DEV)            # one-signed upstream gradient: partial sums grow steadily
+    with torch.no_grad():                                          # drop ReLU-ambiguous samples (see test_fused_rgbnet_vs_torch)
+        x64 = torch.cat([k0, emb[ray_id]], -1).double()
+        z1 = x64 @ net[0].weight.double().t() + net[0].bias.double()
+        z2 = torch.relu(z1) @ net[2][0].weight.double().t() + net[2][0].bias.double()
+        ok = torch.minimum(z1.abs().amin(1), z2.abs().amin(1)) > 1e-5
+        del x64, z1, z2
+    k0, ray_id, gr = k0[ok].clone(), ray_id[ok].contiguous(), gr[ok].contiguous()
+    net64 = models._make_rgbnet(39, 128, 3).to(DEV).double()
+    net64.load_state_dict({k: v.double() for k, v in net.state_dict().items()})
+    want = {}
+    for lo in range(0, k0.shape[0], 200_000):                       # fp64 yardstick, chunked to bound memory
+        sl = slice(lo, lo + 200_000)
+        out64 = torch.sigmoid(net64(torch.cat([k0[sl], emb[ray_id[sl]]], -1).double()))
+        (out64 * gr[sl].double()).sum().backward()
+    want = [p.grad.clone() for p in net64.parameters()]
+    k0 = k0.requires_grad_(True)
+    out = shade_mod.shade(net, k0, emb, ray_id)
+    (out * gr).sum().backward()
+    for a, b, nm in zip([p.grad for p in net.parameters()], want, ['W1', 'b1', 'W2', 'b2', 'W3', 'b3']):
+        scale = float(b.abs().max())
+        err = float((a.double() - b).abs().max()) / scale
+        print(f'[dw2-long] grad {nm}: max error {err:.2e} of scale')
+        assert err <= 1e-5, f'grad {nm}: {err:.2e} of scale vs fp64'
+
+
 def test_progressive_growing_and_occupancy_utilities(oracle):
     """scale_volume_grid / update_occupancy_cache / voxel_count_views / maskout_near_cam_vox / hit_coarse_geo as
     grid-native kernels (csrc/grid_utils.cu), each against the reference's own torch composition (FourierGrid_model.py:375-456)

@@ -244,6 +244,7 @@ __global__ void __launch_bounds__(32 * kMarchWarps) k_march_density_bwd(
     const float* __restrict__ g_weight, const float* __restrict__ g_alpha, const float* __restrict__ g_density,
     const float* __restrict__ g_last, float* __restrict__ grad_grid) {
   __shared__ int s_cnt[kMarchWarps][kMaxChunks];
+  __shared__ __align__(16) float2 s_pair[kMarchWarps][32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int64_t ray = (int64_t)blockIdx.x * kMarchWarps + w;
   if (ray >= n_rays) return;
@@ -274,16 +275,29 @@ __global__ void __launch_bounds__(32 * kMarchWarps) k_march_density_bwd(
     const int64_t ci = off + s_cnt[w][c] + __popc(km & ((1u << lane) - 1));
     const float gw = (keep && g_weight) ? g_weight[ci] : 0.f;
     const float wt = valid ? weight[i] : 0.f;
-    // reverse sequential accumulation over the scanned samples (alpha2weight_backward order)
-    unsigned m = __ballot_sync(0xffffffffu, (f & UBN_FLAG_SCANNED) != 0);
+    // reverse sequential accumulation over the scanned samples (alpha2weight_backward order).  The chain is inherently serial
+    // (one fp32 fma per scanned sample, in the reference's order), so every lane runs it redundantly on warp-uniform operands.
+    // They used to be fetched with two shuffles per sample from a data-dependent lane (ncu, round 2: mio_throttle + short
+    // scoreboard = 55 % of the kernel's stall samples); now the chunk's 32 (grad, weight) pairs go through 256 bytes of shared
+    // memory and come back as 16 broadcast LDS.128 in a fully unrolled loop.
+    const unsigned m = __ballot_sync(0xffffffffu, (f & UBN_FLAG_SCANNED) != 0);
     float my_back = 0.f;
-    while (m) {
-      const int j = 31 - __clz(m);
-      m &= ~(1u << j);
-      const float gj = __shfl_sync(0xffffffffu, gw, j);
-      const float wj = __shfl_sync(0xffffffffu, wt, j);
-      if (lane == j) my_back = back_cum;
-      back_cum += gj * wj;            // float fma (render_utils_kernel.cu:674)
+    if (m) {
+      s_pair[w][lane] = make_float2(gw, wt);
+      __syncwarp();
+#pragma unroll
+      for (int jj = 15; jj >= 0; --jj) {
+        const float4 v = *reinterpret_cast<const float4*>(&s_pair[w][2 * jj]);      // pairs 2jj (x, y) and 2jj + 1 (z, w)
+        if (m & (2u << (2 * jj))) {
+          if (lane == 2 * jj + 1) my_back = back_cum;
+          back_cum = fmaf(v.z, v.w, back_cum);            // float fma (render_utils_kernel.cu:674)
+        }
+        if (m & (1u << (2 * jj))) {
+          if (lane == 2 * jj) my_back = back_cum;
+          back_cum = fmaf(v.x, v.y, back_cum);
+        }
+      }
+      __syncwarp();
     }
     if (!(f & UBN_FLAG_QUERIED)) continue;
     const float a = alpha[i];

@@ -319,6 +319,29 @@ __global__ void __launch_bounds__(kRows * kHalves, 1) k_shade_fwd_tc(
       }
       tmem_st32(tmem + lane_base + cA2hi + c * 32, hi);
       if (kThreePass) tmem_st32(tmem + lane_base + cA2lo + c * 32, lo);
+      // ---- layer 2 MMA, issued K-chunk by K-chunk: as soon as every warp has its 32-column piece of H1 in tensor memory, the
+      // K-steps that read those columns go to the tensor pipe and run while the next pieces are still being produced (the whole
+      // layer used to be issued after the last piece: 48 MMAs = ~3 k cycles of a ~12 k cycle tile with every warp waiting) ----
+      tmem_st_wait();
+      tc_fence_before();
+      __syncthreads();
+      if (warp == 0 && elect_one()) {   // one elected lane of a CONVERGED warp: plain UTCHMMA issue (see elect_one)
+        tc_fence_after();
+#pragma unroll
+        for (int hh = 0; hh < kHalves; ++hh) {
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {
+            const int ks = (hh * kChunksPerHalf + cc) * 4 + k4;
+            mma_ts(tmem + cD2, tmem + cA2hi + ks * 8, dW2hi + ks * kStep, (cc > 0 || hh > 0 || k4 > 0) ? 1u : 0u);
+            if (kThreePass) {
+              mma_ts(tmem + cD2, tmem + cA2lo + ks * 8, dW2hi + ks * kStep, 1);
+              mma_ts(tmem + cD2, tmem + cA2hi + ks * 8, dW2lo + ks * kStep, 1);
+            }
+          }
+        }
+        if (cc == kChunksPerHalf - 1) mma_commit(bar_addr);
+      }
+      // the activation save goes out while the tensor pipe works on this piece
       if (kSave) {
         if (kPanel) {
           float4* dst = reinterpret_cast<float4*>(h1_out + tile * (kRows * kHidden) + (int64_t)(c * 8) * (kRows * 4) + rtid * 4);
@@ -329,22 +352,6 @@ __global__ void __launch_bounds__(kRows * kHalves, 1) k_shade_fwd_tc(
                            h1_out + (tile * kRows + (warp & 3) * 32) * kHidden, c * 32, n_pts - (tile * kRows + (warp & 3) * 32), tid & 31);
         }
       }
-    }
-    tmem_st_wait();
-    tc_fence_before();
-    __syncthreads();
-    // ---- layer 2 MMA: A from TMEM ----
-    if (warp == 0 && elect_one()) {   // one elected lane of a CONVERGED warp: plain UTCHMMA issue (see elect_one)
-      tc_fence_after();
-#pragma unroll 4
-      for (int ks = 0; ks < kHidden / 8; ++ks) {
-        mma_ts(tmem + cD2, tmem + cA2hi + ks * 8, dW2hi + ks * kStep, ks > 0);
-        if (kThreePass) {
-          mma_ts(tmem + cD2, tmem + cA2lo + ks * 8, dW2hi + ks * kStep, 1);
-          mma_ts(tmem + cD2, tmem + cA2hi + ks * 8, dW2lo + ks * kStep, 1);
-        }
-      }
-      mma_commit(bar_addr);
     }
     mbar_wait(bar_addr, phase);
     phase ^= 1;
@@ -696,6 +703,17 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
       : "memory");
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+      "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+      "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+      "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+      : "memory");
 }
 
 // stage this warp's 32 x 32 chunk (thread = row) so that afterwards lane = column: stg[row * 36 + col]
@@ -1191,25 +1209,29 @@ __global__ void __launch_bounds__(2 * kRows, 1) k_shade_bwd_fused_ws(
         }
         tmem_st32(tmem + lane_base + cAhi + c * 32, hi);
         if (kThree) tmem_st32(tmem + lane_base + cAlo + c * 32, lo);
+        // dH1 = dZ2 . W2 is issued K-chunk by K-chunk: the four K-steps that read this 32-column piece of dZ2 start as soon as
+        // all four row warps have stored it and run on the tensor pipe while the next piece is computed (issued after the last
+        // piece, the 48 MMAs = ~3 k cycles were pure waiting for the row warps)
+        tmem_st_wait();
+        tc_fence_before();
+        row_warps_sync();
+        if (warp == 0 && elect_one()) {   // one elected lane of a CONVERGED warp: plain UTCHMMA issue (see elect_one)
+          tc_fence_after();
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {
+            const int ks = c * 4 + k4;
+            mma_ts(tmem + cDHf, tmem + cAhi + ks * 8, dWThi + ks * kStepK, ks > 0);
+            if (kThree) {
+              mma_ts(tmem + cDHf, tmem + cAlo + ks * 8, dWThi + ks * kStepK, 1);
+              mma_ts(tmem + cDHf, tmem + cAhi + ks * 8, dWTlo + ks * kStepK, 1);
+            }
+          }
+          if (c == kHidden / 32 - 1) mma_commit(bar_addr);
+        }
         publish(q8);                                        // H2 chunk -> db2 / dW3 on the column warp
         WS_T(2 + c);
       }
-      tmem_st_wait();
-      tc_fence_before();
-      row_warps_sync();
       WS_T(6);
-      if (warp == 0 && elect_one()) {   // one elected lane of a CONVERGED warp: plain UTCHMMA issue (see elect_one)
-        tc_fence_after();
-#pragma unroll 4
-        for (int ks = 0; ks < kHidden / 8; ++ks) {
-          mma_ts(tmem + cDHf, tmem + cAhi + ks * 8, dWThi + ks * kStepK, ks > 0);
-          if (kThree) {
-            mma_ts(tmem + cDHf, tmem + cAlo + ks * 8, dWThi + ks * kStepK, 1);
-            mma_ts(tmem + cDHf, tmem + cAhi + ks * 8, dWTlo + ks * kStepK, 1);
-          }
-        }
-        mma_commit(bar_addr);
-      }
 #pragma unroll
       for (int q = 0; q < kHidden / 4; ++q) {
         hrow[q] = make_float4(0, 0, 0, 0);
@@ -1414,9 +1436,19 @@ __global__ void __launch_bounds__(2 * kRows, 1) k_shade_bwd_fused_ws(
 // ---- dW2 += dZ2^T . H1 as its own split-K GEMM ----------------------------------------------------------------------
 // Round = 32 consecutive samples.  Warp w stages rows 4w..4w+3; lane l serves row (l & 3) and hidden units j = 8*jj + (l >> 2)
 // (jj < 16): for one store instruction the 32 lanes hit 32 distinct banks of one K-major panel (conflict free).
-// The kernel is global-load-latency bound (ncu: 75 % long-scoreboard stalls with one CTA per SM), so it is sized for
-// THREE co-resident CTAs per SM (66 KB smem, 128 TMEM columns each) and every thread prefetches the next round's 32 values
-// into registers before it waits for the tensor pipe to release the single staging buffer.
+// The kernel is bound by the load/store pipe (ncu: l1tex 68 %, long-scoreboard stalls): every thread prefetches the next round's
+// 32 values into registers before it waits for the tensor pipe to release the single staging buffer, and one lane asks L2 for the
+// next 128-sample tile of both saves (cp.async.bulk.prefetch) while the current one is consumed.
+//
+// ACCUMULATION LENGTH.  The tensor core adds into its fp32 accumulator with TRUNCATION, not round-to-nearest: a chain of n
+// accumulating MMAs carries a systematic bias of ~n/2 ulp of the running value.  Harmless for the K = 128 chains of the other
+// kernels (48 MMAs: ~1.4e-6), but a split-K GEMM over samples is one chain per CTA -- 3 540 MMAs on the truck workload -- and the
+// round-2 parity run at size measured exactly that: dW2 off by 1.4e-4 of its scale on truck (295 rounds per CTA), 4.5e-5 on bicycle
+// (91 rounds), linear in the chain length, against 2.6e-6 for the reference's cuBLAS path (tests/test_gpu_parity_at_size.py).
+// So the MMA accumulator is restarted every kFlush = 4 rounds (48 MMAs) and the group results are summed with ordinary fp32
+// round-to-nearest adds into a RUNNING SUM that lives in a second 128-column block of tensor memory (tcgen05.ld / add / tcgen05.st
+// by the eight warps: TMEM as a 64 KB private scratchpad; no registers held across rounds, no shared memory, no HBM / L2 traffic).
+// 256 TMEM columns per CTA -> two co-resident CTAs per SM.
 namespace dw {
 constexpr int kThreadsDW = 256;
 constexpr uint32_t kK = 32;
@@ -1424,7 +1456,9 @@ constexpr uint32_t kOpBytes = (kK / 4) * kPanelBytes;          // 16 KB per oper
 constexpr uint32_t oW3d = 4 * kOpBytes;                        // A hi, A lo, B hi, B lo
 constexpr uint32_t oBarD = oW3d + 3 * kHidden * 4;             // mbarrier + tmem slot
 constexpr uint32_t kSmemBytesD = oBarD + 16;
-constexpr int kCtasPerSM = 3;
+constexpr int kCtasPerSM = 2;
+constexpr int kFlush = 4;                                      // rounds per MMA accumulation chain (= one 128-sample tile)
+constexpr uint32_t cAcc = 0, cSum = 128;                       // TMEM columns: MMA accumulator, running fp32 sum
 }  // namespace dw
 
 template <bool kThree, bool kPanel>
@@ -1444,7 +1478,7 @@ __global__ void __launch_bounds__(dw::kThreadsDW, dw::kCtasPerSM) k_shade_dw2_tc
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(tmem_slot)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   fence_async_smem();
@@ -1456,13 +1490,17 @@ __global__ void __launch_bounds__(dw::kThreadsDW, dw::kCtasPerSM) k_shade_dw2_tc
   const uint64_t dAhi = make_desc(smem_u32(smem)), dAlo = make_desc(smem_u32(smem + kOpBytes));
   const uint64_t dBhi = make_desc(smem_u32(smem + 2 * kOpBytes)), dBlo = make_desc(smem_u32(smem + 3 * kOpBytes));
 
+  // contiguous range of rounds per CTA, aligned to whole 128-sample tiles (kFlush rounds) so that a chain never straddles CTAs
   const int64_t n_rounds = (n_pts + kK - 1) / kK;
-  const int64_t per_cta = (n_rounds + gridDim.x - 1) / gridDim.x;
-  const int64_t r_begin = (int64_t)blockIdx.x * per_cta, r_end = min(n_rounds, r_begin + per_cta);
+  const int64_t n_groups = (n_rounds + kFlush - 1) / kFlush;
+  const int64_t g_per_cta = (n_groups + gridDim.x - 1) / gridDim.x;
+  const int64_t r_begin = (int64_t)blockIdx.x * g_per_cta * kFlush, r_end = min(n_rounds, r_begin + g_per_cta * kFlush);
   uint32_t phase = 0;
   const uint32_t s_local = (uint32_t)warp * 4 + (uint32_t)(lane & 3);
   const uint32_t soff = (s_local >> 2) * kPanelBytes + (s_local & 3) * 4;
   const int q = lane >> 2;
+  // this warp's share of the 128 x 128 result in tensor memory: lane quarter (warp & 3), column half (warp >> 2)
+  const uint32_t my_tmem = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(warp >> 2) * 64;
 
   float p2[kHidden / 8], p1[kHidden / 8], pd[3];     // prefetched h2 / h1 values and dz3 of my row for the coming round
   auto prefetch = [&](int64_t rd) {
@@ -1485,17 +1523,45 @@ __global__ void __launch_bounds__(dw::kThreadsDW, dw::kCtasPerSM) k_shade_dw2_tc
       p1[jj] = live ? __ldg(h1 + idx) : 0.f;
     }
   };
+  // fold the finished chain (MMA accumulator) into the running sum; `first`: the sum block is still uninitialised
+  auto fold = [&](bool first) {
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {           // 16-column pieces keep the transient register footprint small
+      float v[16], sum[16];
+      tmem_ld16(my_tmem + cAcc + c * 16, v);
+      if (!first) {
+        tmem_ld16(my_tmem + cSum + c * 16, sum);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) v[e] = __fadd_rn(sum[e], v[e]);
+      }
+      tmem_st16(my_tmem + cSum + c * 16, v);
+    }
+    tmem_st_wait();
+  };
   if (r_begin < r_end) prefetch(r_begin);
   bool pending = false;
+  int n_folded = 0;
   for (int64_t rd = r_begin; rd < r_end; ++rd) {
+    const int i = (int)(rd - r_begin);
     float c2[kHidden / 8], c1[kHidden / 8];
 #pragma unroll
     for (int jj = 0; jj < kHidden / 8; ++jj) { c2[jj] = p2[jj]; c1[jj] = p1[jj]; }
     const float d0 = pd[0], d1 = pd[1], d2 = pd[2];
     prefetch(rd + 1);                       // loads for the next round fly while this round is staged and multiplied
+    if ((i % kFlush) == 0 && warp == 1 && rd + kFlush < r_end && elect_one()) {     // next tile of both saves -> L2
+      const int64_t r0 = (rd + kFlush) * kK;
+      const uint32_t nr = (uint32_t)min((int64_t)kRows, n_pts - r0);
+      l2_prefetch(h2 + r0 * kHidden, (kPanel ? (uint32_t)kRows : nr) * kHidden * 4);
+      l2_prefetch(h1 + r0 * kHidden, (kPanel ? (uint32_t)kRows : nr) * kHidden * 4);
+    }
     if (pending) {                          // tensor pipe must have finished reading the staging buffer
       mbar_wait(bar_addr, phase);
       phase ^= 1;
+    }
+    if (i > 0 && (i % kFlush) == 0) {       // the chain of the previous kFlush rounds is complete: fold it, restart the accumulator
+      tc_fence_after();
+      fold(n_folded == 0);
+      ++n_folded;
     }
 #pragma unroll
     for (int jj = 0; jj < kHidden / 8; ++jj) {
@@ -1513,12 +1579,13 @@ __global__ void __launch_bounds__(dw::kThreadsDW, dw::kCtasPerSM) k_shade_dw2_tc
     __syncthreads();
     if (warp == 0 && elect_one()) {   // one elected lane of a CONVERGED warp: plain UTCHMMA issue (see elect_one)
       tc_fence_after();
+      const bool fresh = (i % kFlush) == 0;
 #pragma unroll
       for (int ks = 0; ks < (int)(kK / 8); ++ks) {
-        mma_ss(tmem, dAhi + ks * kStepK, dBhi + ks * kStepK, (rd > r_begin || ks > 0) ? 1u : 0u);
+        mma_ss(tmem + cAcc, dAhi + ks * kStepK, dBhi + ks * kStepK, (!fresh || ks > 0) ? 1u : 0u);
         if (kThree) {
-          mma_ss(tmem, dAlo + ks * kStepK, dBhi + ks * kStepK, 1);
-          mma_ss(tmem, dAhi + ks * kStepK, dBlo + ks * kStepK, 1);
+          mma_ss(tmem + cAcc, dAlo + ks * kStepK, dBhi + ks * kStepK, 1);
+          mma_ss(tmem + cAcc, dAhi + ks * kStepK, dBlo + ks * kStepK, 1);
         }
       }
       mma_commit(bar_addr);
@@ -1528,19 +1595,19 @@ __global__ void __launch_bounds__(dw::kThreadsDW, dw::kCtasPerSM) k_shade_dw2_tc
   if (pending) {
     mbar_wait(bar_addr, phase);
     tc_fence_after();
-    if (warp < 4) {                        // warps 0..3 own TMEM lanes 32w..32w+31 = rows j of dW2
+    fold(n_folded == 0);
 #pragma unroll 1
-      for (int c = 0; c < kHidden / 32; ++c) {
-        float v[32];
-        tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c * 32, v);
+    for (int c = 0; c < 2; ++c) {
+      float v[32];
+      tmem_ld32(my_tmem + cSum + c * 32, v);
+      float* dst = gW2 + ((warp & 3) * 32 + lane) * kHidden + (warp >> 2) * 64 + c * 32;
 #pragma unroll
-        for (int e = 0; e < 32; ++e) atomicAdd(gW2 + tid * kHidden + c * 32 + e, v[e]);
-      }
+      for (int e = 0; e < 32; ++e) atomicAdd(dst + e, v[e]);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem) : "memory");
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem) : "memory");
 }
 
 }  // namespace tc
