@@ -273,6 +273,32 @@ def test_fused_rgbnet_vs_torch(mode, monkeypatch):
                 assert_close(a, b, rtol=2e-5, atol=(2e-6 if nm == 'k0' else 1e-5) * scale + 1e-9, what=f'grad {nm} M={M}')
 
 
+def test_backward_scatter_overlap_gives_the_same_gradients():
+    """march.set_backward_overlap(True): the density scatter runs on a side stream under the k0 scatter (joined before backward
+    returns).  Same kernels, same inputs: gradients agree to the atomics' summation order."""
+    from unboundednerfpytorch_b200 import march
+    m, _ = _fresh_model('fouriergrid', 40, 3, 1e-4, 21, dens_mean=4.0, dens_std=3.0)
+    m = m.to(DEV)
+    ro, rd, vd = seeded_rays(900, 5, DEV)
+    rk = dict(near=0., far=1e9, bg=1, rand_bkgd=False, stepsize=0.5, render_depth=True)
+    grads = []
+    try:
+        for on in (False, True, True):
+            march.set_backward_overlap(on)
+            m.zero_grad(set_to_none=True)
+            ret = m(ro, rd, vd, global_step=None, **rk)
+            (ret['rgb_marched'].sum() + ret['depth'].sum() * 1e-2).backward()
+            torch.cuda.synchronize()
+            grads.append({k: p.grad.detach().clone() for k, p in m.named_parameters() if p.grad is not None})
+    finally:
+        march.set_backward_overlap(False)
+    for g in grads[1:]:
+        assert g.keys() == grads[0].keys()
+        for k in g:
+            scale = float(grads[0][k].abs().max()) + 1e-30
+            assert float((g[k] - grads[0][k]).abs().max()) <= 1e-5 * scale, k
+
+
 def test_rgbnet_dw2_long_sample_sum_vs_fp64():
     """dW2 = sum over ALL samples of dZ2^T H1 is a split-K tensor-core GEMM.  tcgen05 adds into its fp32 accumulator with
     truncation, so one accumulator chain per CTA over hundreds of 32-sample rounds carries a bias that grows linearly with the
@@ -472,7 +498,7 @@ def test_feature_kernel_families_agree(flavor, F_, thres):
     rk = dict(near=0., far=1e9, bg=1, rand_bkgd=False, stepsize=0.5, render_depth=True)
     outs, grads = [], []
     try:
-        for variant in (0, 1, 2, 3):
+        for variant in (0, 1, 2, 3, 4, 5):
             ops.set_feature_kernel(variant)
             assert ops.get_feature_kernel() == variant
             m.zero_grad(set_to_none=True)
@@ -481,7 +507,7 @@ def test_feature_kernel_families_agree(flavor, F_, thres):
             outs.append(ret)
             grads.append(m.k0.grid.grad.detach().clone())
     finally:
-        ops.set_feature_kernel(1)
+        ops.set_feature_kernel(3)
     for ret in outs[1:]:
         assert torch.equal(ret['ray_id'], outs[0]['ray_id']) and torch.equal(ret['step_id'], outs[0]['step_id'])
         for k in ('weights', 'raw_density', 't'):
@@ -498,11 +524,11 @@ def test_feature_kernel_families_agree(flavor, F_, thres):
     # (oracle.cpu_ref.fourier_grid_forward on CUDA tensors = FourierGrid_grid.py:60-78 / grid.py:50-61 verbatim)
     from oracle import cpu_ref
     with torch.no_grad():
-        ops.set_feature_kernel(1)
+        ops.set_feature_kernel(3)
         try:
             (w, last, alpha, dens, k0, ray_id, step_id, t, inner), _ = m._march(ro, rd, 0.5)
         finally:
-            ops.set_feature_kernel(1)
+            ops.set_feature_kernel(3)
         pts, _, _ = m._sample_dense(ro, rd, 0.5)
         want = cpu_ref.fourier_grid_forward(m.k0.grid.detach().contiguous(), pts[ray_id, step_id], m.xyz_min, m.xyz_max,
                                             F_ if flavor == 'fouriergrid' else 0)

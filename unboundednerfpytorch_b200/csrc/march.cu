@@ -29,6 +29,8 @@ __device__ __forceinline__ float grid_density(const GridView& g, float x, float 
 // ------------------------------------------------------------------------------------------------
 // pass A forward
 // ------------------------------------------------------------------------------------------------
+// kP > 0: compile-time slab count + contiguous single-channel grid -> grid_density_fast (march_common.cuh); kP = 0: generic layout
+template <int kP>
 __global__ void __launch_bounds__(32 * kMarchWarps) k_march_density_fwd(
     const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float* __restrict__ t_table,
     GridView g, const uint8_t* __restrict__ mask_world, MarchParams p, int64_t n_rays,
@@ -91,7 +93,7 @@ __global__ void __launch_bounds__(32 * kMarchWarps) k_march_density_fwd(
 
     float dens = 0.f, alpha = 0.f;
     if (queried) {
-      dens = grid_density(g, x, y, z);
+      dens = kP > 0 ? grid_density_fast<(kP > 0 ? kP : 1)>(g, x, y, z) : grid_density(g, x, y, z);
       const float e = expf(dens + p.shift);
       alpha = 1 - powf(1 + e, -p.interval);
     }
@@ -236,6 +238,7 @@ __global__ void __launch_bounds__(32 * kMarchWarps) k_march_feature(
 // ------------------------------------------------------------------------------------------------
 constexpr int kMaxChunks = 128;   // S <= 4096
 
+template <int kP>
 __global__ void __launch_bounds__(32 * kMarchWarps) k_march_density_bwd(
     const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float* __restrict__ t_table,
     GridView g /* data = grad grid */, MarchParams p, int64_t n_rays, const float* __restrict__ density,
@@ -317,6 +320,10 @@ __global__ void __launch_bounds__(32 * kMarchWarps) k_march_density_bwd(
     const float ny = norm_coord(y, g.mn[1], g.len[1]);
     const float nz = norm_coord(z, g.mn[2], g.len[2]);
     gd = slab_mean_scale(gd, g.P);
+    if (kP > 0) {
+      grid_density_scatter_fast<(kP > 0 ? kP : 1)>(grad_grid, g, nx, ny, nz, gd);
+      continue;
+    }
     for (int sl = 0; sl < g.P; ++sl) {
       const float cx = src_index(fourier_gamma(sl, nx), g.X);
       const float cy = src_index(fourier_gamma(sl, ny), g.Y);
@@ -325,6 +332,16 @@ __global__ void __launch_bounds__(32 * kMarchWarps) k_march_density_bwd(
       else trilerp1_scatter(grad_grid + sl * g.sp, g.sv, g.X, g.Y, g.Z, cx, cy, cz, gd);
     }
   }
+}
+
+// the fast density paths need: contiguous single channel, >= 2 voxels per axis, 32-bit offsets inside a slab, and an 8-byte aligned
+// buffer (the pair reductions align on the ADDRESS, so odd-sized slabs -- 153^3 -- are fine: the +0 half of a pair may fall on the
+// last voxel of the previous slab, never before the buffer)
+static int density_fast_slabs(const GridView& g) {
+  const bool ok = g.sv == 1 && g.X >= 2 && g.Y >= 2 && g.Z >= 2 && (int64_t)g.X * g.Y * g.Z < (1ll << 31) &&
+                  ((uintptr_t)g.data & 7) == 0;
+  if (!ok) return 0;
+  return (g.P == 1 || g.P == 3 || g.P == 5 || g.P == 7 || g.P == 9) ? g.P : 0;
 }
 
 // second-generation feature kernels (march_feature.cu); -1 = configuration not covered, use the generic kernel
@@ -349,7 +366,7 @@ using namespace ubn;
 extern "C" {
 
 int ubn_set_feature_kernel(int variant) {
-  if (variant < 0 || variant > 3) return finish(cudaErrorInvalidValue);
+  if (variant < 0 || variant > 5) return finish(cudaErrorInvalidValue);
   set_feature_kernel(variant);
   return 0;
 }
@@ -364,8 +381,18 @@ int ubn_march_density_fwd(const float* rays_o, const float* rays_d, const float*
   if (g.C != 1) return finish(cudaErrorInvalidValue);
   const MarchParams p = make_params(cfg);
   if (p.use_mask && !mask_world) return finish(cudaErrorInvalidValue);
-  k_march_density_fwd<<<blocks_for(n_rays, kMarchWarps), 32 * kMarchWarps, 0, as_stream(stream)>>>(
-      rays_o, rays_d, t_table, g, mask_world, p, n_rays, density, alpha, weight, T, flags, alphainv_last, n_keep);
+#define UBN_DFWD(P)                                                                                              \
+  k_march_density_fwd<P><<<blocks_for(n_rays, kMarchWarps), 32 * kMarchWarps, 0, as_stream(stream)>>>(           \
+      rays_o, rays_d, t_table, g, mask_world, p, n_rays, density, alpha, weight, T, flags, alphainv_last, n_keep)
+  switch (density_fast_slabs(g)) {
+    case 1: UBN_DFWD(1); break;
+    case 3: UBN_DFWD(3); break;
+    case 5: UBN_DFWD(5); break;
+    case 7: UBN_DFWD(7); break;
+    case 9: UBN_DFWD(9); break;
+    default: UBN_DFWD(0); break;
+  }
+#undef UBN_DFWD
   UBN_LAUNCH_CHECK();
   return 0;
 }
@@ -425,9 +452,19 @@ int ubn_march_density_bwd(const float* rays_o, const float* rays_d, const float*
   if (g.C != 1) return finish(cudaErrorInvalidValue);
   const MarchParams p = make_params(cfg);
   if (p.S > 32 * kMaxChunks) return finish(cudaErrorInvalidValue);
-  k_march_density_bwd<<<blocks_for(n_rays, kMarchWarps), 32 * kMarchWarps, 0, as_stream(stream)>>>(
-      rays_o, rays_d, t_table, g, p, n_rays, density, alpha, weight, T, flags, alphainv_last, offsets, g_weight,
-      g_alpha, g_density, g_last, grad_density_grid);
+#define UBN_DBWD(P)                                                                                              \
+  k_march_density_bwd<P><<<blocks_for(n_rays, kMarchWarps), 32 * kMarchWarps, 0, as_stream(stream)>>>(           \
+      rays_o, rays_d, t_table, g, p, n_rays, density, alpha, weight, T, flags, alphainv_last, offsets, g_weight,  \
+      g_alpha, g_density, g_last, grad_density_grid)
+  switch (density_fast_slabs(g)) {
+    case 1: UBN_DBWD(1); break;
+    case 3: UBN_DBWD(3); break;
+    case 5: UBN_DBWD(5); break;
+    case 7: UBN_DBWD(7); break;
+    case 9: UBN_DBWD(9); break;
+    default: UBN_DBWD(0); break;
+  }
+#undef UBN_DBWD
   UBN_LAUNCH_CHECK();
   return 0;
 }

@@ -16,21 +16,6 @@
 
 namespace ubn {
 
-struct CellR {
-  int v;            // base voxel index  (x0*Y + y0)*Z + z0, pre-clamped
-  float fx, fy, fz; // fractions in [0,1]
-};
-
-__device__ __forceinline__ CellR make_cell(float cx, float cy, float cz, int X, int Y, int Z) {
-  CellR c;
-  const float x0 = fminf(fmaxf(floorf(cx), 0.f), (float)(X - 2));
-  const float y0 = fminf(fmaxf(floorf(cy), 0.f), (float)(Y - 2));
-  const float z0 = fminf(fmaxf(floorf(cz), 0.f), (float)(Z - 2));
-  c.fx = cx - x0; c.fy = cy - y0; c.fz = cz - z0;
-  c.v = ((int)x0 * Y + (int)y0) * Z + (int)z0;
-  return c;
-}
-
 template <int kP, bool kBackward, int kGroup>
 __global__ void __launch_bounds__(32 * kMarchWarps, (kGroup <= 1 ? 8 : (kGroup <= 2 ? 6 : (kGroup <= 4 ? 4 : 5)))) k_march_feature_v2(
     const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float* __restrict__ t_table,
@@ -372,9 +357,14 @@ template <int kP, int kGroup>
 __global__ void __launch_bounds__(32 * kMarchWarps, 6) k_march_feature_bwd_slab(
     const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float* __restrict__ t_table,
     GridView g, MarchParams p, int64_t n_rays, const uint8_t* __restrict__ flags,
-    const int64_t* __restrict__ offsets, const float* __restrict__ gfeat, float* __restrict__ grad_grid) {
+    const int64_t* __restrict__ offsets, const float* __restrict__ gfeat, float* __restrict__ grad_grid, int n_split) {
+  // n_split > 1: every slab is swept n_split times, pass `part` scattering only the samples whose cell starts in the part-th
+  // x-range of the slab, so the live gradient footprint is 1 / n_split of a slab (86 MB for two parts of a 153^3 x 12 slab:
+  // inside the 126 MB L2) at the price of repeating the chunk preamble
   const int lane = threadIdx.x & 31;
-  const int sl = blockIdx.y;
+  const int sl = blockIdx.y / n_split, part = blockIdx.y - sl * n_split;
+  const int v_lo = (int)(((int64_t)(g.X - 1) * part) / n_split) * g.Y * g.Z;
+  const int v_hi = (part + 1 == n_split) ? 0x7fffffff : (int)(((int64_t)(g.X - 1) * (part + 1)) / n_split) * g.Y * g.Z;
   const int64_t ray = (int64_t)blockIdx.x * kMarchWarps + (threadIdx.x >> 5);
   if (ray >= n_rays) return;
   int64_t out_base = offsets[ray];
@@ -394,7 +384,6 @@ __global__ void __launch_bounds__(32 * kMarchWarps, 6) k_march_feature_bwd_slab(
     const bool keep = (f & UBN_FLAG_KEEP) != 0;
     const unsigned km = __ballot_sync(0xffffffffu, keep);
     if (km == 0) continue;
-    const int n_here = __popc(km);
     CellR cell;
     {
       float x = 0, y = 0, z = 0;
@@ -405,19 +394,25 @@ __global__ void __launch_bounds__(32 * kMarchWarps, 6) k_march_feature_bwd_slab(
       cell = make_cell(src_index(fourier_gamma(sl, nx), g.X), src_index(fourier_gamma(sl, ny), g.Y),
                        src_index(fourier_gamma(sl, nz), g.Z), g.X, g.Y, g.Z);
     }
-    if (km != 0xffffffffu) {
-      const int src = __fns(km, 0, lane + 1) & 31;
+    // survivors of the chunk that this pass serves; `row` = their position in the compacted gradient rows
+    const unsigned sm = __ballot_sync(0xffffffffu, keep && cell.v >= v_lo && cell.v < v_hi);
+    const int n_here = __popc(sm);
+    int row = __popc(km & ((1u << lane) - 1));
+    if (sm != 0xffffffffu) {
+      const int src = __fns(sm, 0, lane + 1) & 31;
       cell.v = __shfl_sync(0xffffffffu, cell.v, src);
       cell.fx = __shfl_sync(0xffffffffu, cell.fx, src);
       cell.fy = __shfl_sync(0xffffffffu, cell.fy, src);
       cell.fz = __shfl_sync(0xffffffffu, cell.fz, src);
+      row = __shfl_sync(0xffffffffu, row, src);
     }
     for (int g0 = 0; g0 < n_here; g0 += kGroup) {
       float4 gin[kGroup];
 #pragma unroll
       for (int j = 0; j < kGroup; ++j) {
         gin[j] = make_float4(0, 0, 0, 0);
-        if (quad_on && g0 + j < n_here) gin[j] = __ldg(reinterpret_cast<const float4*>(gfeat + (out_base + g0 + j) * g.C + quad * 4));
+        const int rj = __shfl_sync(0xffffffffu, row, (g0 + j) & 31);
+        if (quad_on && g0 + j < n_here) gin[j] = __ldg(reinterpret_cast<const float4*>(gfeat + (out_base + rj) * g.C + quad * 4));
       }
 #pragma unroll
       for (int j = 0; j < kGroup; ++j) {
@@ -435,26 +430,30 @@ __global__ void __launch_bounds__(32 * kMarchWarps, 6) k_march_feature_bwd_slab(
         }
       }
     }
-    out_base += n_here;
+    out_base += __popc(km);
   }
 }
 
 template <int kP>
 static int launch_bwd_slab(const float* rays_o, const float* rays_d, const float* t_table, const GridView& g, const MarchParams& p,
                            int64_t n_rays, const uint8_t* flags, const int64_t* offsets, const float* gfeat, float* grad_grid,
-                           cudaStream_t st) {
-  const dim3 grid(blocks_for(n_rays, kMarchWarps), kP);
-  k_march_feature_bwd_slab<kP, 4><<<grid, 32 * kMarchWarps, 0, st>>>(rays_o, rays_d, t_table, g, p, n_rays, flags, offsets, gfeat, grad_grid);
+                           int n_split, cudaStream_t st) {
+  const dim3 grid(blocks_for(n_rays, kMarchWarps), kP * n_split);
+  k_march_feature_bwd_slab<kP, 4><<<grid, 32 * kMarchWarps, 0, st>>>(rays_o, rays_d, t_table, g, p, n_rays, flags, offsets, gfeat, grad_grid,
+                                                                     n_split);
   UBN_LAUNCH_CHECK();
   return 0;
 }
 
-// 0 = warp-cooperative kernels (v2), 1 = lane-per-sample (v3) for the forward (default), 2 = for forward and backward, 3 = lane-per-sample forward + SLAB-MAJOR cooperative
+// 0 = warp-cooperative kernels (v2), 1 = lane-per-sample (v3) for the forward, 2 = for forward and backward, 3 (default) = lane-per-sample forward + SLAB-MAJOR cooperative
 // scatter (k_march_feature_bwd_slab).  Set
 // through ubn_set_feature_kernel (tests exercise every value).  The scatter stays cooperative: one warp instruction issues the 24
 // vector reductions of a sample into 8 x 48 contiguous bytes, whereas lane-per-sample reductions hit 32 unrelated records per
 // instruction and serialise in the L2 atomic units.
-static int g_feature_kernel = 1;     // measured (profiles/, truck 8192 x 512): forward 3.94 ms cooperative -> 1.55 ms lane-per-sample; backward 4.16 vs 7.48 ms
+// Measured on the truck workload (8192 x 512, 9 slabs; profiles/README.md): forward 3.94 ms cooperative -> 1.55 ms lane-per-sample;
+// backward 4.20 ms cooperative, 7.48 ms lane-per-sample, 3.76 ms slab-major (4.40 / 5.34 ms with each slab swept in 2 / 4 x-ranges:
+// the repeated preamble costs more than the L2 hits return).  Default: lane-per-sample forward + slab-major scatter.
+static int g_feature_kernel = 3;
 void set_feature_kernel(int v) { g_feature_kernel = v; }
 int get_feature_kernel() { return g_feature_kernel; }
 
@@ -466,16 +465,17 @@ int march_feature_v2(bool backward, const float* rays_o, const float* rays_d, co
                      uint8_t* o_inner, cudaStream_t st) {
   if (g.X < 2 || g.Y < 2 || g.Z < 2) return -1;
   if ((int64_t)g.X * g.Y * g.Z * g.C >= (1ll << 31)) return -1;   // 32-bit voxel offsets inside a slab
-  if (backward && g_feature_kernel == 3 && g.P > 1) {
+  if (backward && g_feature_kernel >= 3 && g.P > 1) {     // 3 / 4 / 5: slab-major scatter, each slab swept in 1 / 2 / 4 x-ranges
+    const int n_split = 1 << (g_feature_kernel - 3);
     switch (g.P) {
-      case 3: return launch_bwd_slab<3>(rays_o, rays_d, t_table, g, p, n_rays, flags, offsets, feat, grad_grid, st);
-      case 5: return launch_bwd_slab<5>(rays_o, rays_d, t_table, g, p, n_rays, flags, offsets, feat, grad_grid, st);
-      case 7: return launch_bwd_slab<7>(rays_o, rays_d, t_table, g, p, n_rays, flags, offsets, feat, grad_grid, st);
-      case 9: return launch_bwd_slab<9>(rays_o, rays_d, t_table, g, p, n_rays, flags, offsets, feat, grad_grid, st);
+      case 3: return launch_bwd_slab<3>(rays_o, rays_d, t_table, g, p, n_rays, flags, offsets, feat, grad_grid, n_split, st);
+      case 5: return launch_bwd_slab<5>(rays_o, rays_d, t_table, g, p, n_rays, flags, offsets, feat, grad_grid, n_split, st);
+      case 7: return launch_bwd_slab<7>(rays_o, rays_d, t_table, g, p, n_rays, flags, offsets, feat, grad_grid, n_split, st);
+      case 9: return launch_bwd_slab<9>(rays_o, rays_d, t_table, g, p, n_rays, flags, offsets, feat, grad_grid, n_split, st);
       default: break;
     }
   }
-  if (g.C == 12 && (g_feature_kernel == 2 || ((g_feature_kernel == 1 || g_feature_kernel == 3) && !backward))) {
+  if (g.C == 12 && (g_feature_kernel == 2 || ((g_feature_kernel == 1 || g_feature_kernel >= 3) && !backward))) {
 #define UBN_V3(P)                                                                                                               \
   case P:                                                                                                                       \
     return launch_v3<P>(backward, rays_o, rays_d, t_table, g, p, n_rays, flags, offsets, density, alpha, weight, feat, grad_grid, \
