@@ -402,7 +402,6 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference', 'reference-gpu'])
     ap.add_argument('--workload', default='truck', choices=['truck', 'bicycle', 'garden', 'missionbay'])
     ap.add_argument('--cpu-rays', type=int, default=1024, help='upper bound of the ray sample of the CPU legs (shrunk to fit the time budget)')
-    ap.add_argument('--bwd-overlap', type=int, default=None, choices=[0, 1], help='density scatter on a side stream under the k0 scatter (A/B)')
     ap.add_argument('--feature-kernel', type=int, default=None, choices=[0, 1, 2, 3, 4, 5],
                     help='A/B: pass-B kernel family (0 warp-cooperative, 1 lane-per-sample forward, 2 forward + backward); default = library default')
     ap.add_argument('--tma', action='store_true', help='A/B (render workloads): TMA-staged brick feature read instead of the gather kernel')
@@ -484,9 +483,6 @@ def main():
     from unboundednerfpytorch_b200.functional import render_loss
     from unboundednerfpytorch_b200.masked_adam import create_optimizer_or_freeze_model
     _cabi.load()
-    if args.bwd_overlap is not None:
-        from unboundednerfpytorch_b200 import march as _march
-        _march.set_backward_overlap(bool(args.bwd_overlap))
     if args.feature_kernel is not None:
         from unboundednerfpytorch_b200 import ops as _ops
         _ops.set_feature_kernel(args.feature_kernel)

@@ -396,11 +396,14 @@ int ubn_rgbnet_bwd_small(const float* feat, const int64_t* ray_id, const float* 
  * Replaces ubn_rgbnet_bwd_tc_data + ubn_rgbnet_bwd_small (which round-tripped dZ1 [n_pts,128] through HBM and re-read H2).
  * single_pass bit 0: one TF32 pass per product instead of the 3-pass split (the opt-in reduced-precision training mode);
  * bit 1: launch 1 without warp specialisation (4 warps do the tensor-core chain AND the sample reductions; A/B);
- * bit 2: h1_save / h2_save are in the panel layout of ubn_rgbnet_fwd_tc (not combinable with bit 1: cudaErrorInvalidValue). */
+ * bit 2: h1_save / h2_save are in the panel layout of ubn_rgbnet_fwd_tc (not combinable with bit 1: cudaErrorInvalidValue).
+ * h2_mask_scratch: NULL, or ceil(n_pts/128)*512 uint32 of scratch.  With bit 2 set and a scratch given, launch 1 leaves the ReLU
+ * masks of H2 there ([tile][32-unit chunk][row], bit = unit) and launch 2 rebuilds dZ2 from them (dz3 . W3 gated by the mask)
+ * instead of reading h2_save a second time. */
 int ubn_rgbnet_bwd_tc_fused(const float* feat, const int64_t* ray_id, const float* W1k, const float* W2, const float* W3,
                             const float* rgb, const float* h1_save, const float* h2_save, const float* grad_rgb, int64_t n_pts,
                             float* grad_feat, float* grad_view_bias, float* grad_W1k, float* grad_W2, float* grad_b2,
-                            float* grad_W3, float* grad_b3, int single_pass, void* stream);
+                            float* grad_W3, float* grad_b3, uint32_t* h2_mask_scratch, int single_pass, void* stream);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

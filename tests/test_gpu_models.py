@@ -221,12 +221,13 @@ def test_training_step_reduces_loss():
     assert all(torch.isfinite(p).all() for p in student.parameters())
 
 
-@pytest.mark.parametrize('mode', ['simt', 'tc3', 'tc3w4', 'tc1', 'tc3+tcbwd', 'tc3+fused', 'tc3+fused4', 'tc1+fused'])
+@pytest.mark.parametrize('mode', ['simt', 'tc3', 'tc3w4', 'tc1', 'tc3+tcbwd', 'tc3+fused', 'tc3+fusedh2', 'tc3+fused4', 'tc1+fused'])
 def test_fused_rgbnet_vs_torch(mode, monkeypatch):
     """csrc/shade.cu (fp32 FFMA) and csrc/shade_tc.cu (tcgen05: 3xTF32 fp32-grade, single-pass TF32 preview) vs the torch
     nn.Sequential they replace: forward and every gradient."""
     from unboundednerfpytorch_b200 import models, shade as shade_mod
-    monkeypatch.setattr(shade_mod, 'BWD_MODE', {'tcbwd': 'tc3', 'fused': 'fused', 'fused4': 'fused4'}.get(mode.split('+')[-1], 'simt'))
+    monkeypatch.setattr(shade_mod, 'BWD_MODE', {'tcbwd': 'tc3', 'fused': 'fused', 'fusedh2': 'fused', 'fused4': 'fused4'}.get(mode.split('+')[-1], 'simt'))
+    monkeypatch.setattr(shade_mod, 'DW2_FROM_MASKS', not mode.endswith('fusedh2'))      # 'fusedh2': the dW2 launch re-reads H2 (A/B of the mask rebuild)
     mode = mode.split('+')[0]
     monkeypatch.setattr(shade_mod, 'MODE', mode)
     fwd_tol = dict(rtol=1e-5, atol=1e-6) if mode != 'tc1' else dict(rtol=5e-3, atol=5e-3)
@@ -271,32 +272,6 @@ def test_fused_rgbnet_vs_torch(mode, monkeypatch):
                 # parameter gradients are fp32 sums over M samples whose partial sums reach `scale`: two summation orders differ
                 # by a few ulp(scale) * sqrt(#adds) -- judged at the north-star 1e-5 of the largest element; k0 is per sample
                 assert_close(a, b, rtol=2e-5, atol=(2e-6 if nm == 'k0' else 1e-5) * scale + 1e-9, what=f'grad {nm} M={M}')
-
-
-def test_backward_scatter_overlap_gives_the_same_gradients():
-    """march.set_backward_overlap(True): the density scatter runs on a side stream under the k0 scatter (joined before backward
-    returns).  Same kernels, same inputs: gradients agree to the atomics' summation order."""
-    from unboundednerfpytorch_b200 import march
-    m, _ = _fresh_model('fouriergrid', 40, 3, 1e-4, 21, dens_mean=4.0, dens_std=3.0)
-    m = m.to(DEV)
-    ro, rd, vd = seeded_rays(900, 5, DEV)
-    rk = dict(near=0., far=1e9, bg=1, rand_bkgd=False, stepsize=0.5, render_depth=True)
-    grads = []
-    try:
-        for on in (False, True, True):
-            march.set_backward_overlap(on)
-            m.zero_grad(set_to_none=True)
-            ret = m(ro, rd, vd, global_step=None, **rk)
-            (ret['rgb_marched'].sum() + ret['depth'].sum() * 1e-2).backward()
-            torch.cuda.synchronize()
-            grads.append({k: p.grad.detach().clone() for k, p in m.named_parameters() if p.grad is not None})
-    finally:
-        march.set_backward_overlap(False)
-    for g in grads[1:]:
-        assert g.keys() == grads[0].keys()
-        for k in g:
-            scale = float(grads[0][k].abs().max()) + 1e-30
-            assert float((g[k] - grads[0][k]).abs().max()) <= 1e-5 * scale, k
 
 
 def test_rgbnet_dw2_long_sample_sum_vs_fp64():

@@ -1056,7 +1056,7 @@ __global__ void __launch_bounds__(2 * kRows, 1) k_shade_bwd_fused_ws(
     const float* __restrict__ W2, const float* __restrict__ W3, const float* __restrict__ rgb,
     const float* __restrict__ h1, const float* __restrict__ h2, const float* __restrict__ g_rgb, int64_t n_pts,
     float* __restrict__ g_feat, float* __restrict__ g_vb, float* __restrict__ gW1k, float* __restrict__ gb2,
-    float* __restrict__ gW3, float* __restrict__ gb3) {
+    float* __restrict__ gW3, float* __restrict__ gb3, uint32_t* __restrict__ h2_mask) {
   using namespace bf2;
   using bf::cAhi; using bf::cAlo; using bf::cDHf; using bf::cDX; using bf::kIdescN16; using bf::kPanelN16;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -1342,14 +1342,20 @@ __global__ void __launch_bounds__(2 * kRows, 1) k_shade_bwd_fused_ws(
         const int j = c * 32 + lane;
         const float w3a = sW3[j], w3b = sW3[kHidden + j], w3c = sW3[2 * kHidden + j];
         float a0 = accW3[c][0], a1 = accW3[c][1], a2 = accW3[c][2], ab = accB2[c];
+        uint32_t my_mask = 0;                               // lane s: bit j = [H2[s][32 c + j] > 0]
 #pragma unroll 8
         for (int sidx = 0; sidx < 32; ++sidx) {
           const float h = stg[sidx * kStgStride + lane];
           const float4 dz = sDz3[rw * 32 + sidx];
           a0 = fmaf(dz.x, h, a0); a1 = fmaf(dz.y, h, a1); a2 = fmaf(dz.z, h, a2);
           ab += h > 0.f ? fmaf(dz.z, w3c, fmaf(dz.y, w3b, dz.x * w3a)) : 0.f;
+          const uint32_t b = __ballot_sync(0xffffffffu, h > 0.f);      // the ReLU mask of sample sidx over this chunk's 32 units
+          if (lane == sidx) my_mask = b;
         }
         release();
+        // ReLU masks of H2 for the dW2 kernel, [tile][chunk][row] (one 128-byte store per warp and chunk): with them dW2 rebuilds
+        // dZ2 from dz3 and W3 without reading the 2.1 GB of H2 a second time
+        if (h2_mask) h2_mask[tile * 512 + c * 128 + rw * 32 + lane] = my_mask;
         WS_T(16 + c);
         accW3[c][0] = a0; accW3[c][1] = a1; accW3[c][2] = a2; accB2[c] = ab;
       }
@@ -1610,6 +1616,193 @@ __global__ void __launch_bounds__(dw::kThreadsDW, dw::kCtasPerSM) k_shade_dw2_tc
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem) : "memory");
 }
 
+// ---- dW2 from the ReLU masks: the default second launch of the fused backward (panel-layout saves) -----------------------
+// Same GEMM, same chains and running sum as k_shade_dw2_tc, different staging.  That kernel re-reads both activation saves
+// (4.3 GB) and transposes them into the K-major operand panels with 4-byte loads and 4-byte shared-memory stores: 144 load/store
+// instructions per thread and 32-sample round, the load/store pipe at 68 % (ncu) with the tensor pipe at 25 %.  Here
+//   * dZ2 is REBUILT instead of loaded: dZ2[s][j] = [H2[s][j] > 0] (dz3[s] . W3[:, j]).  The masks come from the first launch
+//     (the column warps of k_shade_bwd_fused_ws ballot them while they reduce H2: 2 KB per 128-sample tile instead of 64 KB);
+//     dz3 of a thread's four samples from 96 bytes of rgb / grad_rgb; the W3 columns live in registers;
+//   * a thread owns (hidden unit j, four consecutive samples): the four K-slots of one operand row are ONE 16-byte shared-memory
+//     store, a warp's 32 rows are 512 contiguous bytes (conflict free), and H1 is fetched as 4-byte words of four adjacent rows.
+// Per thread and round: 26 loads + 3 broadcast-free register rebuilds + 16 STS.128, i.e. 3.4x fewer load/store instructions, and
+// H2 is not read at all.
+template <bool kThree>
+__global__ void __launch_bounds__(dw::kThreadsDW, dw::kCtasPerSM) k_shade_dw2_mask_tc(
+    const float* __restrict__ W3, const float* __restrict__ rgb, const float* __restrict__ h1,
+    const uint32_t* __restrict__ h2_mask, const float* __restrict__ g_rgb, int64_t n_pts, float* __restrict__ gW2) {
+  using namespace dw;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + oBarD);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + oBarD + 8);
+  const uint32_t bar_addr = smem_u32(bar);
+  if (tid == 0) {
+    mbar_init(bar_addr, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  constexpr uint64_t kStepK = (uint64_t)((2 * kPanelBytes) >> 4);
+  const uint64_t dAhi = make_desc(smem_u32(smem)), dAlo = make_desc(smem_u32(smem + kOpBytes));
+  const uint64_t dBhi = make_desc(smem_u32(smem + 2 * kOpBytes)), dBlo = make_desc(smem_u32(smem + 3 * kOpBytes));
+
+  const int64_t n_rounds = (n_pts + kK - 1) / kK;
+  const int64_t n_groups = (n_rounds + kFlush - 1) / kFlush;
+  const int64_t g_per_cta = (n_groups + gridDim.x - 1) / gridDim.x;
+  const int64_t r_begin = (int64_t)blockIdx.x * g_per_cta * kFlush, r_end = min(n_rounds, r_begin + g_per_cta * kFlush);
+  uint32_t phase = 0;
+  const uint32_t my_tmem = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(warp >> 2) * 64;
+  // warp = sample quad of the round (samples 4 warp .. 4 warp + 3 = the four K slots of panel `warp`), lane -> units j = 32 i + lane
+  float w3a[4], w3b[4], w3c[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    w3a[i] = W3[32 * i + lane]; w3b[i] = W3[kHidden + 32 * i + lane]; w3c[i] = W3[2 * kHidden + 32 * i + lane];
+  }
+  const uint32_t row_off = (uint32_t)warp * kPanelBytes + (uint32_t)lane * 16;      // + i * 512: operand row j = 32 i + lane
+
+  uint4 pm[4];                 // masks of my four samples, chunk i
+  float ph[4][4];              // H1[s0 + t][32 i + lane]
+  float4 po[3], pg[3];         // rgb / grad_rgb of my four samples (12 floats each)
+  auto prefetch = [&](int64_t rd) {
+    const bool on = rd < r_end;
+    const int64_t tile = rd >> 2;
+    const int r_in = (int)(rd & 3) * 32 + warp * 4;                 // first of my four rows inside the tile
+    const int64_t row0 = rd * kK + warp * 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      pm[i] = make_uint4(0, 0, 0, 0);
+      if (on) pm[i] = __ldg(reinterpret_cast<const uint4*>(h2_mask + tile * 512 + i * 128 + r_in));
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+        ph[i][t] = on ? __ldg(h1 + tile * (int64_t)(kRows * kHidden) + (int64_t)(8 * i + (lane >> 2)) * (kRows * 4) + (r_in + t) * 4 + (lane & 3))
+                      : 0.f;
+    }
+    if (on && row0 + 4 <= n_pts) {
+      const float4* o = reinterpret_cast<const float4*>(rgb + row0 * 3);
+      const float4* g = reinterpret_cast<const float4*>(g_rgb + row0 * 3);
+      po[0] = __ldg(o); po[1] = __ldg(o + 1); po[2] = __ldg(o + 2);
+      pg[0] = __ldg(g); pg[1] = __ldg(g + 1); pg[2] = __ldg(g + 2);
+    } else {
+      float fo[12], fg[12];
+#pragma unroll
+      for (int e = 0; e < 12; ++e) {
+        const bool ok = on && row0 * 3 + e < n_pts * 3;
+        fo[e] = ok ? rgb[row0 * 3 + e] : 0.f;
+        fg[e] = ok ? g_rgb[row0 * 3 + e] : 0.f;
+      }
+      po[0] = make_float4(fo[0], fo[1], fo[2], fo[3]); po[1] = make_float4(fo[4], fo[5], fo[6], fo[7]); po[2] = make_float4(fo[8], fo[9], fo[10], fo[11]);
+      pg[0] = make_float4(fg[0], fg[1], fg[2], fg[3]); pg[1] = make_float4(fg[4], fg[5], fg[6], fg[7]); pg[2] = make_float4(fg[8], fg[9], fg[10], fg[11]);
+    }
+  };
+  auto fold = [&](bool first) {
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      float v[16], sum[16];
+      tmem_ld16(my_tmem + cAcc + c * 16, v);
+      if (!first) {
+        tmem_ld16(my_tmem + cSum + c * 16, sum);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) v[e] = __fadd_rn(sum[e], v[e]);
+      }
+      tmem_st16(my_tmem + cSum + c * 16, v);
+    }
+    tmem_st_wait();
+  };
+  if (r_begin < r_end) prefetch(r_begin);
+  bool pending = false;
+  int n_folded = 0;
+  for (int64_t rd = r_begin; rd < r_end; ++rd) {
+    const int i_rd = (int)(rd - r_begin);
+    // dz3 of my four samples (sigmoid' folded in), in the summation order of the other kernels
+    float d0[4], d1[4], d2[4];
+    {
+      const float fo[12] = {po[0].x, po[0].y, po[0].z, po[0].w, po[1].x, po[1].y, po[1].z, po[1].w, po[2].x, po[2].y, po[2].z, po[2].w};
+      const float fg[12] = {pg[0].x, pg[0].y, pg[0].z, pg[0].w, pg[1].x, pg[1].y, pg[1].z, pg[1].w, pg[2].x, pg[2].y, pg[2].z, pg[2].w};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        d0[t] = fg[3 * t] * (fo[3 * t] * (1.f - fo[3 * t]));
+        d1[t] = fg[3 * t + 1] * (fo[3 * t + 1] * (1.f - fo[3 * t + 1]));
+        d2[t] = fg[3 * t + 2] * (fo[3 * t + 2] * (1.f - fo[3 * t + 2]));
+      }
+    }
+    if ((i_rd % kFlush) == 0 && warp == 1 && rd + kFlush < r_end && elect_one())     // next tile of H1 -> L2
+      l2_prefetch(h1 + (rd + kFlush) * (int64_t)(kK * kHidden), (uint32_t)kRows * kHidden * 4);
+    if (pending) {                          // tensor pipe must have finished reading the staging buffer
+      mbar_wait(bar_addr, phase);
+      phase ^= 1;
+    }
+    if (i_rd > 0 && (i_rd % kFlush) == 0) { // the chain of the previous kFlush rounds is complete: fold it, restart the accumulator
+      tc_fence_after();
+      fold(n_folded == 0);
+      ++n_folded;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t mw[4] = {pm[i].x, pm[i].y, pm[i].z, pm[i].w};
+      uint4 zh, hh;
+      float4 zl, hl;
+      uint32_t* zhp = &zh.x; uint32_t* hhp = &hh.x; float* zlp = &zl.x; float* hlp = &hl.x;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float z = ((mw[t] >> lane) & 1u) ? fmaf(d2[t], w3c[i], fmaf(d1[t], w3b[i], d0[t] * w3a[i])) : 0.f;
+        zhp[t] = tf32_hi_bits(z);
+        zlp[t] = z - __uint_as_float(zhp[t]);
+        hhp[t] = tf32_hi_bits(ph[i][t]);
+        hlp[t] = ph[i][t] - __uint_as_float(hhp[t]);
+      }
+      const uint32_t off = row_off + (uint32_t)i * 512;
+      *reinterpret_cast<uint4*>(smem + off) = zh;
+      *reinterpret_cast<float4*>(smem + kOpBytes + off) = zl;
+      *reinterpret_cast<uint4*>(smem + 2 * kOpBytes + off) = hh;
+      *reinterpret_cast<float4*>(smem + 3 * kOpBytes + off) = hl;
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0 && elect_one()) {   // one elected lane of a CONVERGED warp: plain UTCHMMA issue (see elect_one)
+      tc_fence_after();
+      const bool fresh = (i_rd % kFlush) == 0;
+#pragma unroll
+      for (int ks = 0; ks < (int)(kK / 8); ++ks) {
+        mma_ss(tmem + cAcc, dAhi + ks * kStepK, dBhi + ks * kStepK, (!fresh || ks > 0) ? 1u : 0u);
+        if (kThree) {
+          mma_ss(tmem + cAcc, dAlo + ks * kStepK, dBhi + ks * kStepK, 1);
+          mma_ss(tmem + cAcc, dAhi + ks * kStepK, dBlo + ks * kStepK, 1);
+        }
+      }
+      mma_commit(bar_addr);
+    }
+    pending = true;
+    // the next round's loads fly while the tensor pipe works on this one (a single register set: issuing them before the staging
+    // would double the live registers past the 128 a two-CTA-per-SM kernel may use)
+    prefetch(rd + 1);
+  }
+  if (pending) {
+    mbar_wait(bar_addr, phase);
+    tc_fence_after();
+    fold(n_folded == 0);
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      float v[32];
+      tmem_ld32(my_tmem + cSum + c * 32, v);
+      float* dst = gW2 + ((warp & 3) * 32 + lane) * kHidden + (warp >> 2) * 64 + c * 32;
+#pragma unroll
+      for (int e = 0; e < 32; ++e) atomicAdd(dst + e, v[e]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem) : "memory");
+}
+
 }  // namespace tc
 }  // namespace ubn
 
@@ -1685,7 +1878,8 @@ extern "C" int ubn_rgbnet_bwd_tc_data(const float* W2, const float* W3, const fl
 extern "C" int ubn_rgbnet_bwd_tc_fused(const float* feat, const int64_t* ray_id, const float* W1k, const float* W2, const float* W3,
                                        const float* rgb, const float* h1_save, const float* h2_save, const float* grad_rgb,
                                        int64_t n_pts, float* grad_feat, float* grad_view_bias, float* grad_W1k, float* grad_W2,
-                                       float* grad_b2, float* grad_W3, float* grad_b3, int single_pass, void* stream) {
+                                       float* grad_b2, float* grad_W3, float* grad_b3, uint32_t* h2_mask_scratch, int single_pass,
+                                       void* stream) {
   if (n_pts <= 0) return 0;
   cudaStream_t st = as_stream(stream);
   {   // dX + every sample reduction except dW2
@@ -1707,7 +1901,8 @@ extern "C" int ubn_rgbnet_bwd_tc_fused(const float* feat, const int64_t* ray_id,
       if (e != cudaSuccess) return finish(e);                                                                                  \
       tc::k_shade_bwd_fused_ws<T, P><<<grid, 2 * tc::kRows, tc::bf2::kSmemBytesF2, st>>>(feat, ray_id, W1k, W2, W3, rgb, h1_save, h2_save, \
                                                                                       grad_rgb, n_pts, grad_feat, grad_view_bias,        \
-                                                                                      grad_W1k, grad_b2, grad_W3, grad_b3);              \
+                                                                                      grad_W1k, grad_b2, grad_W3, grad_b3,               \
+                                                                                      (P) ? h2_mask_scratch : nullptr);                  \
     } while (0)
     const bool one_pass = (single_pass & 1) != 0, plain = (single_pass & 2) != 0, panel = (single_pass & 4) != 0;
     if (plain && panel) return finish(cudaErrorInvalidValue);       // the 4-warp A/B kernel reads row-major saves only
@@ -1728,8 +1923,20 @@ extern "C" int ubn_rgbnet_bwd_tc_fused(const float* feat, const int64_t* ray_id,
       if (e != cudaSuccess) return finish(e);                                                                                  \
       tc::k_shade_dw2_tc<T, P><<<grid, tc::dw::kThreadsDW, tc::dw::kSmemBytesD, st>>>(W3, rgb, h1_save, h2_save, grad_rgb, n_pts, grad_W2); \
     } while (0)
-    if (single_pass & 4) { if (single_pass & 1) UBN_DW(false, true); else UBN_DW(true, true); }
-    else                 { if (single_pass & 1) UBN_DW(false, false); else UBN_DW(true, false); }
+#define UBN_DWM(T)                                                                                                             \
+    do {                                                                                                                       \
+      cudaError_t e = cudaFuncSetAttribute(tc::k_shade_dw2_mask_tc<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,            \
+                                           (int)tc::dw::kSmemBytesD);                                                          \
+      if (e != cudaSuccess) return finish(e);                                                                                  \
+      tc::k_shade_dw2_mask_tc<T><<<grid, tc::dw::kThreadsDW, tc::dw::kSmemBytesD, st>>>(W3, rgb, h1_save, h2_mask_scratch, grad_rgb, n_pts, \
+                                                                                      grad_W2);                                \
+    } while (0)
+    // panel saves + warp-specialised first launch + a mask scratch: dZ2 rebuilt from the ReLU masks (H2 is not read again)
+    const bool from_masks = (single_pass & 4) && !(single_pass & 2) && h2_mask_scratch != nullptr;
+    if (from_masks)           { if (single_pass & 1) UBN_DWM(false); else UBN_DWM(true); }
+    else if (single_pass & 4) { if (single_pass & 1) UBN_DW(false, true); else UBN_DW(true, true); }
+    else                      { if (single_pass & 1) UBN_DW(false, false); else UBN_DW(true, false); }
+#undef UBN_DWM
 #undef UBN_DW
     UBN_LAUNCH_CHECK();
   }

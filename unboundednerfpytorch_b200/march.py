@@ -36,24 +36,6 @@ def t_schedule(world_len, stepsize, bg_len, t_boundary, device):
     return hit
 
 
-# Overlap of the two backward scatters (density grid on a side stream under the k0 scatter).  Process-wide switch, set through
-# set_backward_overlap(); bench.py --bwd-overlap {0,1} measures both, tests/test_gpu_models.py checks equal gradients.
-BACKWARD_OVERLAP = False
-_SIDE_STREAMS = {}
-
-
-def set_backward_overlap(on):
-    global BACKWARD_OVERLAP
-    BACKWARD_OVERLAP = bool(on)
-
-
-def _side_stream(dev):
-    key = torch.device(dev).index if torch.device(dev).index is not None else torch.cuda.current_device()
-    if key not in _SIDE_STREAMS:
-        _SIDE_STREAMS[key] = torch.cuda.Stream(device=key)
-    return _SIDE_STREAMS[key]
-
-
 TMA_STATS = None          # optional torch.int64[2] CUDA tensor: += {blocks served by TMA, blocks served by the fallback} (tests / bench)
 
 
@@ -176,28 +158,16 @@ class March(torch.autograd.Function):
                 grad_d = buf_d if buf_d is not None else torch.empty_strided(*ctx.dmeta, dtype=torch.float32, device=dev).zero_()
             if want_k:
                 grad_k = buf_k if buf_k is not None else torch.empty_strided(*ctx.kmeta, dtype=torch.float32, device=dev).zero_()
-            def density_bwd():
+            if want_k:
+                with _cabi.timed('march_feature_bwd'):
+                    check(lib.ubn_march_feature_bwd(ptr(rays_o), ptr(rays_d), ptr(t_table), ctx.kdesc, ctx.cfg, c_i64(N),
+                                                    ptr(flags), ptr(offsets), ptr(g_feat), ptr(grad_k), stream_of(rays_o)))
+            if want_d:
                 with _cabi.timed('march_density_bwd'):
                     check(lib.ubn_march_density_bwd(ptr(rays_o), ptr(rays_d), ptr(t_table), ctx.ddesc, ctx.cfg, c_i64(N),
                                                     ptr(dens), ptr(alpha), ptr(weight), ptr(T), ptr(flags), ptr(last),
                                                     ptr(offsets), ptr(g_weight), ptr(g_alpha), ptr(g_dens), ptr(g_last),
                                                     ptr(grad_d), stream_of(rays_o)))
-            # the two scatters are independent (different grids, different upstream gradients): with the overlap on, the density
-            # scatter runs on a side stream underneath the k0 scatter, joined before backward returns
-            side = _side_stream(dev) if (want_k and want_d and BACKWARD_OVERLAP) else None
-            if side is not None:
-                cur = torch.cuda.current_stream(dev)
-                side.wait_stream(cur)
-                with torch.cuda.stream(side):
-                    density_bwd()
-            if want_k:
-                with _cabi.timed('march_feature_bwd'):
-                    check(lib.ubn_march_feature_bwd(ptr(rays_o), ptr(rays_d), ptr(t_table), ctx.kdesc, ctx.cfg, c_i64(N),
-                                                    ptr(flags), ptr(offsets), ptr(g_feat), ptr(grad_k), stream_of(rays_o)))
-            if side is not None:
-                cur.wait_stream(side)
-            elif want_d:
-                density_bwd()
         if buf_d is not None:
             ctx.dparam.grad, grad_d = buf_d, None
         if buf_k is not None:

@@ -22,6 +22,8 @@ MODE = os.environ.get('UBN_RGBNET_MODE', 'tc3')
 # intermediate in HBM; 'fused4' = the same without warp specialisation (A/B); 'tc3' = the previous three-launch form (dZ1 round trip + CUDA-core kernel for
 # the small gradients; kept for A/B); 'simt' = fp32 FFMA
 BWD_MODE = os.environ.get('UBN_RGBNET_BWD_MODE', 'fused')
+# dW2 launch of the fused backward: True = rebuild dZ2 from ReLU masks written by the first launch (default), False = re-read H2 (A/B)
+DW2_FROM_MASKS = os.environ.get('UBN_RGBNET_DW2', 'masks') == 'masks'
 
 
 class _ShadeFn(torch.autograd.Function):
@@ -72,10 +74,13 @@ class _ShadeFn(torch.autograd.Function):
         with ops._Guard(feat) as lib:
             bwd_mode = ctx.bwd_mode                      # as chosen in forward (the save layout depends on it)
             if bwd_mode in ('fused', 'fused4'):          # 'fused4': the same kernel without warp specialisation (A/B)
+                # panel saves: launch 1 leaves the ReLU masks of H2 (2 KB per 128-sample tile) in this scratch and the dW2 launch
+                # rebuilds dZ2 from them instead of reading the 512 B/sample of H2 again
+                masks = torch.empty(-(-M // 128) * 512, dtype=torch.int32, device=dev) if (ctx.panel and DW2_FROM_MASKS) else None
                 with _cabi.timed('rgbnet_bwd'):
                     check(lib.ubn_rgbnet_bwd_tc_fused(ptr(feat), ptr(ray_id), ptr(W1k), ptr(W2), ptr(W3), ptr(rgb), ptr(h1), ptr(h2),
                                                       ptr(g_rgb), c_i64(M), ptr(g_feat), ptr(g_vb), ptr(gW1k), ptr(gW2), ptr(gb2),
-                                                      ptr(gW3), ptr(gb3), c_int((1 if MODE == 'tc1' else 0) | (2 if bwd_mode == 'fused4' else 0) | (4 if ctx.panel else 0)),
+                                                      ptr(gW3), ptr(gb3), ptr(masks), c_int((1 if MODE == 'tc1' else 0) | (2 if bwd_mode == 'fused4' else 0) | (4 if ctx.panel else 0)),
                                                       stream_of(feat)))
                 return g_feat, g_vb, None, gW1k, gW2, gb2, gW3, gb3, None
             if bwd_mode == 'tc3':
