@@ -368,10 +368,11 @@ int ubn_rgbnet_fwd(const float* feat, const float* view_bias, const int64_t* ray
  * meets the 1e-5 parity gate); single_pass bit 0: one TF32 pass (~1e-3 relative); bit 1: the 4-warp form of the kernel (A/B);
  * bit 2: h1_save / h2_save are written in the PANEL layout [ceil(n_pts/128)][32 column quads][128 rows][4 floats] -- coalesced
  * for the row-per-thread kernels on both sides -- and must hold ceil(n_pts/128)*128 rows; only ubn_rgbnet_bwd_tc_fused called
- * with the same bit reads that layout. */
+ * with the same bit reads that layout.  h1_mask (bit 2 only; may be NULL): ceil(n_pts/128)*512 uint32 that receive the ReLU masks
+ * of H1, [tile][32-unit chunk][row], bit = unit -- ubn_rgbnet_bwd_tc_fused then gates dH1 with them instead of loading H1 rows. */
 int ubn_rgbnet_fwd_tc(const float* feat, const float* view_bias, const int64_t* ray_id, const float* W1k, const float* W2,
                       const float* b2, const float* W3, const float* b3, int64_t n_pts, float* rgb, float* h1_save,
-                      float* h2_save, int single_pass, void* stream);
+                      float* h2_save, uint32_t* h1_mask, int single_pass, void* stream);
 /* Backward of the above wrt feat (grad_feat[n_pts,12], fully written) and, ACCUMULATED into zero-initialised buffers,
  * view_bias (grad_view_bias[n_rays,128]), W1k, W2, b2, W3, b3.  ray_id must be sorted. */
 int ubn_rgbnet_bwd(const float* feat, const int64_t* ray_id, const float* W1k, const float* W2, const float* W3,
@@ -399,11 +400,13 @@ int ubn_rgbnet_bwd_small(const float* feat, const int64_t* ray_id, const float* 
  * bit 2: h1_save / h2_save are in the panel layout of ubn_rgbnet_fwd_tc (not combinable with bit 1: cudaErrorInvalidValue).
  * h2_mask_scratch: NULL, or ceil(n_pts/128)*512 uint32 of scratch.  With bit 2 set and a scratch given, launch 1 leaves the ReLU
  * masks of H2 there ([tile][32-unit chunk][row], bit = unit) and launch 2 rebuilds dZ2 from them (dz3 . W3 gated by the mask)
- * instead of reading h2_save a second time. */
+ * instead of reading h2_save a second time.  h1_mask: NULL, or the masks ubn_rgbnet_fwd_tc wrote (bit 2 only): launch 1 then reads
+ * 16 bytes per sample instead of the H1 row and fetches the next tile's H2 row half a tile ahead. */
 int ubn_rgbnet_bwd_tc_fused(const float* feat, const int64_t* ray_id, const float* W1k, const float* W2, const float* W3,
                             const float* rgb, const float* h1_save, const float* h2_save, const float* grad_rgb, int64_t n_pts,
                             float* grad_feat, float* grad_view_bias, float* grad_W1k, float* grad_W2, float* grad_b2,
-                            float* grad_W3, float* grad_b3, uint32_t* h2_mask_scratch, int single_pass, void* stream);
+                            float* grad_W3, float* grad_b3, uint32_t* h2_mask_scratch, const uint32_t* h1_mask, int single_pass,
+                            void* stream);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

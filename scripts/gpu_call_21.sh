@@ -1,0 +1,7 @@
+# double-buffered 16-warp dW2 pipeline
+O=gpurun_out/call21; mkdir -p $O
+timeout 900 python -m pytest tests/test_gpu_models.py tests/test_gpu_parity_at_size.py -q --timeout 300 -x -rf > $O/pytest.log 2>&1; echo "pytest rc=$?"; grep -n "^E  \|passed\|failed\|FAILED" $O/pytest.log | cut -c1-300 | head -20
+timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-reference-gpu > $O/bench.json 2> $O/bench.err
+echo "--- bench rc=$?"; python -c "
+import json;d=json.load(open('$O/bench.json'));print(d['ms_per_step'],d['roofline']['all_kernels_ms'],d['fwd_only']['ms_per_step'],d['tail_ms']['value'])"; tail -2 $O/bench.err
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/launches.csv python bench.py --only-timed --steps 1 --warmup 2 --no-reference-gpu > $O/ncu_launch.log 2>&1; grep -E "dw2|fused_ws|fwd_tc" $O/launches.csv | tail -3 | cut -d, -f5,13-15 | cut -c1-60,200-260

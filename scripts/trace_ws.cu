@@ -22,19 +22,22 @@ int main(int argc, char** argv) {
   float *gfeat = (float*)dev(n * 12 * 4), *gvb = (float*)dev(n_rays * 128 * 4), *gW1 = (float*)dev(128 * 12 * 4), *gW2 = (float*)dev(128 * 128 * 4);
   float *gb2 = (float*)dev(128 * 4), *gW3 = (float*)dev(3 * 128 * 4), *gb3 = (float*)dev(16);
   int64_t* ray = (int64_t*)dev(n * 8);
+  uint32_t* masks = (uint32_t*)dev((n / 128) * 512 * 4);
+  uint32_t* masks1 = (uint32_t*)dev((n / 128) * 512 * 4);
+  cudaMemset(masks1, 0x5a, (n / 128) * 512 * 4);
   std::vector<int64_t> hr(n);
   for (int64_t i = 0; i < n; ++i) hr[i] = i / 512;
   cudaMemcpy(ray, hr.data(), n * 8, cudaMemcpyHostToDevice);
   fill(feat, n * 12, -1, 1); fill(W1k, 128 * 12, -.3f, .3f); fill(W2, 128 * 128, -.1f, .1f); fill(W3, 3 * 128, -.1f, .1f);
   fill(rgb, n * 3, .05f, .95f); fill(h1, n * 128, -1, 1); fill(h2, n * 128, -1, 1); fill(g, n * 3, -1, 1);
   for (int rep = 0; rep < 3; ++rep) {
-    int rc = ubn_rgbnet_bwd_tc_fused(feat, ray, W1k, W2, W3, rgb, h1, h2, g, n, gfeat, gvb, gW1, gW2, gb2, gW3, gb3, flags, nullptr);
+    int rc = ubn_rgbnet_bwd_tc_fused(feat, ray, W1k, W2, W3, rgb, h1, h2, g, n, gfeat, gvb, gW1, gW2, gb2, gW3, gb3, masks, masks1, flags, nullptr);
     if (rc) { printf("launch rc=%d\n", rc); return 1; }
     cudaDeviceSynchronize();
   }
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   cudaEventRecord(e0);
-  ubn_rgbnet_bwd_tc_fused(feat, ray, W1k, W2, W3, rgb, h1, h2, g, n, gfeat, gvb, gW1, gW2, gb2, gW3, gb3, flags, nullptr);
+  ubn_rgbnet_bwd_tc_fused(feat, ray, W1k, W2, W3, rgb, h1, h2, g, n, gfeat, gvb, gW1, gW2, gb2, gW3, gb3, masks, masks1, flags, nullptr);
   cudaEventRecord(e1); cudaEventSynchronize(e1);
   float ms; cudaEventElapsedTime(&ms, e0, e1);
   printf("both kernels: %.3f ms for %lld tiles/CTA -> %.2f us per tile (incl. dW2 kernel)\n", ms, (long long)tiles_per_cta, ms * 1e3 / tiles_per_cta);

@@ -57,11 +57,11 @@ _SIGNATURES = {
     'ubn_alpha2weight_backward': [c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_i64, c_p, c_p, c_p, c_p],
     'ubn_segment_sum': [c_p, c_i64, c_p, c_i64, c_i64, c_p, c_p, c_p, c_p],
     'ubn_rgbnet_fwd': [c_p] * 8 + [c_i64] + [c_p] * 4,
-    'ubn_rgbnet_fwd_tc': [c_p] * 8 + [c_i64] + [c_p] * 3 + [c_int, c_p],
+    'ubn_rgbnet_fwd_tc': [c_p] * 8 + [c_i64] + [c_p] * 4 + [c_int, c_p],
     'ubn_rgbnet_bwd_tc_data': [c_p] * 6 + [c_i64] + [c_p] * 3,
     'ubn_rgbnet_bwd_small': [c_p] * 8 + [c_i64] + [c_p] * 7,
     'ubn_rgbnet_bwd': [c_p] * 9 + [c_i64] + [c_p] * 8,
-    'ubn_rgbnet_bwd_tc_fused': [c_p] * 9 + [c_i64] + [c_p] * 8 + [c_int, c_p],
+    'ubn_rgbnet_bwd_tc_fused': [c_p] * 9 + [c_i64] + [c_p] * 9 + [c_int, c_p],
     'ubn_total_variation_add_grad': [c_p, c_p, c_f, c_f, c_f, c_i64, c_i64, c_i64, c_i64, c_i64, c_int, c_p],
     'ubn_adam_upd': [c_p, c_p, c_p, c_p, c_p, c_i64, c_int, c_f, c_f, c_f, c_f, c_int, c_p],
     'ubn_tv_adam_fused': [c_p, c_p, c_p, c_p, c_f, c_f, c_f, c_i64, c_i64, c_i64, c_i64, c_i64, c_int, c_int,

@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(kRows * kHalves, 1) k_shade_fwd_tc(
     const float* __restrict__ feat, const float* __restrict__ vb, const int64_t* __restrict__ ray_id,
     const float* __restrict__ W1k, const float* __restrict__ W2, const float* __restrict__ b2,
     const float* __restrict__ W3, const float* __restrict__ b3, int64_t n_pts, float* __restrict__ rgb,
-    float* __restrict__ h1_out, float* __restrict__ h2_out) {
+    float* __restrict__ h1_out, float* __restrict__ h2_out, uint32_t* __restrict__ h1_mask) {
   constexpr int kThreads = kRows * kHalves;
   constexpr int kChunksPerHalf = (kHidden / 32) / kHalves;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -343,6 +343,15 @@ __global__ void __launch_bounds__(kRows * kHalves, 1) k_shade_fwd_tc(
       }
       // the activation save goes out while the tensor pipe works on this piece
       if (kSave) {
+        if (kPanel && h1_mask) {
+          // ReLU mask of this row's 32-unit piece for the backward's dZ1 = dH1 * [H1 > 0] (bit e = unit 32 c + e): the first
+          // backward launch then reads 16 bytes per sample instead of the 512-byte H1 row.  0 - h is negative exactly when
+          // h > 0 (h = max(x, 0) is +0 or positive), and a funnel shift appends its sign bit: two instructions per unit.
+          uint32_t w = 0;
+#pragma unroll
+          for (int e = 31; e >= 0; --e) w = __funnelshift_l(__float_as_uint(__fsub_rn(0.f, v[e])), w, 1);
+          h1_mask[tile * 512 + c * 128 + rtid] = live ? w : 0u;
+        }
         if (kPanel) {
           float4* dst = reinterpret_cast<float4*>(h1_out + tile * (kRows * kHidden) + (int64_t)(c * 8) * (kRows * 4) + rtid * 4);
 #pragma unroll
@@ -1050,13 +1059,17 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar_smem) {
 }
 __device__ __forceinline__ void row_warps_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
-template <bool kThree, bool kPanel>      // kPanel: h1 / h2 in the panel layout of k_shade_fwd_tc<.., kPanel = true>
+// kPanel: h1 / h2 in the panel layout of k_shade_fwd_tc<.., kPanel = true>.  kMask1 (panel only): dZ1 = dH1 * [H1 > 0] takes the mask
+// bits the forward left in h1_mask instead of loading the H1 row, and the register row that H1 used to occupy in phase 2 receives
+// the NEXT tile's H2 row half a tile ahead of its use (phase trace, profiles/r02_trace_ws_phases.txt: 2.7 k of a tile's 16.6 k
+// cycles were the row warps waiting for H2 at the tile start, another 2.5 k pushing the 32 H1 loads through a busy LSU).
+template <bool kThree, bool kPanel, bool kMask1>
 __global__ void __launch_bounds__(2 * kRows, 1) k_shade_bwd_fused_ws(
     const float* __restrict__ feat, const int64_t* __restrict__ ray_id, const float* __restrict__ W1k,
     const float* __restrict__ W2, const float* __restrict__ W3, const float* __restrict__ rgb,
     const float* __restrict__ h1, const float* __restrict__ h2, const float* __restrict__ g_rgb, int64_t n_pts,
     float* __restrict__ g_feat, float* __restrict__ g_vb, float* __restrict__ gW1k, float* __restrict__ gb2,
-    float* __restrict__ gW3, float* __restrict__ gb3, uint32_t* __restrict__ h2_mask) {
+    float* __restrict__ gW3, float* __restrict__ gb3, uint32_t* __restrict__ h2_mask, const uint32_t* __restrict__ h1_mask) {
   using namespace bf2;
   using bf::cAhi; using bf::cAlo; using bf::cDHf; using bf::cDX; using bf::kIdescN16; using bf::kPanelN16;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -1136,6 +1149,19 @@ __global__ void __launch_bounds__(2 * kRows, 1) k_shade_bwd_fused_ws(
       if (lane == 0) mbar_arrive(full0 + 8 * b);
       ++seq;
     };
+    float4 hrow[kHidden / 4];                                // this thread's H2 row (phase 1) / H1 row (phase 2 without masks)
+    auto load_h2_row = [&](int64_t t) {
+      const int64_t r = t * kRows + rtid;
+      const bool ok = t < tile_end && r < n_pts;
+#pragma unroll
+      for (int q = 0; q < kHidden / 4; ++q) {
+        hrow[q] = make_float4(0, 0, 0, 0);
+        if (ok)
+          hrow[q] = __ldg(reinterpret_cast<const float4*>(kPanel ? h2 + t * (kRows * kHidden) + (int64_t)q * (kRows * 4) + rtid * 4
+                                                                 : h2 + r * kHidden + q * 4));
+      }
+    };
+    if (kMask1) load_h2_row(tile_begin);
     for (int64_t tile = tile_begin; tile < tile_end; ++tile) {
       const int tp = (int)((tile - tile_begin) & 1);
       float* sX = reinterpret_cast<float*>(smem + oX2) + tp * kRows * kFeat;
@@ -1150,20 +1176,22 @@ __global__ void __launch_bounds__(2 * kRows, 1) k_shade_bwd_fused_ws(
       if (warp == 1 && tile + 1 < tile_end && elect_one()) {
         const int64_t r0 = (tile + 1) * kRows;
         const uint32_t nr = (uint32_t)min((int64_t)kRows, n_pts - r0);
-        l2_prefetch(h2 + r0 * kHidden, (kPanel ? (uint32_t)kRows : nr) * kHidden * 4);   // panel layout: rows interleaved, buffer padded
-        l2_prefetch(h1 + r0 * kHidden, (kPanel ? (uint32_t)kRows : nr) * kHidden * 4);
+        if (!kMask1) {
+          l2_prefetch(h2 + r0 * kHidden, (kPanel ? (uint32_t)kRows : nr) * kHidden * 4);   // panel layout: rows interleaved, buffer padded
+          l2_prefetch(h1 + r0 * kHidden, (kPanel ? (uint32_t)kRows : nr) * kHidden * 4);
+        } else if (tile + 2 < tile_end) {     // the H2 row of tile + 1 is fetched into registers during THIS tile: ask L2 two tiles ahead
+          l2_prefetch(h2 + (r0 + kRows) * kHidden, (uint32_t)kRows * kHidden * 4);
+        }
         l2_prefetch(feat + r0 * kFeat, nr * kFeat * 4);
         l2_prefetch(rgb + r0 * 3, (nr * 12) & ~15u);
         l2_prefetch(g_rgb + r0 * 3, (nr * 12) & ~15u);
         l2_prefetch(ray_id + r0, nr * 8);
       }
-      float4 hrow[kHidden / 4];                              // H2 row first: the longest wait of the tile starts at once
+      if (!kMask1) load_h2_row(tile);                        // H2 row first: the longest wait of the tile starts at once
+      uint32_t m1[kHidden / 32] = {0u, 0u, 0u, 0u};          // ReLU mask of my H1 row
+      if (kMask1 && live) {
 #pragma unroll
-      for (int q = 0; q < kHidden / 4; ++q) {
-        hrow[q] = make_float4(0, 0, 0, 0);
-        if (live)
-          hrow[q] = __ldg(reinterpret_cast<const float4*>(kPanel ? h2 + tile * (kRows * kHidden) + (int64_t)q * (kRows * 4) + rtid * 4
-                                                                 : h2 + row * kHidden + q * 4));
+        for (int c = 0; c < kHidden / 32; ++c) m1[c] = __ldg(h1_mask + tile * 512 + c * 128 + rtid);
       }
       {
         int my_ray = -1;
@@ -1232,12 +1260,16 @@ __global__ void __launch_bounds__(2 * kRows, 1) k_shade_bwd_fused_ws(
         WS_T(2 + c);
       }
       WS_T(6);
+      if (kMask1) {
+        load_h2_row(tile + 1);                               // the H2 row is consumed: the next tile's goes into the same registers now
+      } else {
 #pragma unroll
-      for (int q = 0; q < kHidden / 4; ++q) {
-        hrow[q] = make_float4(0, 0, 0, 0);
-        if (live)
-          hrow[q] = __ldg(reinterpret_cast<const float4*>(kPanel ? h1 + tile * (kRows * kHidden) + (int64_t)q * (kRows * 4) + rtid * 4
-                                                                 : h1 + row * kHidden + q * 4));
+        for (int q = 0; q < kHidden / 4; ++q) {
+          hrow[q] = make_float4(0, 0, 0, 0);
+          if (live)
+            hrow[q] = __ldg(reinterpret_cast<const float4*>(kPanel ? h1 + tile * (kRows * kHidden) + (int64_t)q * (kRows * 4) + rtid * 4
+                                                                   : h1 + row * kHidden + q * 4));
+        }
       }
       WS_T(7);
       mbar_wait(bar_addr, phase);
@@ -1252,9 +1284,15 @@ __global__ void __launch_bounds__(2 * kRows, 1) k_shade_bwd_fused_ws(
         float4 q8[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          const float4 hv = hrow[c * 8 + q];
-          q8[q].x = hv.x > 0.f ? v[q * 4] : 0.f; q8[q].y = hv.y > 0.f ? v[q * 4 + 1] : 0.f;
-          q8[q].z = hv.z > 0.f ? v[q * 4 + 2] : 0.f; q8[q].w = hv.w > 0.f ? v[q * 4 + 3] : 0.f;
+          if (kMask1) {
+            const uint32_t mb = m1[c] >> (q * 4);
+            q8[q].x = (mb & 1u) ? v[q * 4] : 0.f; q8[q].y = (mb & 2u) ? v[q * 4 + 1] : 0.f;
+            q8[q].z = (mb & 4u) ? v[q * 4 + 2] : 0.f; q8[q].w = (mb & 8u) ? v[q * 4 + 3] : 0.f;
+          } else {
+            const float4 hv = hrow[c * 8 + q];
+            q8[q].x = hv.x > 0.f ? v[q * 4] : 0.f; q8[q].y = hv.y > 0.f ? v[q * 4 + 1] : 0.f;
+            q8[q].z = hv.z > 0.f ? v[q * 4 + 2] : 0.f; q8[q].w = hv.w > 0.f ? v[q * 4 + 3] : 0.f;
+          }
           const float zs[4] = {q8[q].x, q8[q].y, q8[q].z, q8[q].w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
@@ -1810,7 +1848,7 @@ using namespace ubn;
 
 extern "C" int ubn_rgbnet_fwd_tc(const float* feat, const float* view_bias, const int64_t* ray_id, const float* W1k,
                                  const float* W2, const float* b2, const float* W3, const float* b3, int64_t n_pts,
-                                 float* rgb, float* h1_save, float* h2_save, int single_pass, void* stream) {
+                                 float* rgb, float* h1_save, float* h2_save, uint32_t* h1_mask, int single_pass, void* stream) {
   if (n_pts <= 0) return 0;
   const bool save = h1_save != nullptr && h2_save != nullptr;
   const int64_t n_tiles = (n_pts + tc::kRows - 1) / tc::kRows;
@@ -1823,7 +1861,8 @@ extern "C" int ubn_rgbnet_fwd_tc(const float* feat, const float* view_bias, cons
                                          (int)tc::kSmemBytes);                                                          \
     if (e != cudaSuccess) return finish(e);                                                                             \
     tc::k_shade_fwd_tc<SAVE, THREE, H, P><<<grid, tc::kRows * H, tc::kSmemBytes, st>>>(feat, view_bias, ray_id, W1k, W2, b2, W3, \
-                                                                                        b3, n_pts, rgb, h1_save, h2_save);   \
+                                                                                        b3, n_pts, rgb, h1_save, h2_save,    \
+                                                                                        (SAVE && P) ? h1_mask : nullptr);    \
   } while (0)
 #define UBN_TC_LAUNCH(SAVE, THREE, P)                                \
   do {                                                               \
@@ -1878,8 +1917,8 @@ extern "C" int ubn_rgbnet_bwd_tc_data(const float* W2, const float* W3, const fl
 extern "C" int ubn_rgbnet_bwd_tc_fused(const float* feat, const int64_t* ray_id, const float* W1k, const float* W2, const float* W3,
                                        const float* rgb, const float* h1_save, const float* h2_save, const float* grad_rgb,
                                        int64_t n_pts, float* grad_feat, float* grad_view_bias, float* grad_W1k, float* grad_W2,
-                                       float* grad_b2, float* grad_W3, float* grad_b3, uint32_t* h2_mask_scratch, int single_pass,
-                                       void* stream) {
+                                       float* grad_b2, float* grad_W3, float* grad_b3, uint32_t* h2_mask_scratch,
+                                       const uint32_t* h1_mask, int single_pass, void* stream) {
   if (n_pts <= 0) return 0;
   cudaStream_t st = as_stream(stream);
   {   // dX + every sample reduction except dW2
@@ -1894,21 +1933,21 @@ extern "C" int ubn_rgbnet_bwd_tc_fused(const float* feat, const int64_t* ray_id,
                                                                              n_pts, grad_feat, grad_view_bias, grad_W1k, grad_b2,       \
                                                                              grad_W3, grad_b3);                                         \
     } while (0)
-#define UBN_BFW(T, P)                                                                                                          \
+#define UBN_BFW(T, P, M1)                                                                                                      \
     do {                                                                                                                       \
-      cudaError_t e = cudaFuncSetAttribute(tc::k_shade_bwd_fused_ws<T, P>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+      cudaError_t e = cudaFuncSetAttribute(tc::k_shade_bwd_fused_ws<T, P, M1>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
                                            (int)tc::bf2::kSmemBytesF2);                                                        \
       if (e != cudaSuccess) return finish(e);                                                                                  \
-      tc::k_shade_bwd_fused_ws<T, P><<<grid, 2 * tc::kRows, tc::bf2::kSmemBytesF2, st>>>(feat, ray_id, W1k, W2, W3, rgb, h1_save, h2_save, \
-                                                                                      grad_rgb, n_pts, grad_feat, grad_view_bias,        \
-                                                                                      grad_W1k, grad_b2, grad_W3, grad_b3,               \
-                                                                                      (P) ? h2_mask_scratch : nullptr);                  \
+      tc::k_shade_bwd_fused_ws<T, P, M1><<<grid, 2 * tc::kRows, tc::bf2::kSmemBytesF2, st>>>(                                  \
+          feat, ray_id, W1k, W2, W3, rgb, h1_save, h2_save, grad_rgb, n_pts, grad_feat, grad_view_bias, grad_W1k, grad_b2, grad_W3,   \
+          grad_b3, (P) ? h2_mask_scratch : nullptr, h1_mask);                                                                  \
     } while (0)
     const bool one_pass = (single_pass & 1) != 0, plain = (single_pass & 2) != 0, panel = (single_pass & 4) != 0;
     if (plain && panel) return finish(cudaErrorInvalidValue);       // the 4-warp A/B kernel reads row-major saves only
     if (plain)      { if (one_pass) UBN_BF(false); else UBN_BF(true); }
-    else if (panel) { if (one_pass) UBN_BFW(false, true); else UBN_BFW(true, true); }
-    else            { if (one_pass) UBN_BFW(false, false); else UBN_BFW(true, false); }
+    else if (panel && h1_mask) { if (one_pass) UBN_BFW(false, true, true); else UBN_BFW(true, true, true); }
+    else if (panel)            { if (one_pass) UBN_BFW(false, true, false); else UBN_BFW(true, true, false); }
+    else                       { if (one_pass) UBN_BFW(false, false, false); else UBN_BFW(true, false, false); }
 #undef UBN_BFW
 #undef UBN_BF
     UBN_LAUNCH_CHECK();

@@ -24,6 +24,8 @@ MODE = os.environ.get('UBN_RGBNET_MODE', 'tc3')
 BWD_MODE = os.environ.get('UBN_RGBNET_BWD_MODE', 'fused')
 # dW2 launch of the fused backward: True = rebuild dZ2 from ReLU masks written by the first launch (default), False = re-read H2 (A/B)
 DW2_FROM_MASKS = os.environ.get('UBN_RGBNET_DW2', 'masks') == 'masks'
+# forward leaves the ReLU masks of H1 for the first backward launch (True, default) / that launch loads the H1 rows (False, A/B)
+H1_MASKS = os.environ.get('UBN_RGBNET_H1', 'masks') == 'masks'
 
 
 class _ShadeFn(torch.autograd.Function):
@@ -44,11 +46,13 @@ class _ShadeFn(torch.autograd.Function):
         rows = -(-M // 128) * 128 if panel else M
         h1 = torch.empty(rows, 128, dtype=torch.float32, device=dev) if need_grad else None
         h2 = torch.empty(rows, 128, dtype=torch.float32, device=dev) if need_grad else None
+        # ReLU masks of H1 (16 B per sample): the first backward launch gates dH1 with them instead of loading the 512-byte H1 rows
+        m1 = torch.empty(rows * 4, dtype=torch.int32, device=dev) if (panel and H1_MASKS) else None
         with ops._Guard(feat) as lib:
             with _cabi.timed('rgbnet_fwd'):
                 if MODE in ('tc3', 'tc1', 'tc3w4'):      # 'tc3w4': the 4-warp form of the forward kernel (A/B of the 8-warp default)
                     check(lib.ubn_rgbnet_fwd_tc(ptr(feat), ptr(vb), ptr(ray_id), ptr(W1k), ptr(W2), ptr(b2), ptr(W3), ptr(b3),
-                                                c_i64(M), ptr(rgb), ptr(h1), ptr(h2),
+                                                c_i64(M), ptr(rgb), ptr(h1), ptr(h2), ptr(m1),
                                                 c_int((1 if MODE == 'tc1' else 0) | (2 if MODE == 'tc3w4' else 0) | (4 if panel else 0)),
                                                 stream_of(feat)))
                 else:
@@ -56,6 +60,7 @@ class _ShadeFn(torch.autograd.Function):
                                              c_i64(M), ptr(rgb), ptr(h1), ptr(h2), stream_of(feat)))
         if need_grad:
             ctx.save_for_backward(feat, ray_id, W1k, W2, W3, rgb, h1, h2)
+            ctx.m1 = m1
             ctx.n_rays = vb.shape[0]
             ctx.panel = panel
             ctx.bwd_mode = BWD_MODE
@@ -80,7 +85,7 @@ class _ShadeFn(torch.autograd.Function):
                 with _cabi.timed('rgbnet_bwd'):
                     check(lib.ubn_rgbnet_bwd_tc_fused(ptr(feat), ptr(ray_id), ptr(W1k), ptr(W2), ptr(W3), ptr(rgb), ptr(h1), ptr(h2),
                                                       ptr(g_rgb), c_i64(M), ptr(g_feat), ptr(g_vb), ptr(gW1k), ptr(gW2), ptr(gb2),
-                                                      ptr(gW3), ptr(gb3), ptr(masks), c_int((1 if MODE == 'tc1' else 0) | (2 if bwd_mode == 'fused4' else 0) | (4 if ctx.panel else 0)),
+                                                      ptr(gW3), ptr(gb3), ptr(masks), ptr(ctx.m1 if bwd_mode == 'fused' else None), c_int((1 if MODE == 'tc1' else 0) | (2 if bwd_mode == 'fused4' else 0) | (4 if ctx.panel else 0)),
                                                       stream_of(feat)))
                 return g_feat, g_vb, None, gW1k, gW2, gb2, gW3, gb3, None
             if bwd_mode == 'tc3':
