@@ -32,7 +32,7 @@ extern "C" {
 #pragma GCC visibility push(default)
 #endif
 
-#define UBN_ABI_VERSION 2
+#define UBN_ABI_VERSION 3
 
 /* ---- library introspection ------------------------------------------------------------------ */
 int ubn_abi_version(void);

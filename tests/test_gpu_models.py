@@ -227,8 +227,7 @@ def test_fused_rgbnet_vs_torch(mode, monkeypatch):
     nn.Sequential they replace: forward and every gradient."""
     from unboundednerfpytorch_b200 import models, shade as shade_mod
     monkeypatch.setattr(shade_mod, 'BWD_MODE', {'tcbwd': 'tc3', 'fused': 'fused', 'fusedh2': 'fused', 'fused4': 'fused4'}.get(mode.split('+')[-1], 'simt'))
-    monkeypatch.setattr(shade_mod, 'DW2_FROM_MASKS', not mode.endswith('fusedh2'))      # 'fusedh2': the dW2 launch re-reads H2 and
-    monkeypatch.setattr(shade_mod, 'H1_MASKS', not mode.endswith('fusedh2'))            # launch 1 loads H1 rows (A/B of the ReLU masks)
+    monkeypatch.setattr(shade_mod, 'USE_MASKS', not mode.endswith('fusedh2'))      # 'fusedh2': both backward launches re-read the saves (A/B of the ReLU masks)
     mode = mode.split('+')[0]
     monkeypatch.setattr(shade_mod, 'MODE', mode)
     fwd_tol = dict(rtol=1e-5, atol=1e-6) if mode != 'tc1' else dict(rtol=5e-3, atol=5e-3)

@@ -34,7 +34,7 @@ class UbnMarchCfg(ctypes.Structure):
                 ('use_maskcache', c_i32), ('mask_sz', c_i32 * 3), ('mask_scale', c_f * 3), ('mask_shift', c_f * 3)]
 
 
-ABI_VERSION = 2          # UBN_ABI_VERSION of include/ubnerf_b200.h this binding was written against
+ABI_VERSION = 3          # UBN_ABI_VERSION of include/ubnerf_b200.h this binding was written against
 FLAG_QUERIED, FLAG_LISTED, FLAG_SCANNED, FLAG_KEEP, FLAG_INNER = 1, 2, 4, 8, 16
 
 # name -> argtypes (all functions return int unless listed in _RESTYPE)

@@ -1063,7 +1063,7 @@ __device__ __forceinline__ void row_warps_sync() { asm volatile("bar.sync 1, 128
 // bits the forward left in h1_mask instead of loading the H1 row, and the register row that H1 used to occupy in phase 2 receives
 // the NEXT tile's H2 row half a tile ahead of its use (phase trace, profiles/r02_trace_ws_phases.txt: 2.7 k of a tile's 16.6 k
 // cycles were the row warps waiting for H2 at the tile start, another 2.5 k pushing the 32 H1 loads through a busy LSU).
-template <bool kThree, bool kPanel, bool kMask1>
+template <bool kThree, bool kPanel, bool kMask1>     // kMask1 also means: db2 is summed by the dW2 launch (which rebuilds dZ2 anyway)
 __global__ void __launch_bounds__(2 * kRows, 1) k_shade_bwd_fused_ws(
     const float* __restrict__ feat, const int64_t* __restrict__ ray_id, const float* __restrict__ W1k,
     const float* __restrict__ W2, const float* __restrict__ W3, const float* __restrict__ rgb,
@@ -1386,7 +1386,7 @@ __global__ void __launch_bounds__(2 * kRows, 1) k_shade_bwd_fused_ws(
           const float h = stg[sidx * kStgStride + lane];
           const float4 dz = sDz3[rw * 32 + sidx];
           a0 = fmaf(dz.x, h, a0); a1 = fmaf(dz.y, h, a1); a2 = fmaf(dz.z, h, a2);
-          ab += h > 0.f ? fmaf(dz.z, w3c, fmaf(dz.y, w3b, dz.x * w3a)) : 0.f;
+          if (!kMask1) ab += h > 0.f ? fmaf(dz.z, w3c, fmaf(dz.y, w3b, dz.x * w3a)) : 0.f;
           const uint32_t b = __ballot_sync(0xffffffffu, h > 0.f);      // the ReLU mask of sample sidx over this chunk's 32 units
           if (lane == sidx) my_mask = b;
         }
@@ -1467,7 +1467,7 @@ __global__ void __launch_bounds__(2 * kRows, 1) k_shade_bwd_fused_ws(
   for (int i = tid; i < kHidden * kFeat; i += 2 * kRows)      // sAccW1 is [k][j]; gW1k is [j][k]
     atomicAdd(gW1k + i, sAccW1[(i % kFeat) * kHidden + i / kFeat]);
   for (int i = tid; i < 3 * kHidden; i += 2 * kRows) atomicAdd(gW3 + i, sAccW3[i]);
-  if (tid < kHidden) atomicAdd(gb2 + tid, sAccB2[tid]);
+  if (!kMask1 && tid < kHidden) atomicAdd(gb2 + tid, sAccB2[tid]);
   if (tid < 3) atomicAdd(gb3 + tid, sAccB3[tid]);
   tc_fence_before();
   __syncthreads();
@@ -1668,7 +1668,8 @@ __global__ void __launch_bounds__(dw::kThreadsDW, dw::kCtasPerSM) k_shade_dw2_tc
 template <bool kThree>
 __global__ void __launch_bounds__(dw::kThreadsDW, dw::kCtasPerSM) k_shade_dw2_mask_tc(
     const float* __restrict__ W3, const float* __restrict__ rgb, const float* __restrict__ h1,
-    const uint32_t* __restrict__ h2_mask, const float* __restrict__ g_rgb, int64_t n_pts, float* __restrict__ gW2) {
+    const uint32_t* __restrict__ h2_mask, const float* __restrict__ g_rgb, int64_t n_pts, float* __restrict__ gW2,
+    float* __restrict__ gb2) {
   using namespace dw;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -1705,6 +1706,9 @@ __global__ void __launch_bounds__(dw::kThreadsDW, dw::kCtasPerSM) k_shade_dw2_ma
     w3a[i] = W3[32 * i + lane]; w3b[i] = W3[kHidden + 32 * i + lane]; w3c[i] = W3[2 * kHidden + 32 * i + lane];
   }
   const uint32_t row_off = (uint32_t)warp * kPanelBytes + (uint32_t)lane * 16;      // + i * 512: operand row j = 32 i + lane
+  float accb[4] = {0.f, 0.f, 0.f, 0.f};
+  float* sB2 = reinterpret_cast<float*>(smem + oW3d);        // [128] db2 partials of the CTA (the W3 slot of k_shade_dw2_tc is free here)
+  if (tid < kHidden) sB2[tid] = 0.f;
 
   uint4 pm[4];                 // masks of my four samples, chunk i
   float ph[4][4];              // H1[s0 + t][32 i + lane]
@@ -1791,6 +1795,7 @@ __global__ void __launch_bounds__(dw::kThreadsDW, dw::kCtasPerSM) k_shade_dw2_ma
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
         const float z = ((mw[t] >> lane) & 1u) ? fmaf(d2[t], w3c[i], fmaf(d1[t], w3b[i], d0[t] * w3a[i])) : 0.f;
+        accb[i] += z;                                       // db2[j] = sum over samples of dZ2[s][j]: rebuilt here anyway
         zhp[t] = tf32_hi_bits(z);
         zlp[t] = z - __uint_as_float(zhp[t]);
         hhp[t] = tf32_hi_bits(ph[i][t]);
@@ -1836,8 +1841,11 @@ __global__ void __launch_bounds__(dw::kThreadsDW, dw::kCtasPerSM) k_shade_dw2_ma
       for (int e = 0; e < 32; ++e) atomicAdd(dst + e, v[e]);
     }
   }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) atomicAdd(sB2 + 32 * i + lane, accb[i]);      // the eight sample-quad warps hold partials of the same units
   tc_fence_before();
   __syncthreads();
+  if (tid < kHidden && gb2) atomicAdd(gb2 + tid, sB2[tid]);
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem) : "memory");
 }
 
@@ -1945,7 +1953,7 @@ extern "C" int ubn_rgbnet_bwd_tc_fused(const float* feat, const int64_t* ray_id,
     const bool one_pass = (single_pass & 1) != 0, plain = (single_pass & 2) != 0, panel = (single_pass & 4) != 0;
     if (plain && panel) return finish(cudaErrorInvalidValue);       // the 4-warp A/B kernel reads row-major saves only
     if (plain)      { if (one_pass) UBN_BF(false); else UBN_BF(true); }
-    else if (panel && h1_mask) { if (one_pass) UBN_BFW(false, true, true); else UBN_BFW(true, true, true); }
+    else if (panel && h1_mask && h2_mask_scratch) { if (one_pass) UBN_BFW(false, true, true); else UBN_BFW(true, true, true); }
     else if (panel)            { if (one_pass) UBN_BFW(false, true, false); else UBN_BFW(true, true, false); }
     else                       { if (one_pass) UBN_BFW(false, false, false); else UBN_BFW(true, false, false); }
 #undef UBN_BFW
@@ -1968,10 +1976,10 @@ extern "C" int ubn_rgbnet_bwd_tc_fused(const float* feat, const int64_t* ray_id,
                                            (int)tc::dw::kSmemBytesD);                                                          \
       if (e != cudaSuccess) return finish(e);                                                                                  \
       tc::k_shade_dw2_mask_tc<T><<<grid, tc::dw::kThreadsDW, tc::dw::kSmemBytesD, st>>>(W3, rgb, h1_save, h2_mask_scratch, grad_rgb, n_pts, \
-                                                                                      grad_W2);                                \
+                                                                                      grad_W2, grad_b2);                       \
     } while (0)
     // panel saves + warp-specialised first launch + a mask scratch: dZ2 rebuilt from the ReLU masks (H2 is not read again)
-    const bool from_masks = (single_pass & 4) && !(single_pass & 2) && h2_mask_scratch != nullptr;
+    const bool from_masks = (single_pass & 4) && !(single_pass & 2) && h2_mask_scratch != nullptr && h1_mask != nullptr;
     if (from_masks)           { if (single_pass & 1) UBN_DWM(false); else UBN_DWM(true); }
     else if (single_pass & 4) { if (single_pass & 1) UBN_DW(false, true); else UBN_DW(true, true); }
     else                      { if (single_pass & 1) UBN_DW(false, false); else UBN_DW(true, false); }

@@ -22,10 +22,10 @@ MODE = os.environ.get('UBN_RGBNET_MODE', 'tc3')
 # intermediate in HBM; 'fused4' = the same without warp specialisation (A/B); 'tc3' = the previous three-launch form (dZ1 round trip + CUDA-core kernel for
 # the small gradients; kept for A/B); 'simt' = fp32 FFMA
 BWD_MODE = os.environ.get('UBN_RGBNET_BWD_MODE', 'fused')
-# dW2 launch of the fused backward: True = rebuild dZ2 from ReLU masks written by the first launch (default), False = re-read H2 (A/B)
-DW2_FROM_MASKS = os.environ.get('UBN_RGBNET_DW2', 'masks') == 'masks'
-# forward leaves the ReLU masks of H1 for the first backward launch (True, default) / that launch loads the H1 rows (False, A/B)
-H1_MASKS = os.environ.get('UBN_RGBNET_H1', 'masks') == 'masks'
+# ReLU masks instead of activation re-reads in the fused backward (default on): the forward leaves the masks of H1 (16 B per sample)
+# so that launch 1 gates dH1 without loading the H1 rows; launch 1 ballots the masks of H2 so that the dW2 launch rebuilds dZ2 (and
+# sums db2) without reading H2 a second time.  Off = both launches re-read the saves (A/B; tests cover both).
+USE_MASKS = os.environ.get('UBN_RGBNET_MASKS', '1') == '1'
 
 
 class _ShadeFn(torch.autograd.Function):
@@ -47,7 +47,7 @@ class _ShadeFn(torch.autograd.Function):
         h1 = torch.empty(rows, 128, dtype=torch.float32, device=dev) if need_grad else None
         h2 = torch.empty(rows, 128, dtype=torch.float32, device=dev) if need_grad else None
         # ReLU masks of H1 (16 B per sample): the first backward launch gates dH1 with them instead of loading the 512-byte H1 rows
-        m1 = torch.empty(rows * 4, dtype=torch.int32, device=dev) if (panel and H1_MASKS) else None
+        m1 = torch.empty(rows * 4, dtype=torch.int32, device=dev) if (panel and USE_MASKS) else None
         with ops._Guard(feat) as lib:
             with _cabi.timed('rgbnet_fwd'):
                 if MODE in ('tc3', 'tc1', 'tc3w4'):      # 'tc3w4': the 4-warp form of the forward kernel (A/B of the 8-warp default)
@@ -81,7 +81,7 @@ class _ShadeFn(torch.autograd.Function):
             if bwd_mode in ('fused', 'fused4'):          # 'fused4': the same kernel without warp specialisation (A/B)
                 # panel saves: launch 1 leaves the ReLU masks of H2 (2 KB per 128-sample tile) in this scratch and the dW2 launch
                 # rebuilds dZ2 from them instead of reading the 512 B/sample of H2 again
-                masks = torch.empty(-(-M // 128) * 512, dtype=torch.int32, device=dev) if (ctx.panel and DW2_FROM_MASKS) else None
+                masks = torch.empty(-(-M // 128) * 512, dtype=torch.int32, device=dev) if (ctx.panel and ctx.m1 is not None) else None
                 with _cabi.timed('rgbnet_bwd'):
                     check(lib.ubn_rgbnet_bwd_tc_fused(ptr(feat), ptr(ray_id), ptr(W1k), ptr(W2), ptr(W3), ptr(rgb), ptr(h1), ptr(h2),
                                                       ptr(g_rgb), c_i64(M), ptr(g_feat), ptr(g_vb), ptr(gW1k), ptr(gW2), ptr(gb2),
