@@ -27,7 +27,7 @@ def test_header_symbols_exported():
 def test_abi_version_and_counters():
     from unboundednerfpytorch_b200 import _cabi
     lib = _cabi.load()
-    assert lib.ubn_abi_version() == 2
+    assert lib.ubn_abi_version() == _cabi.ABI_VERSION == 3
     _cabi.reset_launch_count()
     assert _cabi.launch_count() == 0
 
