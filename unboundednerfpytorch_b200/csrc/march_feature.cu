@@ -419,7 +419,8 @@ __global__ void __launch_bounds__(32 * kMarchWarps, 6) k_march_feature_bwd_slab(
       // one vector reduction (the scatter is bound by the number of L2 reduction sectors, ncu: 0.38 sector per slice and clock
       // with every other unit below 60 %).  The cell index is warp-uniform after the shuffle, so the test costs no divergence.
       // (Handing the shared FACE of two neighbouring cells over the same way -- four of eight corners, one xor-shuffle per float --
-      // was measured slower: 3.38 vs 2.97 ms.  Half-populated reduction instructions do not halve the cost of an instruction.)
+      // was measured slower: 3.38 vs 2.97 ms.  Half-populated reduction instructions do not halve the cost of an instruction.  So was
+      // a run-length merge carried across groups and chunks: 3.49 ms -- the open run serialises the group's reductions.)
       int vj[kGroup];
       float4 val[kGroup];
 #pragma unroll
