@@ -640,9 +640,19 @@ def main():
     def kernel_roof(name, kms):
         if name in abytes:
             ach = abytes[name] * units[name] / (kms * 1e-3) / 1e9
-            return {'kernel': name, 'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
-                    'traffic': load_traffic(name) if args.workload == 'truck' else None, 'traffic_source': traffic_src, 'kernel_ms': kms,
-                    'algorithmic_bytes_per_sample': abytes[name], 'samples_per_launch': units[name], 'peak_source': peak_src}
+            traffic = load_traffic(name) if args.workload == 'truck' else None
+            out = {'kernel': name, 'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
+                   'traffic': traffic, 'traffic_source': traffic_src, 'kernel_ms': kms,
+                   'algorithmic_bytes_per_sample': abytes[name], 'samples_per_launch': units[name], 'peak_source': peak_src}
+            if traffic:
+                # the physical side of the same launch: DRAM bytes of the committed ncu capture over this run's kernel time
+                out['dram_achieved'] = traffic / (kms * 1e-3) / 1e9
+                out['dram_frac'] = out['dram_achieved'] / peak
+            if out['frac'] > 1.0:
+                out['note'] = ('frac > 1: SURVEY 8d counts every corner record of every sample as HBM traffic; neighbouring samples share '
+                               'corners in L1 / L2 (and the scatter merges equal cells in registers), so the kernel moves fewer DRAM bytes '
+                               'than the model -- dram_frac is the physical utilisation')
+            return out
         ach = aflops[name] * units[name] / (kms * 1e-3) / 1e12
         return {'kernel': name, 'bound': 'tensor', 'achieved': ach, 'peak': tpeak, 'unit': 'TFLOP/s', 'frac': ach / tpeak,
                 'traffic': load_traffic(name) if args.workload == 'truck' else None, 'traffic_source': traffic_src, 'kernel_ms': kms,

@@ -238,7 +238,13 @@ __global__ void __launch_bounds__(32 * kMarchWarps) k_march_feature(
 // ------------------------------------------------------------------------------------------------
 constexpr int kMaxChunks = 128;   // S <= 4096
 
-template <int kP>
+// kRuns (kP > 0 only): the scatter is a SECOND phase with lane = a run of consecutive samples of the ray.  Phase 1 (reverse scan,
+// lane = sample of a 32-sample chunk) parks the per-sample density gradients in shared memory; in phase 2 every lane walks its
+// ceil(S / 32) consecutive samples slab by slab and keeps the cell it is in open in registers (cell index + its 8 corner sums):
+// samples that stay in the cell -- 40 % of the steps in slab 0 and the lowest sin / cos slabs at half-voxel spacing -- are added in
+// registers, and a cell leaves as four pair reductions only when the ray moves on.  The scatter is bound by the count of L2
+// reduction requests (ncu: 226 M requests, 0.32 sector / slice / clock, issue 21 %), so fewer requests is the only lever.
+template <int kP, bool kRuns>
 __global__ void __launch_bounds__(32 * kMarchWarps) k_march_density_bwd(
     const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float* __restrict__ t_table,
     GridView g /* data = grad grid */, MarchParams p, int64_t n_rays, const float* __restrict__ density,
@@ -248,12 +254,15 @@ __global__ void __launch_bounds__(32 * kMarchWarps) k_march_density_bwd(
     const float* __restrict__ g_last, float* __restrict__ grad_grid) {
   __shared__ int s_cnt[kMarchWarps][kMaxChunks];
   __shared__ __align__(16) float2 s_pair[kMarchWarps][32];
+  extern __shared__ float s_gd_all[];                      // kRuns: [kMarchWarps][S + 33] parked gradients, index s + s / L
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int64_t ray = (int64_t)blockIdx.x * kMarchWarps + w;
   if (ray >= n_rays) return;
   const Ray r = load_ray(rays_o + 3 * ray, rays_d + 3 * ray, p);
   const int S = p.S;
   const int n_chunks = (S + 31) / 32;
+  const int L = n_chunks;                                  // kRuns: consecutive samples per lane in phase 2 (= ceil(S / 32))
+  float* s_gd = s_gd_all + w * (S + 33);
 
   // exclusive prefix of KEEP counts per chunk -> compact index of every kept sample
   int run = 0;
@@ -302,15 +311,21 @@ __global__ void __launch_bounds__(32 * kMarchWarps) k_march_density_bwd(
       }
       __syncwarp();
     }
-    if (!(f & UBN_FLAG_QUERIED)) continue;
-    const float a = alpha[i];
-    float ga = (keep && g_alpha) ? g_alpha[ci] : 0.f;
-    if (f & UBN_FLAG_SCANNED) ga += (float)(gw * T[i] - my_back / (1 - a + 1e-10));
-    const float d = density[i];
-    float gd = (keep && g_density) ? g_density[ci] : 0.f;
-    if (ga != 0.f) {
-      const float e = expf(d + p.shift);
-      gd += (float)(fmin((double)e, 1e10) * powf(1 + e, -p.interval - 1) * p.interval * ga);
+    float gd = 0.f;
+    if (f & UBN_FLAG_QUERIED) {
+      const float a = alpha[i];
+      float ga = (keep && g_alpha) ? g_alpha[ci] : 0.f;
+      if (f & UBN_FLAG_SCANNED) ga += (float)(gw * T[i] - my_back / (1 - a + 1e-10));
+      const float d = density[i];
+      gd = (keep && g_density) ? g_density[ci] : 0.f;
+      if (ga != 0.f) {
+        const float e = expf(d + p.shift);
+        gd += (float)(fmin((double)e, 1e10) * powf(1 + e, -p.interval - 1) * p.interval * ga);
+      }
+    }
+    if (kRuns) {                                           // park it (already divided by the slab count) for phase 2
+      if (valid) s_gd[s + s / L] = slab_mean_scale(gd, g.P);
+      continue;
     }
     if (gd == 0.f) continue;
     // scatter into the density grid gradient (adjoint of grid_density)
@@ -331,6 +346,75 @@ __global__ void __launch_bounds__(32 * kMarchWarps) k_march_density_bwd(
       if (g.sv == 1) trilerp1_scatter_pairs(grad_grid + sl * g.sp, g.X, g.Y, g.Z, cx, cy, cz, gd);
       else trilerp1_scatter(grad_grid + sl * g.sp, g.sv, g.X, g.Y, g.Z, cx, cy, cz, gd);
     }
+  }
+  if (!kRuns || kP <= 0) return;
+
+  // ---- phase 2: lane = samples lane * L .. lane * L + L - 1, one pass per frequency (slab 0 | sin, cos of 2^k x) ----
+  __syncwarp();
+  constexpr int kPP = kP > 0 ? kP : 1;
+  const int dY = g.Z, dX = g.Y * g.Z;
+  struct Run { int v; float c[8]; };
+  auto flush = [&](const Run& run, float* slab) {          // the four (x, y) edges of the open cell as pair reductions
+    float* rec = slab + run.v;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float* a = rec + (e >> 1) * dX + (e & 1) * dY;
+      const float w0 = run.c[2 * e], w1 = run.c[2 * e + 1];
+      const bool odd = (reinterpret_cast<uintptr_t>(a) & 4) != 0;
+      red_add_v2(a - (odd ? 1 : 0), odd ? 0.f : w0, odd ? w0 : w1);
+      if (odd) atomicAdd(a + 1, w1);
+    }
+  };
+  auto visit = [&](Run& run, float* slab, float cx, float cy, float cz, float gd) {
+    const CellR c = make_cell(cx, cy, cz, g.X, g.Y, g.Z);
+    float wgt[8];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {                          // same products as grid_density_scatter_fast: ((wz * wy) * wx) * gd
+      const int bx = e >> 1, by = e & 1;
+      const float wy = by ? c.fy : 1.f - c.fy, wx = bx ? c.fx : 1.f - c.fx;
+      wgt[2 * e] = (((1.f - c.fz) * wy) * wx) * gd;
+      wgt[2 * e + 1] = ((c.fz * wy) * wx) * gd;
+    }
+    if (c.v == run.v) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) run.c[q] += wgt[q];
+    } else {
+      if (run.v >= 0) flush(run, slab);
+      run.v = c.v;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) run.c[q] = wgt[q];
+    }
+  };
+#pragma unroll 1
+  for (int k = 0; k <= (kPP - 1) / 2; ++k) {
+    Run ra, rb;
+    ra.v = -1; rb.v = -1;
+    float* slab_a = grad_grid + (int64_t)(k == 0 ? 0 : 2 * k - 1) * g.sp;
+    float* slab_b = grad_grid + (int64_t)(2 * k) * g.sp;
+    const float m = (float)(1 << (k > 0 ? k - 1 : 0));
+    for (int i = 0; i < L; ++i) {
+      const int s = lane * L + i;
+      if (s >= S) break;
+      const float gd = s_gd[s + lane];
+      if (gd == 0.f) continue;
+      float x, y, z;
+      sample_point(r, t_table[s], p, x, y, z);
+      const float nx = norm_coord(x, g.mn[0], g.len[0]);
+      const float ny = norm_coord(y, g.mn[1], g.len[1]);
+      const float nz = norm_coord(z, g.mn[2], g.len[2]);
+      if (k == 0) {
+        visit(ra, slab_a, src_index(nx, g.X), src_index(ny, g.Y), src_index(nz, g.Z), gd);
+      } else {
+        float sx, cx, sy, cy, sz, cz;
+        sincosf(__fmul_rn(m, nx), &sx, &cx);
+        sincosf(__fmul_rn(m, ny), &sy, &cy);
+        sincosf(__fmul_rn(m, nz), &sz, &cz);
+        visit(ra, slab_a, src_index(sx, g.X), src_index(sy, g.Y), src_index(sz, g.Z), gd);
+        visit(rb, slab_b, src_index(cx, g.X), src_index(cy, g.Y), src_index(cz, g.Z), gd);
+      }
+    }
+    if (ra.v >= 0) flush(ra, slab_a);
+    if (rb.v >= 0) flush(rb, slab_b);
   }
 }
 
@@ -353,6 +437,8 @@ int march_feature_v2(bool backward, const float* rays_o, const float* rays_d, co
 
 void set_feature_kernel(int v);
 int get_feature_kernel();
+static int g_density_scatter = 1;      // 1 = run-merging two-phase scatter (default), 0 = per-sample scatter
+static int get_density_scatter() { return g_density_scatter; }
 
 static bool feature_grid_ok(const GridView& g) {
   return g.sc == 1 && g.sv == g.C && (g.C == 4 || g.C == 8 || g.C == 12 || g.C == 16) && g.P <= 16 &&
@@ -371,6 +457,13 @@ int ubn_set_feature_kernel(int variant) {
   return 0;
 }
 int ubn_get_feature_kernel(void) { return get_feature_kernel(); }
+
+int ubn_set_density_scatter(int variant) {
+  if (variant < 0 || variant > 1) return finish(cudaErrorInvalidValue);
+  g_density_scatter = variant;
+  return 0;
+}
+int ubn_get_density_scatter(void) { return g_density_scatter; }
 
 int ubn_march_density_fwd(const float* rays_o, const float* rays_d, const float* t_table, const float* density_grid,
                           const UbnGridDesc* density_desc, const uint8_t* mask_world, const UbnMarchCfg* cfg,
@@ -452,10 +545,20 @@ int ubn_march_density_bwd(const float* rays_o, const float* rays_d, const float*
   if (g.C != 1) return finish(cudaErrorInvalidValue);
   const MarchParams p = make_params(cfg);
   if (p.S > 32 * kMaxChunks) return finish(cudaErrorInvalidValue);
-#define UBN_DBWD(P)                                                                                              \
-  k_march_density_bwd<P><<<blocks_for(n_rays, kMarchWarps), 32 * kMarchWarps, 0, as_stream(stream)>>>(           \
-      rays_o, rays_d, t_table, g, p, n_rays, density, alpha, weight, T, flags, alphainv_last, offsets, g_weight,  \
-      g_alpha, g_density, g_last, grad_density_grid)
+  // run-merging scatter (two-phase kernel) by default; ubn_set_density_scatter(0) selects the per-sample scatter (A/B, tests)
+  const size_t smem_runs = sizeof(float) * kMarchWarps * (size_t)(p.S + 33);
+  const bool runs = get_density_scatter() == 1 && smem_runs <= 40 * 1024;
+#define UBN_DBWD(P)                                                                                                  \
+  do {                                                                                                               \
+    if (runs && (P) > 0)                                                                                             \
+      k_march_density_bwd<P, true><<<blocks_for(n_rays, kMarchWarps), 32 * kMarchWarps, smem_runs, as_stream(stream)>>>( \
+          rays_o, rays_d, t_table, g, p, n_rays, density, alpha, weight, T, flags, alphainv_last, offsets, g_weight,  \
+          g_alpha, g_density, g_last, grad_density_grid);                                                            \
+    else                                                                                                             \
+      k_march_density_bwd<P, false><<<blocks_for(n_rays, kMarchWarps), 32 * kMarchWarps, 0, as_stream(stream)>>>(    \
+          rays_o, rays_d, t_table, g, p, n_rays, density, alpha, weight, T, flags, alphainv_last, offsets, g_weight,  \
+          g_alpha, g_density, g_last, grad_density_grid);                                                            \
+  } while (0)
   switch (density_fast_slabs(g)) {
     case 1: UBN_DBWD(1); break;
     case 3: UBN_DBWD(3); break;
