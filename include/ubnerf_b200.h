@@ -316,6 +316,12 @@ int ubn_exclusive_scan_i32(const int32_t* in, int64_t n, int64_t* offsets, int64
  * launches.  Returns cudaErrorInvalidValue for other values. */
 int ubn_set_feature_kernel(int variant);
 int ubn_get_feature_kernel(void);
+/* How ubn_march_density_bwd scatters into the density-grid gradient (contiguous single-channel grids): 1 (the default) = two-phase
+ * kernel whose second phase walks runs of consecutive samples per lane and merges the contributions of samples that stay in the same
+ * cell before they leave as pair reductions; 0 = every sample scatters its own 8 corners.  Same sums up to fp32 addition order.
+ * Process-wide like ubn_set_feature_kernel. */
+int ubn_set_density_scatter(int variant);
+int ubn_get_density_scatter(void);
 
 /* Pass B: for every survivor (flags bit1), in (ray, step) order at offsets[ray]+rank: recompute the
  * contracted point, query the feature grid (k0), and emit the compacted per-survivor records. */

@@ -490,6 +490,7 @@ def model_forward(flavor, p, rays_o, rays_d, viewdirs, stepsize, bg=1, rand_bkgd
     else:
         ray_pts, inner_mask, tt = ray_pts.reshape(-1, 3), inner_mask.reshape(-1), tt.reshape(-1)
     density = dgrid(ray_pts)
+    density_q, pts_q = density, ray_pts          # every queried sample, before the threshold compactions (kept for the fp64 yardsticks)
     alpha = _Raw2Alpha.apply(density.contiguous(), float(p['act_shift']), interval)
     if thres > 0:
         mask = alpha > thres
@@ -524,6 +525,7 @@ def model_forward(flavor, p, rays_o, rays_d, viewdirs, stepsize, bg=1, rand_bkgd
             ret['depth'] = torch.zeros(N, device=dev).index_add_(0, ray_id, weights * s)
     if keep_intermediates:      # for the fp64 re-evaluation of the colour branch in tests/parity_at_size.py
         ret['_ray_pts'], ret['_k0'] = ray_pts.detach(), k0.detach()
+        ret['_density_q'], ret['_pts_q'] = density_q, pts_q.detach()     # graph tensor: d loss / d raw density of all queried samples
     return ret
 
 

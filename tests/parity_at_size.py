@@ -127,6 +127,23 @@ def colour_branch_fp64(flavor, p, ref, vd, target, n_rays, chunk=1 << 19):
     return grads, n_amb
 
 
+def density_scatter_fp64(p, pts_q, g_density_q, chunk=1 << 20):
+    """fp64 evaluation of the density-grid scatter: the adjoint of the reference's grid read (F.grid_sample over the slabs + mean)
+    applied to the reference run's own per-sample gradients d loss / d raw_density.  The fp32 implementations (ATen's atomicAdd
+    scatter in the reference, the vector reductions here) differ from each other only by the order -- and, in this library, the
+    in-register merging -- of fp32 additions; this is what both are judged against."""
+    from oracle import cpu_ref
+    dev = pts_q.device
+    kg = torch.zeros_like(p['density_grid'], dtype=torch.float64).requires_grad_(True)
+    gmin = torch.tensor([-1., -1., -1.], device=dev, dtype=torch.float64) - p['bg_len']
+    gmax = torch.tensor([1., 1., 1.], device=dev, dtype=torch.float64) + p['bg_len']
+    for lo in range(0, pts_q.shape[0], chunk):
+        sl = slice(lo, min(lo + chunk, pts_q.shape[0]))
+        d = cpu_ref.fourier_grid_forward(kg, pts_q[sl].double(), gmin, gmax, p['freq_density'])
+        (d.reshape(-1) * g_density_q[sl].double().reshape(-1)).sum().backward()
+    return kg.grad
+
+
 def _vs_truth(a, b, truth):
     """Deviation of ours (a) and of the reference GPU path (b) from the fp64 yardstick, relative to max |truth|."""
     t = truth.reshape(b.shape)
@@ -170,7 +187,9 @@ def compare(name, dev, n_rays=8192, backward=True, ext=None, truth=True):
     if backward:
         ours.zero_grad(set_to_none=True)
         bench.step_loss(ret, target, n_rays).backward()
-        bench.step_loss(ref, target, n_rays).backward()
+        loss_ref = bench.step_loss(ref, target, n_rays)
+        g_dq = torch.autograd.grad(loss_ref, ref['_density_q'], retain_graph=True)[0] if truth else None
+        loss_ref.backward()
         pairs = [('density.grid', ours.density.grid.grad, p['density_grid'].grad), ('k0.grid', ours.k0.grid.grad, p['k0_grid'].grad)]
         names = {'W1': ours.rgbnet[0].weight, 'b1': ours.rgbnet[0].bias, 'W2': ours.rgbnet[2][0].weight,
                  'b2': ours.rgbnet[2][0].bias, 'W3': ours.rgbnet[3].weight, 'b3': ours.rgbnet[3].bias}
@@ -182,6 +201,8 @@ def compare(name, dev, n_rays=8192, backward=True, ext=None, truth=True):
             for nm, a, b in pairs:
                 if nm in grads64:
                     out['truth ' + nm] = _vs_truth(a, b, grads64[nm])
+            out['truth density.grid'] = _vs_truth(pairs[0][1], pairs[0][2], density_scatter_fp64(p, ref['_pts_q'], g_dq))
+            del g_dq
         # the reference against ITSELF: its grid scatters are fp32 atomicAdds (ATen grid_sampler_3d_backward), so two runs of the
         # reference differ by the summation order alone -- the floor any other implementation can be asked to reach
         first = {nm: b.detach().clone() for nm, a, b in pairs[:2]}

@@ -274,6 +274,39 @@ def test_fused_rgbnet_vs_torch(mode, monkeypatch):
                 assert_close(a, b, rtol=2e-5, atol=(2e-6 if nm == 'k0' else 1e-5) * scale + 1e-9, what=f'grad {nm} M={M}')
 
 
+@pytest.mark.parametrize('flavor,F_,thres', [('fouriergrid', 4, 0.0), ('fouriergrid', 2, 1e-4), ('dcvgo', 0, 1e-4)])
+def test_density_scatter_variants_agree(flavor, F_, thres):
+    """ubn_set_density_scatter 0 / 1: per-sample scatter vs the two-phase run-merging scatter of the fused march backward -- the same
+    addends, merged before or inside the L2 reductions: density-grid gradients agree to fp32 summation order, everything else
+    is untouched."""
+    from unboundednerfpytorch_b200 import ops
+    m, _ = _fresh_model(flavor, 40, F_, thres, 13, dens_mean=5.0 if thres else 0.0, dens_std=3.0 if thres else 1.0)
+    m = m.to(DEV)
+    ro, rd, vd = seeded_rays(700, 17, DEV)
+    rk = dict(near=0., far=1e9, bg=1, rand_bkgd=False, stepsize=0.5, render_depth=True)
+    grads = []
+    try:
+        for variant in (0, 1):
+            ops.set_density_scatter(variant)
+            assert ops.get_density_scatter() == variant
+            m.zero_grad(set_to_none=True)
+            ret = m(ro, rd, vd, global_step=None, **rk)
+            (ret['rgb_marched'].sum() + 1e-2 * ret['depth'].sum() + 0.1 * ret['raw_rgb'].pow(2).sum()).backward()
+            grads.append({k: p.grad.detach().clone() for k, p in m.named_parameters() if p.grad is not None})
+    finally:
+        ops.set_density_scatter(1)
+    a, b = grads
+    assert a.keys() == b.keys()
+    scale = float(a['density.grid'].abs().max())
+    assert scale > 0
+    assert float((a['density.grid'] - b['density.grid']).abs().max()) <= 1e-5 * scale
+    assert float((a['density.grid'].double().sum() - b['density.grid'].double().sum()).abs()) <= 1e-5 * float(a['density.grid'].double().abs().sum())
+    for k in a:
+        if k != 'density.grid':
+            s_ = float(a[k].abs().max()) + 1e-30
+            assert float((a[k] - b[k]).abs().max()) <= 1e-5 * s_, k
+
+
 def test_rgbnet_dw2_long_sample_sum_vs_fp64():
     """dW2 = sum over ALL samples of dZ2^T H1 is a split-K tensor-core GEMM.  tcgen05 adds into its fp32 accumulator with
     truncation, so one accumulator chain per CTA over hundreds of 32-sample rounds carries a bias that grows linearly with the

@@ -94,6 +94,8 @@ _SIGNATURES = {
                                   c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
     'ubn_set_feature_kernel': [c_int],
     'ubn_get_feature_kernel': [],
+    'ubn_set_density_scatter': [c_int],
+    'ubn_get_density_scatter': [],
     'ubn_march_feature_bwd': [c_p, c_p, c_p, ctypes.POINTER(UbnGridDesc), ctypes.POINTER(UbnMarchCfg), c_i64,
                               c_p, c_p, c_p, c_p, c_p],
     'ubn_march_density_bwd': [c_p, c_p, c_p, ctypes.POINTER(UbnGridDesc), ctypes.POINTER(UbnMarchCfg), c_i64,

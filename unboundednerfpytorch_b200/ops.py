@@ -443,6 +443,18 @@ def get_feature_kernel():
     return int(load().ubn_get_feature_kernel())
 
 
+def set_density_scatter(variant):
+    """Density-grid scatter of the fused march backward: 1 = run-merging two-phase kernel (default), 0 = per-sample scatter
+    (ubn_set_density_scatter).  Process-wide."""
+    from ._cabi import load
+    check(load().ubn_set_density_scatter(c_int(int(variant))))
+
+
+def get_density_scatter():
+    from ._cabi import load
+    return int(load().ubn_get_density_scatter())
+
+
 def cumdist_thres(dist, thres):
     _chk(dist, 'dist')
     mask = torch.empty(dist.shape, dtype=torch.bool, device=dist.device)
