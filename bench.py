@@ -402,7 +402,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference', 'reference-gpu'])
     ap.add_argument('--workload', default='truck', choices=['truck', 'bicycle', 'garden', 'missionbay'])
     ap.add_argument('--cpu-rays', type=int, default=1024, help='upper bound of the ray sample of the CPU legs (shrunk to fit the time budget)')
-    ap.add_argument('--feature-kernel', type=int, default=None, choices=[0, 1, 2, 3, 4, 5],
+    ap.add_argument('--feature-kernel', type=int, default=None, choices=[0, 1, 2, 3, 4, 5, 6],
                     help='A/B: pass-B kernel family (0 warp-cooperative, 1 lane-per-sample forward, 2 forward + backward); default = library default')
     ap.add_argument('--tma', action='store_true', help='A/B (render workloads): TMA-staged brick feature read instead of the gather kernel')
     ap.add_argument('--no-tma', action='store_true', help='(default; kept for old scripts)')

@@ -311,7 +311,7 @@ int ubn_exclusive_scan_i32(const int32_t* in, int64_t n, int64_t* offsets, int64
 /* Which pass-B kernel family serves 12-channel channels-last feature grids: 0 = warp-cooperative (lane = corner x channel quad),
  * 1 = lane-per-sample for the forward, 2 = lane-per-sample for forward and backward, 3 (the default) / 4 / 5 = lane-per-sample
  * forward + slab-major cooperative scatter (FourierGrid k0 grids: one slab of the gradient live in L2 at a time), each slab swept in 1 / 2 / 4
- * x-ranges.  Same results to fp32 rounding (the
+ * x-ranges; 6 = as 3 with the gather that gives a sample three lanes (one per channel quad), 8 samples per instruction.  Same results to fp32 rounding (the
  * lane-per-sample forward is bit-identical to F.grid_sample(...).mean(0)); process-wide, not thread-safe against concurrent
  * launches.  Returns cudaErrorInvalidValue for other values. */
 int ubn_set_feature_kernel(int variant);

@@ -506,7 +506,7 @@ def test_feature_kernel_families_agree(flavor, F_, thres):
     rk = dict(near=0., far=1e9, bg=1, rand_bkgd=False, stepsize=0.5, render_depth=True)
     outs, grads = [], []
     try:
-        for variant in (0, 1, 2, 3, 4, 5):
+        for variant in (0, 1, 2, 3, 4, 5, 6):
             ops.set_feature_kernel(variant)
             assert ops.get_feature_kernel() == variant
             m.zero_grad(set_to_none=True)
@@ -531,13 +531,14 @@ def test_feature_kernel_families_agree(flavor, F_, thres):
     # bit parity of the lane-per-sample forward with what the REFERENCE computes: F.grid_sample over the slabs + .mean(0) in torch
     # (oracle.cpu_ref.fourier_grid_forward on CUDA tensors = FourierGrid_grid.py:60-78 / grid.py:50-61 verbatim)
     from oracle import cpu_ref
-    with torch.no_grad():
-        ops.set_feature_kernel(3)
-        try:
-            (w, last, alpha, dens, k0, ray_id, step_id, t, inner), _ = m._march(ro, rd, 0.5)
-        finally:
-            ops.set_feature_kernel(3)
-        pts, _, _ = m._sample_dense(ro, rd, 0.5)
-        want = cpu_ref.fourier_grid_forward(m.k0.grid.detach().contiguous(), pts[ray_id, step_id], m.xyz_min, m.xyz_max,
-                                            F_ if flavor == 'fouriergrid' else 0)
-    assert torch.equal(k0, want), f'{int((k0 != want).sum())} of {k0.numel()} feature values differ from grid_sample + mean'
+    for variant in (3, 6):          # both lane-per-sample gathers (32 samples x 1 lane, 8 samples x 3 quad lanes per instruction)
+        with torch.no_grad():
+            ops.set_feature_kernel(variant)
+            try:
+                (w, last, alpha, dens, k0, ray_id, step_id, t, inner), _ = m._march(ro, rd, 0.5)
+            finally:
+                ops.set_feature_kernel(3)
+            pts, _, _ = m._sample_dense(ro, rd, 0.5)
+            want = cpu_ref.fourier_grid_forward(m.k0.grid.detach().contiguous(), pts[ray_id, step_id], m.xyz_min, m.xyz_max,
+                                                F_ if flavor == 'fouriergrid' else 0)
+        assert torch.equal(k0, want), f'variant {variant}: {int((k0 != want).sum())} of {k0.numel()} feature values differ from grid_sample + mean'

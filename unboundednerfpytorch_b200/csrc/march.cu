@@ -452,7 +452,7 @@ using namespace ubn;
 extern "C" {
 
 int ubn_set_feature_kernel(int variant) {
-  if (variant < 0 || variant > 5) return finish(cudaErrorInvalidValue);
+  if (variant < 0 || variant > 6) return finish(cudaErrorInvalidValue);
   set_feature_kernel(variant);
   return 0;
 }

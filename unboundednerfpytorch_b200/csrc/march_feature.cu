@@ -324,6 +324,121 @@ __global__ void __launch_bounds__(32 * kMarchWarps, 4) k_march_feature_v3(
   }
 }
 
+// =====================================================================================================================
+// Fourth generation of the gather: EIGHT samples per instruction, three lanes per sample (lane = sample j of 8, channel quad q).
+// The lane-per-sample kernel above is bound by L1 wavefronts (ncu: l1tex 68 %, issue 21 %): one LDG.128 of its 24 per slab sends
+// 32 lanes to up to 32 different 128-byte lines.  Here the three quad lanes of a sample read the 48 contiguous bytes of ONE
+// corner record, so an instruction touches 8 records instead of 32 and a slab costs 8 load instructions per 8 samples.  The
+// accumulation stays inside the lane (4 channels of its quad over the 8 corners in ATen's order, slabs in torch-CUDA's mean
+// order), so there is still no cross-lane reduction and the features keep their bits.  The cells are computed once per sample
+// (lane = sample, as before) and handed to the (j, q) lanes by 4 shuffles per (pass, slab).
+// =====================================================================================================================
+template <int kP>
+__global__ void __launch_bounds__(32 * kMarchWarps, 4) k_march_feature_v4(
+    const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float* __restrict__ t_table,
+    GridView g, MarchParams p, int64_t n_rays, const uint8_t* __restrict__ flags,
+    const int64_t* __restrict__ offsets, const float* __restrict__ density, const float* __restrict__ alpha,
+    const float* __restrict__ weight, float* __restrict__ feat, float* __restrict__ o_density, float* __restrict__ o_alpha,
+    float* __restrict__ o_weight, int64_t* __restrict__ o_ray_id, int64_t* __restrict__ o_step_id,
+    float* __restrict__ o_t, uint8_t* __restrict__ o_inner) {
+  constexpr int kC = 12;
+  const int lane = threadIdx.x & 31;
+  const int64_t ray = (int64_t)blockIdx.x * kMarchWarps + (threadIdx.x >> 5);
+  if (ray >= n_rays) return;
+  int64_t out_base = offsets[ray];
+  const int64_t out_end = offsets[ray + 1];
+  if (out_base == out_end) return;
+  const Ray r = load_ray(rays_o + 3 * ray, rays_d + 3 * ray, p);
+  const int S = p.S;
+  const int dY = g.Z * kC, dX = g.Y * g.Z * kC;
+  const int jq = lane >> 2, q = lane & 3;                 // sample of the pass, channel quad (q == 3: idle lane)
+
+  for (int base = 0; base < S && out_base < out_end; base += 32) {
+    const int s = base + lane;
+    const uint8_t f = (s < S) ? flags[ray * S + s] : 0;
+    const bool keep = (f & UBN_FLAG_KEEP) != 0;
+    const unsigned km = __ballot_sync(0xffffffffu, keep);
+    if (km == 0) continue;
+    const int n_here = __popc(km);
+    const int rank = __popc(km & ((1u << lane) - 1));
+    float nx = 0.f, ny = 0.f, nz = 0.f;
+    if (keep) {
+      float x, y, z;
+      const float t = t_table[s];
+      sample_point(r, t, p, x, y, z);
+      nx = norm_coord(x, g.mn[0], g.len[0]);
+      ny = norm_coord(y, g.mn[1], g.len[1]);
+      nz = norm_coord(z, g.mn[2], g.len[2]);
+      const int64_t o = out_base + rank;
+      const int64_t i = ray * S + s;
+      o_density[o] = density[i];
+      o_alpha[o] = alpha[i];
+      o_weight[o] = weight[i];
+      o_ray_id[o] = ray;
+      o_step_id[o] = s;
+      o_t[o] = t;
+      o_inner[o] = (f & UBN_FLAG_INNER) ? 1 : 0;
+    }
+    if (km != 0xffffffffu) {            // compact: lane i takes the i-th survivor of the chunk
+      const int src = __fns(km, 0, lane + 1) & 31;
+      nx = __shfl_sync(0xffffffffu, nx, src);
+      ny = __shfl_sync(0xffffffffu, ny, src);
+      nz = __shfl_sync(0xffffffffu, nz, src);
+    }
+    // the kP cells of MY sample (lane = i-th survivor), one sincosf per axis and frequency
+    CellR cell[kP];
+    for_each_slab<kP>(g, nx, ny, nz, [&](int sl, float cx, float cy, float cz) { cell[sl] = make_cell(cx, cy, cz, g.X, g.Y, g.Z); });
+#pragma unroll 1
+    for (int pass = 0; pass < 4; ++pass) {
+      if (pass * 8 >= n_here) break;                      // warp-uniform
+      const int j = pass * 8 + jq;
+      const bool act = q < 3 && j < n_here;
+      float4 tot = make_float4(0, 0, 0, 0), grp = make_float4(0, 0, 0, 0);
+#pragma unroll
+      for (int a = 0; a < 4 && a < kP; ++a) {
+#pragma unroll
+        for (int sl = a; sl < kP; sl += 4) {
+          const int v = __shfl_sync(0xffffffffu, cell[sl].v, j);
+          const float fx = __shfl_sync(0xffffffffu, cell[sl].fx, j);
+          const float fy = __shfl_sync(0xffffffffu, cell[sl].fy, j);
+          const float fz = __shfl_sync(0xffffffffu, cell[sl].fz, j);
+          float4 val = make_float4(0, 0, 0, 0);
+          if (act) {
+            const float* rec = g.data + sl * g.sp + (int64_t)v * kC + q * 4;
+#pragma unroll
+            for (int corner = 0; corner < 8; ++corner) {          // tnw, tne, tsw, tse, bnw, bne, bsw, bse (z fastest)
+              const int bx = corner >> 2, by = (corner >> 1) & 1, bz = corner & 1;
+              const float wgt = ((bz ? fz : 1.f - fz) * (by ? fy : 1.f - fy)) * (bx ? fx : 1.f - fx);
+              const float4 c4 = __ldg(reinterpret_cast<const float4*>(rec + bx * dX + by * dY + bz * kC));
+              val.x = fmaf(c4.x, wgt, val.x); val.y = fmaf(c4.y, wgt, val.y); val.z = fmaf(c4.z, wgt, val.z); val.w = fmaf(c4.w, wgt, val.w);
+            }
+          }
+          if (sl == a) { grp.x = __fadd_rn(0.f, val.x); grp.y = __fadd_rn(0.f, val.y); grp.z = __fadd_rn(0.f, val.z); grp.w = __fadd_rn(0.f, val.w); }
+          else { grp.x = __fadd_rn(grp.x, val.x); grp.y = __fadd_rn(grp.y, val.y); grp.z = __fadd_rn(grp.z, val.z); grp.w = __fadd_rn(grp.w, val.w); }
+        }
+        if (a == 0) tot = grp;
+        else { tot.x = __fadd_rn(tot.x, grp.x); tot.y = __fadd_rn(tot.y, grp.y); tot.z = __fadd_rn(tot.z, grp.z); tot.w = __fadd_rn(tot.w, grp.w); }
+      }
+      if (act)
+        *reinterpret_cast<float4*>(feat + (out_base + j) * kC + q * 4) =
+            make_float4(slab_mean_scale(tot.x, kP), slab_mean_scale(tot.y, kP), slab_mean_scale(tot.z, kP), slab_mean_scale(tot.w, kP));
+    }
+    out_base += n_here;
+  }
+}
+
+template <int kP>
+static int launch_v4(const float* rays_o, const float* rays_d, const float* t_table, const GridView& g, const MarchParams& p,
+                     int64_t n_rays, const uint8_t* flags, const int64_t* offsets, const float* density, const float* alpha,
+                     const float* weight, float* feat, float* o_density, float* o_alpha, float* o_weight, int64_t* o_ray_id,
+                     int64_t* o_step_id, float* o_t, uint8_t* o_inner, cudaStream_t st) {
+  k_march_feature_v4<kP><<<blocks_for(n_rays, kMarchWarps), 32 * kMarchWarps, 0, st>>>(rays_o, rays_d, t_table, g, p, n_rays, flags, offsets,
+                                                                                        density, alpha, weight, feat, o_density, o_alpha,
+                                                                                        o_weight, o_ray_id, o_step_id, o_t, o_inner);
+  UBN_LAUNCH_CHECK();
+  return 0;
+}
+
 template <int kP>
 static int launch_v3(bool backward, const float* rays_o, const float* rays_d, const float* t_table, const GridView& g,
                      const MarchParams& p, int64_t n_rays, const uint8_t* flags, const int64_t* offsets,
@@ -480,13 +595,23 @@ int march_feature_v2(bool backward, const float* rays_o, const float* rays_d, co
                      uint8_t* o_inner, cudaStream_t st) {
   if (g.X < 2 || g.Y < 2 || g.Z < 2) return -1;
   if ((int64_t)g.X * g.Y * g.Z * g.C >= (1ll << 31)) return -1;   // 32-bit voxel offsets inside a slab
-  if (backward && g_feature_kernel >= 3 && g.P > 1) {     // 3 / 4 / 5: slab-major scatter, each slab swept in 1 / 2 / 4 x-ranges
-    const int n_split = 1 << (g_feature_kernel - 3);
+  if (backward && g_feature_kernel >= 3 && g.P > 1) {     // 3 / 4 / 5: slab-major scatter, each slab swept in 1 / 2 / 4 x-ranges; 6: as 3
+    const int n_split = g_feature_kernel == 6 ? 1 : 1 << (g_feature_kernel - 3);
     switch (g.P) {
       case 3: return launch_bwd_slab<3>(rays_o, rays_d, t_table, g, p, n_rays, flags, offsets, feat, grad_grid, n_split, st);
       case 5: return launch_bwd_slab<5>(rays_o, rays_d, t_table, g, p, n_rays, flags, offsets, feat, grad_grid, n_split, st);
       case 7: return launch_bwd_slab<7>(rays_o, rays_d, t_table, g, p, n_rays, flags, offsets, feat, grad_grid, n_split, st);
       case 9: return launch_bwd_slab<9>(rays_o, rays_d, t_table, g, p, n_rays, flags, offsets, feat, grad_grid, n_split, st);
+      default: break;
+    }
+  }
+  if (g.C == 12 && g_feature_kernel == 6 && !backward) {      // 8 samples x 3 channel quads per instruction
+    switch (g.P) {
+      case 1: return launch_v4<1>(rays_o, rays_d, t_table, g, p, n_rays, flags, offsets, density, alpha, weight, feat, o_density, o_alpha, o_weight, o_ray_id, o_step_id, o_t, o_inner, st);
+      case 3: return launch_v4<3>(rays_o, rays_d, t_table, g, p, n_rays, flags, offsets, density, alpha, weight, feat, o_density, o_alpha, o_weight, o_ray_id, o_step_id, o_t, o_inner, st);
+      case 5: return launch_v4<5>(rays_o, rays_d, t_table, g, p, n_rays, flags, offsets, density, alpha, weight, feat, o_density, o_alpha, o_weight, o_ray_id, o_step_id, o_t, o_inner, st);
+      case 7: return launch_v4<7>(rays_o, rays_d, t_table, g, p, n_rays, flags, offsets, density, alpha, weight, feat, o_density, o_alpha, o_weight, o_ray_id, o_step_id, o_t, o_inner, st);
+      case 9: return launch_v4<9>(rays_o, rays_d, t_table, g, p, n_rays, flags, offsets, density, alpha, weight, feat, o_density, o_alpha, o_weight, o_ray_id, o_step_id, o_t, o_inner, st);
       default: break;
     }
   }

@@ -431,8 +431,8 @@ def maskout_near_cam_(slab, cams, near_clip, fill=-100.0):
 
 def set_feature_kernel(variant):
     """Pass-B kernel family for 12-channel channels-last feature grids: 0 = warp-cooperative, 1 = lane-per-sample forward,
-    2 = lane-per-sample forward + backward, 3 / 4 / 5 = lane-per-sample forward + slab-major scatter with each slab swept in 1 / 2 / 4 x-ranges
-    (ubn_set_feature_kernel).
+    2 = lane-per-sample forward + backward, 3 / 4 / 5 = lane-per-sample forward + slab-major scatter with each slab swept in 1 / 2 / 4 x-ranges,
+    6 = as 3 with the 8-samples-per-instruction gather (ubn_set_feature_kernel).
     Process-wide."""
     from ._cabi import load
     check(load().ubn_set_feature_kernel(c_int(int(variant))))
