@@ -535,7 +535,8 @@ __global__ void __launch_bounds__(32 * kMarchWarps, 6) k_march_feature_bwd_slab(
       // with every other unit below 60 %).  The cell index is warp-uniform after the shuffle, so the test costs no divergence.
       // (Handing the shared FACE of two neighbouring cells over the same way -- four of eight corners, one xor-shuffle per float --
       // was measured slower: 3.38 vs 2.97 ms.  Half-populated reduction instructions do not halve the cost of an instruction.  So was
-      // a run-length merge carried across groups and chunks: 3.49 ms -- the open run serialises the group's reductions.)
+      // a run-length merge carried across groups and chunks: 3.49 ms -- the open run serialises the group's reductions; and so was
+      // pairing neighbours 16 positions apart with alternating issue: 3.08 ms -- fewer merges, and nothing gained from spacing.)
       int vj[kGroup];
       float4 val[kGroup];
 #pragma unroll
@@ -605,7 +606,9 @@ int march_feature_v2(bool backward, const float* rays_o, const float* rays_d, co
       default: break;
     }
   }
-  if (g.C == 12 && g_feature_kernel == 6 && !backward) {      // 8 samples x 3 channel quads per instruction
+  // 8 samples x 3 channel quads per instruction: explicitly (6), and by default (3) for single-slab grids, where it measured 0.204 vs
+  // 0.255 ms (bicycle); on the 9-slab FourierGrid the shuffled cells cost more than the wavefronts save (1.84 vs 1.55 ms)
+  if (g.C == 12 && !backward && (g_feature_kernel == 6 || (g_feature_kernel == 3 && g.P == 1))) {
     switch (g.P) {
       case 1: return launch_v4<1>(rays_o, rays_d, t_table, g, p, n_rays, flags, offsets, density, alpha, weight, feat, o_density, o_alpha, o_weight, o_ray_id, o_step_id, o_t, o_inner, st);
       case 3: return launch_v4<3>(rays_o, rays_d, t_table, g, p, n_rays, flags, offsets, density, alpha, weight, feat, o_density, o_alpha, o_weight, o_ray_id, o_step_id, o_t, o_inner, st);
