@@ -375,7 +375,9 @@ int ubn_rgbnet_fwd(const float* feat, const float* view_bias, const int64_t* ray
  * bit 2: h1_save / h2_save are written in the PANEL layout [ceil(n_pts/128)][32 column quads][128 rows][4 floats] -- coalesced
  * for the row-per-thread kernels on both sides -- and must hold ceil(n_pts/128)*128 rows; only ubn_rgbnet_bwd_tc_fused called
  * with the same bit reads that layout.  h1_mask (bit 2 only; may be NULL): ceil(n_pts/128)*512 uint32 that receive the ReLU masks
- * of H1, [tile][32-unit chunk][row], bit = unit -- ubn_rgbnet_bwd_tc_fused then gates dH1 with them instead of loading H1 rows. */
+ * of H1, [tile][32-unit chunk][row], bit = unit -- ubn_rgbnet_bwd_tc_fused then gates dH1 with them instead of loading H1 rows;
+ * with masks, h1_save itself is written TRANSPOSED ([tile][32 sample quads][128 units][4 samples]) for its one remaining reader,
+ * the dW2 launch of ubn_rgbnet_bwd_tc_fused (pass the same h1_mask there). */
 int ubn_rgbnet_fwd_tc(const float* feat, const float* view_bias, const int64_t* ray_id, const float* W1k, const float* W2,
                       const float* b2, const float* W3, const float* b3, int64_t n_pts, float* rgb, float* h1_save,
                       float* h2_save, uint32_t* h1_mask, int single_pass, void* stream);

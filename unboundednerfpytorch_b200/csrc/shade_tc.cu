@@ -351,8 +351,25 @@ __global__ void __launch_bounds__(kRows * kHalves, 1) k_shade_fwd_tc(
 #pragma unroll
           for (int e = 31; e >= 0; --e) w = __funnelshift_l(__float_as_uint(__fsub_rn(0.f, v[e])), w, 1);
           h1_mask[tile * 512 + c * 128 + rtid] = live ? w : 0u;
-        }
-        if (kPanel) {
+          // With the masks the VALUES of H1 have one reader left, the dW2 launch, whose operand rows are (unit k, four consecutive
+          // samples).  So H1 is saved TRANSPOSED, [tile][32 sample quads][128 units][4 samples]: the warp turns its 32 x 32 piece
+          // through its 4.5 KB staging tile and every store instruction writes 512 contiguous bytes; the dW2 launch then fetches an
+          // operand row with ONE coalesced 16-byte load instead of four scattered 4-byte loads (which were half of the L1 wavefronts
+          // of that kernel: l1tex 89 % busy, ncu).
+          float* stg = reinterpret_cast<float*>(smem + oStg + warp * kStgBytesPerWarp);
+          const int ln = tid & 31;
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float4*>(stg + ln * kStgStride + q * 4) = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+          __syncwarp();
+          float* dstT = h1_out + tile * (kRows * kHidden) + (int64_t)(8 * (warp & 3)) * (kHidden * 4) + (c * 32 + ln) * 4;
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float4*>(dstT + q * (kHidden * 4)) =
+                make_float4(stg[(4 * q) * kStgStride + ln], stg[(4 * q + 1) * kStgStride + ln], stg[(4 * q + 2) * kStgStride + ln],
+                            stg[(4 * q + 3) * kStgStride + ln]);
+          __syncwarp();
+        } else if (kPanel) {
           float4* dst = reinterpret_cast<float4*>(h1_out + tile * (kRows * kHidden) + (int64_t)(c * 8) * (kRows * 4) + rtid * 4);
 #pragma unroll
           for (int q = 0; q < 8; ++q) dst[q * kRows] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
@@ -1722,10 +1739,10 @@ __global__ void __launch_bounds__(dw::kThreadsDW, dw::kCtasPerSM) k_shade_dw2_ma
     for (int i = 0; i < 4; ++i) {
       pm[i] = make_uint4(0, 0, 0, 0);
       if (on) pm[i] = __ldg(reinterpret_cast<const uint4*>(h2_mask + tile * 512 + i * 128 + r_in));
-#pragma unroll
-      for (int t = 0; t < 4; ++t)
-        ph[i][t] = on ? __ldg(h1 + tile * (int64_t)(kRows * kHidden) + (int64_t)(8 * i + (lane >> 2)) * (kRows * 4) + (r_in + t) * 4 + (lane & 3))
-                      : 0.f;
+      // H1 transposed by the forward: [tile][sample quad][unit][4 samples] -> my operand row is one 16-byte load
+      float4 h4 = make_float4(0, 0, 0, 0);
+      if (on) h4 = __ldg(reinterpret_cast<const float4*>(h1 + tile * (int64_t)(kRows * kHidden) + (int64_t)(r_in >> 2) * (kHidden * 4) + (32 * i + lane) * 4));
+      ph[i][0] = h4.x; ph[i][1] = h4.y; ph[i][2] = h4.z; ph[i][3] = h4.w;
     }
     if (on && row0 + 4 <= n_pts) {
       const float4* o = reinterpret_cast<const float4*>(rgb + row0 * 3);
