@@ -402,6 +402,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference', 'reference-gpu'])
     ap.add_argument('--workload', default='truck', choices=['truck', 'bicycle', 'garden', 'missionbay'])
     ap.add_argument('--cpu-rays', type=int, default=1024, help='upper bound of the ray sample of the CPU legs (shrunk to fit the time budget)')
+    ap.add_argument('--no-reduced-precision', action='store_true', help='skip the labelled TF32x1 rgbnet line')
     ap.add_argument('--feature-kernel', type=int, default=None, choices=[0, 1, 2, 3, 4, 5, 6],
                     help='A/B: pass-B kernel family (0 warp-cooperative, 1 lane-per-sample forward, 2 forward + backward); default = library default')
     ap.add_argument('--tma', action='store_true', help='A/B (render workloads): TMA-staged brick feature read instead of the gather kernel')
@@ -617,6 +618,20 @@ def main():
     fwd_only(0)
     ms_fwd = timed_region(fwd_only, args.steps)
 
+    # second, clearly labelled line: the same step with the rgbnet at ONE TF32 pass per product (the opt-in reduced-precision
+    # training mode, UBN_RGBNET_MODE=tc1; ~1e-3 relative error inside the MLP, gated at |PSNR delta| <= 0.01 dB by
+    # tests/test_gpu_models.py).  Not the headline: the headline computes at fp32 grade (3xTF32), the reference's own precision.
+    ms_tc1 = None
+    if world == 1 and not args.no_reduced_precision:
+        from unboundednerfpytorch_b200 import shade as _shade
+        mode0, _shade.MODE = _shade.MODE, 'tc1'
+        try:
+            for i in range(3):
+                dev_step(i)
+            ms_tc1 = timed_region(dev_step, args.steps)
+        finally:
+            _shade.MODE = mode0
+
     if rank != 0:
         if world > 1:
             torch.distributed.destroy_process_group()
@@ -681,6 +696,12 @@ def main():
                         'mode': tail_mode},
             'fwd_only': {'value': samples_per_step / (ms_fwd / args.steps * 1e-3), 'unit': 'ray-samples/s',
                          'ms_per_step': ms_fwd / args.steps}}
+    if ms_tc1 is not None:
+        line['reduced_precision_tf32x1'] = {
+            'ms_per_step': ms_tc1 / args.steps, 'value': samples_per_step / (ms_tc1 / args.steps * 1e-3), 'unit': 'ray-samples/s',
+            'dtype': 'tf32 x1 inside the rgbnet (fp32 everywhere else)',
+            'note': 'NOT the headline: same step with one TF32 pass per product in the rgbnet forward and backward (opt-in training mode, '
+                    'PSNR delta gated <= 0.01 dB in tests/test_gpu_models.py); the headline value computes at fp32 grade (3xTF32)'}
     if world == 1 and not args.no_reference_gpu:
         # the real competitor: the reference's GPU path on this same B200 -- its algorithm op by op with its own CUDA
         # extension (oracle/_ref) + ATen grid_sample + cuBLAS; a baseline leg like cpu_baseline, outside every timed region above

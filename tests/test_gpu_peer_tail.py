@@ -145,11 +145,19 @@ def _rank_main(rank, world, port, q):
             wopt.step()
             tail.step(m.tv_terms(1e-3, 1e-4, dense))
             torch.cuda.synchronize()
-            for (ka, va), (kb, vb) in zip(want.state_dict().items(), m.state_dict().items()):
-                if ka == 'k0.grid':
-                    assert torch.equal(va, vb), f'rank {rank}: {ka} differs after step {it}: {(va - vb).abs().max().item():.3e}'
-                elif ka.startswith(('density.grid', 'rgbnet')):       # classic route: NCCL mean (summation order not ours)
-                    assert torch.allclose(va, vb, rtol=1e-5, atol=1e-6), f'rank {rank}: {ka} differs after step {it}'
+            sd_want, sd_ours = want.state_dict(), m.state_dict()
+            # the peer kernel sums the ranks' gradients in rank order, like `mean` above: exact
+            assert torch.equal(sd_want['k0.grid'], sd_ours['k0.grid']), \
+                f"rank {rank}: k0.grid differs after step {it}: {(sd_want['k0.grid'] - sd_ours['k0.grid']).abs().max().item():.3e}"
+            for ka, va in sd_want.items():
+                if ka.startswith(('density.grid', 'rgbnet')):
+                    # classic route: NCCL's mean all-reduce.  For more than two ranks its summation order is not ours, and Adam's
+                    # m / sqrt(v) turns a last-bit difference of a near-zero mean gradient into a full +-lr step: judged by the
+                    # fraction of elements that moved apart, not element by element
+                    vb = sd_ours[ka]
+                    bad = ((va - vb).abs() > 1e-6 + 1e-5 * va.abs()).float().mean().item()
+                    assert bad <= (0.0 if world == 2 else 2e-3), \
+                        f'rank {rank}: {ka}: {bad:.2e} of the elements differ after step {it} (max {(va - vb).abs().max().item():.3e})'
         tail.gather_moments()
         full = opt.state[m.k0.grid]['exp_avg']
         assert torch.equal(full, wopt.state[want.k0.grid]['exp_avg']), 'gathered exp_avg differs'
@@ -162,16 +170,20 @@ def _rank_main(rank, world, port, q):
             dist.destroy_process_group()
 
 
-@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs (gpurun --gpus 2)')
-def test_peer_tail_two_ranks_nccl_match_single_process_mean_gradient_step():
+@pytest.mark.parametrize('world', [2, 4, 8])
+def test_peer_tail_ranks_nccl_match_single_process_mean_gradient_step(world):
+    """world NCCL ranks (one per GPU of the box; skipped where the box has fewer) fed DIFFERENT synthetic gradients must end up with
+    exactly the parameters and moments a single process computes from the mean gradient: k_tv_adam_peer<2 / 4 / 8>."""
+    if torch.cuda.device_count() < world:
+        pytest.skip(f'needs {world} GPUs (gpurun --gpus {world})')
     import torch.multiprocessing as mp
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_rank_main, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_rank_main, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=600) for _ in procs]
     for p in procs:
         p.join(timeout=120)
-    assert sorted(res) == [(0, 'ok'), (1, 'ok')], res
+    assert sorted(res) == [(r, 'ok') for r in range(world)], res
