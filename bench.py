@@ -696,6 +696,12 @@ def main():
                         'mode': tail_mode},
             'fwd_only': {'value': samples_per_step / (ms_fwd / args.steps * 1e-3), 'unit': 'ray-samples/s',
                          'ms_per_step': ms_fwd / args.steps}}
+    # north_star's target is stated on the fused sample + interpolate + composite forward: SURVEY 8d forward bytes of the whole render
+    # pass (density read for every nominal sample + feature read for the survivors) over its measured time, against the HBM peak
+    fwd_bytes = (abytes['march_density_fwd'] * N_RAYS * N_SAMPLES + abytes['march_feature_fwd'] * M) * world
+    fwd_gbs = fwd_bytes / (ms_fwd / args.steps * 1e-3) / 1e9
+    line['fwd_only'].update({'algorithmic_bytes': fwd_bytes, 'achieved_gbs': fwd_gbs, 'frac_of_hbm_peak': fwd_gbs / (peak * world),
+                             'what': 'whole forward / render pass (march + rgbnet + composite, no backward)'})
     if ms_tc1 is not None:
         line['reduced_precision_tf32x1'] = {
             'ms_per_step': ms_tc1 / args.steps, 'value': samples_per_step / (ms_tc1 / args.steps * 1e-3), 'unit': 'ray-samples/s',
