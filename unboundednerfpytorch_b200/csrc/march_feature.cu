@@ -582,14 +582,19 @@ static int launch_bwd_slab(const float* rays_o, const float* rays_d, const float
   return 0;
 }
 
-// 0 = warp-cooperative kernels (v2), 1 = lane-per-sample (v3) for the forward, 2 = for forward and backward, 3 (default) = lane-per-sample forward + SLAB-MAJOR cooperative
-// scatter (k_march_feature_bwd_slab).  Set
-// through ubn_set_feature_kernel (tests exercise every value).  The scatter stays cooperative: one warp instruction issues the 24
-// vector reductions of a sample into 8 x 48 contiguous bytes, whereas lane-per-sample reductions hit 32 unrelated records per
-// instruction and serialise in the L2 atomic units.
-// Measured on the truck workload (8192 x 512, 9 slabs; profiles/README.md): forward 3.94 ms cooperative -> 1.55 ms lane-per-sample;
-// backward 4.20 ms cooperative, 7.48 ms lane-per-sample, 3.76 ms slab-major (4.40 / 5.34 ms with each slab swept in 2 / 4 x-ranges:
-// the repeated preamble costs more than the L2 hits return).  Default: lane-per-sample forward + slab-major scatter.
+// Pass-B kernel family, set through ubn_set_feature_kernel (the GPU tests exercise every value):
+//   0  warp-cooperative gather and scatter (k_march_feature_v2)
+//   1  lane-per-sample gather (k_march_feature_v3) + cooperative scatter
+//   2  lane-per-sample gather and scatter
+//   3  (default) lane-per-sample gather -- the 8-samples-per-instruction k_march_feature_v4 for single-slab grids -- + SLAB-MAJOR
+//      cooperative scatter with the equal-cell merge (k_march_feature_bwd_slab)
+//   4 / 5  as 3 with every slab swept in 2 / 4 x-ranges
+//   6  as 3 with k_march_feature_v4 for every slab count
+// The scatter stays cooperative: one warp instruction issues the 24 vector reductions of a sample into 8 x 48 contiguous bytes,
+// whereas lane-per-sample reductions hit 32 unrelated records per instruction.
+// Measured on the truck workload (8192 x 512, 9 slabs; profiles/README.md): gather 3.94 ms (0) -> 1.55 ms (1, 3) / 1.84 ms (6);
+// scatter 4.20 ms (0, 1), 7.48 ms (2), 3.76 ms slab-major -> 2.97 ms with the merge -> 2.88 ms at 8 resident blocks (3),
+// 4.40 / 5.34 ms (4 / 5: the repeated preamble costs more than the L2 hits return).  Bicycle (1 slab): gather 0.255 (v3) -> 0.204 ms (v4).
 static int g_feature_kernel = 3;
 void set_feature_kernel(int v) { g_feature_kernel = v; }
 int get_feature_kernel() { return g_feature_kernel; }
